@@ -1,0 +1,612 @@
+// engine.cu -- GPU context, plane driver and the compute half of the C ABI.
+//
+// The plane driver re-creates w2xc::convertWithModels (reference src/convertRoutine.cpp:21-51),
+// convertWithModelsBasic (:53-82) and convertWithModelsBlockSplit (:84-169) on top of the layer
+// kernels: replicate-pad by nModel, run the layers, crop nModel.  A plane the reference would
+// block-split is by default processed whole (every output pixel still sees exactly the operands
+// and the operation order it sees inside its reference block, so the result is bit-identical);
+// W2X_WALK_BLOCKS walks the reference's blocks literally.
+//
+// There is no CPU fallback anywhere in this file: without an sm_100 device every compute entry
+// point fails with W2X_ERR_NO_DEVICE.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "w2x_internal.h"
+
+using namespace w2x;
+
+namespace {
+
+struct DevModel {                       // device-resident copy of one model
+    std::vector<float *> w;             // per layer [Cout][Cin][9] fp32
+    std::vector<float *> b;             // per layer [Cout] fp32  ((float)bias, src/modelHandler.cpp:147)
+    std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
+    std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
+};
+
+struct TimedSpan { int layer; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct w2x_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int cc_major = 0, cc_minor = 0;
+    int engine = W2X_ENGINE_AUTO;
+    int walk = W2X_WALK_FUSED;
+    int desc_mode = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    size_t scratch_limit = (size_t)16 << 30;
+    w2x_log_fn log = nullptr;
+    void *log_user = nullptr;
+    uint64_t launches = 0;
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    std::vector<std::string> layer_kernel;
+    std::map<uint64_t, DevModel> models;
+    // scratch
+    void *buf[2] = {nullptr, nullptr};
+    size_t buf_bytes[2] = {0, 0};
+    float *pad_buf = nullptr;
+    size_t pad_bytes = 0;
+    float *io_buf[2] = {nullptr, nullptr};   // device staging for the host-buffer entry points
+    size_t io_bytes[2] = {0, 0};
+    bool tc_ready = false;
+};
+
+namespace {
+
+#define CU_CHECK(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(W2X_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                        cudaGetErrorString(e__));                                                   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure(void **p, size_t *have, size_t need) {
+    if (*have >= need) return W2X_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(W2X_ERR_NOMEM, "cudaMalloc of %zu bytes failed (%s)", need, cudaGetErrorString(e));
+    }
+    *have = need;
+    return W2X_OK;
+}
+
+int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
+    auto it = ctx->models.find(m->uid);
+    if (it != ctx->models.end()) {
+        *out = &it->second;
+        return W2X_OK;
+    }
+    DevModel dm;
+    const size_t n = m->layers.size();
+    dm.w.assign(n, nullptr);
+    dm.b.assign(n, nullptr);
+    dm.pack.assign(n, nullptr);
+    dm.out_scale.assign(n, 1.f);
+    for (size_t i = 0; i < n; i++) {
+        const Layer &L = m->layers[i];
+        CU_CHECK(cudaMalloc(&dm.w[i], L.w.size() * sizeof(float)));
+        CU_CHECK(cudaMemcpyAsync(dm.w[i], L.w.data(), L.w.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<float> bf(L.b.size());
+        for (size_t k = 0; k < bf.size(); k++) bf[k] = static_cast<float>(L.b[k]);
+        CU_CHECK(cudaMalloc(&dm.b[i], bf.size() * sizeof(float)));
+        CU_CHECK(cudaMemcpyAsync(dm.b[i], bf.data(), bf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CU_CHECK(cudaStreamSynchronize(ctx->stream));   // bf goes out of scope
+        const TcPack &P = m->tc[i];
+        if (!P.bytes.empty()) {
+            CU_CHECK(cudaMalloc(&dm.pack[i], P.bytes.size() * 2));
+            CU_CHECK(cudaMemcpyAsync(dm.pack[i], P.bytes.data(), P.bytes.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+            dm.out_scale[i] = 1.0f / (P.wscale * tc::ACT_SCALE);
+        }
+    }
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    auto res = ctx->models.emplace(m->uid, std::move(dm));
+    *out = &res.first->second;
+    return W2X_OK;
+}
+
+cudaEvent_t take_event(w2x_ctx *ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LayerTimer {   // brackets one layer launch with events when timing is on
+    w2x_ctx *ctx;
+    TimedSpan span{};
+    bool on;
+    LayerTimer(w2x_ctx *c, int layer) : ctx(c), on(c->timing) {
+        if (on) {
+            span.layer = layer;
+            span.e0 = take_event(c);
+            span.e1 = take_event(c);
+            cudaEventRecord(span.e0, c->stream);
+        }
+    }
+    ~LayerTimer() {
+        if (on) {
+            cudaEventRecord(span.e1, ctx->stream);
+            ctx->spans.push_back(span);
+        }
+    }
+};
+
+void note_kernel(w2x_ctx *ctx, int layer, const char *name) {
+    if ((int)ctx->layer_kernel.size() <= layer) ctx->layer_kernel.resize((size_t)layer + 1);
+    ctx->layer_kernel[(size_t)layer] = name;
+}
+
+void logf(w2x_ctx *ctx, const char *fmt, int a, int b = 0) {
+    if (!ctx->log) return;
+    char line[128];
+    snprintf(line, sizeof line, fmt, a, b);
+    ctx->log(line, ctx->log_user);
+}
+
+int pick_engine(w2x_ctx *ctx, const w2x_model *m) {
+    int e = ctx->engine;
+    if (e == W2X_ENGINE_AUTO) e = m->tc_eligible ? W2X_ENGINE_TC : W2X_ENGINE_FP32;
+    if (e == W2X_ENGINE_TC && !m->tc_eligible) {
+        fail(W2X_ERR_UNSUPPORTED, "tcgen05 engine needs a 1->{32,64,128}...->1 layer chain");
+        return -1;
+    }
+    return e;
+}
+
+int ensure_tc(w2x_ctx *ctx) {
+    if (ctx->tc_ready) return W2X_OK;
+    CU_CHECK(tc::init_kernels());
+    ctx->tc_ready = true;
+    return W2X_OK;
+}
+
+// ---- convertWithModelsBasic on an already padded ROI ------------------------------------------
+// src: pw x ph fp32 region (row stride src_stride floats) that already contains the n-pixel ring.
+// dst: receives the (pw-2n) x (ph-2n) interior.
+int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const float *src, long src_stride, int pw,
+              int ph, float *dst, long dst_stride) {
+    const int n = (int)m->layers.size();
+    if (pw - 2 * n < 1 || ph - 2 * n < 1) return fail(W2X_ERR_ARG, "plane smaller than the model's receptive ring");
+    int maxc = 1;
+    for (auto &L : m->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
+    if (engine == W2X_ENGINE_FP32) {
+        const size_t need = (size_t)maxc * pw * ph * sizeof(float);
+        for (int i = 0; i < 2; i++) {
+            int rc = ensure(&ctx->buf[i], &ctx->buf_bytes[i], need);
+            if (rc) return rc;
+        }
+        float *cur = static_cast<float *>(ctx->buf[0]), *nxt = static_cast<float *>(ctx->buf[1]);
+        CU_CHECK(launch_copy2d(src, src_stride, cur, pw, pw, ph, ctx->stream));   // ROI -> dense plane
+        ctx->launches++;
+        for (int li = 0; li < n; li++) {
+            const Layer &L = m->layers[(size_t)li];
+            logf(ctx, "Iteration #%d...", li + 1);                                 // src/convertRoutine.cpp:67
+            {
+                LayerTimer t(ctx, li);
+                CU_CHECK(launch_conv3x3_fp32(cur, nxt, dm->w[(size_t)li], dm->b[(size_t)li], L.n_in, L.n_out, pw, ph,
+                                             ctx->stream));
+            }
+            note_kernel(ctx, li, "fp32_direct");
+            ctx->launches++;
+            std::swap(cur, nxt);
+        }
+        CU_CHECK(launch_crop(cur, pw - 2 * n, ph - 2 * n, n, dst, dst_stride, ctx->stream));
+        ctx->launches++;
+        return W2X_OK;
+    }
+    // ---- tcgen05 engine ----
+    int rc = ensure_tc(ctx);
+    if (rc) return rc;
+    const size_t need = tc::act_bytes(maxc, pw, ph);
+    for (int i = 0; i < 2; i++) {
+        rc = ensure(&ctx->buf[i], &ctx->buf_bytes[i], need);
+        if (rc) return rc;
+    }
+    __half *cur = static_cast<__half *>(ctx->buf[0]), *nxt = static_cast<__half *>(ctx->buf[1]);
+    {
+        const Layer &L = m->layers[0];
+        logf(ctx, "Iteration #%d...", 1);
+        LayerTimer t(ctx, 0);
+        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, dm->w[0], dm->b[0], L.n_out, cur, ctx->stream));
+        note_kernel(ctx, 0, "first_1xN");
+        ctx->launches++;
+    }
+    for (int li = 1; li + 1 < n; li++) {
+        const Layer &L = m->layers[(size_t)li];
+        logf(ctx, "Iteration #%d...", li + 1);
+        CUtensorMap map;
+        int e = tc::make_act_tensor_map(&map, cur, L.n_in, pw, ph);
+        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, li);
+        {
+            LayerTimer t(ctx, li);
+            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)li], dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph,
+                                         dm->out_scale[(size_t)li], ctx->desc_mode, ctx->num_sms, ctx->stream));
+        }
+        note_kernel(ctx, li, "tcgen05_f16x3");
+        ctx->launches++;
+        std::swap(cur, nxt);
+    }
+    {
+        const Layer &L = m->layers[(size_t)n - 1];
+        logf(ctx, "Iteration #%d...", n);
+        LayerTimer t(ctx, n - 1);
+        CU_CHECK(tc::launch_last(cur, L.n_in, pw, ph, dm->w[(size_t)n - 1], static_cast<float>(L.b[0]), n, dst,
+                                 dst_stride, ctx->stream));
+        note_kernel(ctx, n - 1, "last_Nx1");
+        ctx->launches++;
+    }
+    return W2X_OK;
+}
+
+// Whole plane (or row band) already available as a padded plane: cut it into horizontal bands that
+// respect the scratch limit, each band re-reads n rows of context above and below.
+int run_padded_plane(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const float *padp, int w, int h,
+                     float *dst, long dst_stride) {
+    const int n = (int)m->layers.size();
+    const int pw = w + 2 * n;
+    int maxc = 1;
+    for (auto &L : m->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
+    const size_t per_row = (size_t)maxc * pw * 4;   // both engines: 4 bytes per activation element
+    long max_rows = (long)(ctx->scratch_limit / per_row) - 2 * n;
+    if (max_rows < 16) max_rows = 16;
+    int band = (int)std::min<long>(h, max_rows);
+    for (int y0 = 0; y0 < h; y0 += band) {
+        const int bh = std::min(band, h - y0);
+        int rc = run_basic(ctx, m, dm, engine, padp + (long)y0 * pw, pw, pw, bh + 2 * n, dst + (long)y0 * dst_stride,
+                           dst_stride);
+        if (rc) return rc;
+    }
+    return W2X_OK;
+}
+
+int check_ctx(w2x_ctx *ctx) {
+    if (!ctx) return fail(W2X_ERR_ARG, "NULL context");
+    return W2X_OK;
+}
+
+int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, int h, size_t in_stride_bytes,
+                   int rows_above, int rows_below, float *d_out, size_t out_stride_bytes, int block_splitting) {
+    if (!m || !d_in || !d_out || w < 1 || h < 1) return fail(W2X_ERR_ARG, "w2x_convert_plane: bad argument");
+    if (in_stride_bytes % 4 || out_stride_bytes % 4 || in_stride_bytes < (size_t)w * 4 || out_stride_bytes < (size_t)w * 4)
+        return fail(W2X_ERR_ARG, "w2x_convert_plane: row strides must be multiples of 4 bytes and >= width*4");
+    if (m->layers.front().n_in != 1 || m->layers.back().n_out != 1)
+        return fail(W2X_ERR_ARG, "w2x_convert_plane: model must map 1 plane to 1 plane");
+    DeviceGuard g(ctx->device);
+    const int engine = pick_engine(ctx, m);
+    if (engine < 0) return W2X_ERR_UNSUPPORTED;
+    DevModel *dm = nullptr;
+    int rc = get_dev_model(ctx, m, &dm);
+    if (rc) return rc;
+    const int n = (int)m->layers.size();
+    const int pw = w + 2 * n, ph = h + 2 * n;
+    rc = ensure(reinterpret_cast<void **>(&ctx->pad_buf), &ctx->pad_bytes, (size_t)pw * ph * sizeof(float));
+    if (rc) return rc;
+    // cv::copyMakeBorder(in, temp, n, n, n, n, BORDER_REPLICATE)   (src/convertRoutine.cpp:35, :96)
+    CU_CHECK(launch_pad_replicate(d_in, w, h, (long)(in_stride_bytes / 4), n, std::min(rows_above, n),
+                                  std::min(rows_below, n), ctx->pad_buf, ctx->stream));
+    ctx->launches++;
+    const long ostride = (long)(out_stride_bytes / 4);
+    const bool split = block_splitting && w2x_requires_splitting(w, h);
+    if (split && ctx->walk == W2X_WALK_BLOCKS) {
+        // the literal block walk of convertWithModelsBlockSplit (src/convertRoutine.cpp:114-165)
+        const Config &cfg = config();
+        int nb = block_table(w, h, cfg.block_w, cfg.block_h, n, nullptr, 0, nullptr, nullptr);
+        if (nb < 0) return fail(W2X_ERR_ARG, "block size too small for a %d-layer model", n);
+        std::vector<int> tab((size_t)nb * 8);
+        block_table(w, h, cfg.block_w, cfg.block_h, n, tab.data(), nb, nullptr, nullptr);
+        for (int i = 0; i < nb; i++) {
+            const int *t = &tab[(size_t)i * 8];
+            logf(ctx, "start process block (%d,%d) ...", t[1], t[0]);              // :133-134 prints (c,r)
+            const int bw_i = t[5] - t[4], bh_i = t[3] - t[2];
+            if (t[6] + bh_i - 2 * n > h || t[7] + bw_i - 2 * n > w)
+                return fail(W2X_ERR_ARG, "block (%d,%d) does not fit the output plane (non-square block size?)", t[1], t[0]);
+            rc = run_basic(ctx, m, dm, engine, ctx->pad_buf + (long)t[2] * pw + t[4], pw, bw_i, bh_i,
+                           d_out + (long)t[6] * ostride + t[7], ostride);
+            if (rc) return rc;
+        }
+        return W2X_OK;
+    }
+    return run_padded_plane(ctx, m, dm, engine, ctx->pad_buf, w, h, d_out, ostride);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int w2x_ctx_create(int device, w2x_ctx **out_ctx) {
+    if (!out_ctx) return fail(W2X_ERR_ARG, "w2x_ctx_create: NULL out pointer");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(W2X_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(W2X_ERR_ARG, "w2x_ctx_create: device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(W2X_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this build carries sm_100a code only", device,
+                    prop.name, prop.major, prop.minor);
+    auto ctx = std::make_unique<w2x_ctx>();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    DeviceGuard g(device);
+    CU_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    *out_ctx = ctx.release();
+    return W2X_OK;
+}
+
+void w2x_ctx_destroy(w2x_ctx *ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->models) {
+        for (auto p : kv.second.w) cudaFree(p);
+        for (auto p : kv.second.b) cudaFree(p);
+        for (auto p : kv.second.pack) cudaFree(p);
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->buf[i]);
+        cudaFree(ctx->io_buf[i]);
+    }
+    cudaFree(ctx->pad_buf);
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int w2x_ctx_set_engine(w2x_ctx *ctx, int engine) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (engine < W2X_ENGINE_AUTO || engine > W2X_ENGINE_TC) return fail(W2X_ERR_ARG, "unknown engine %d", engine);
+    ctx->engine = engine;
+    return W2X_OK;
+}
+int w2x_ctx_get_engine(const w2x_ctx *ctx) { return ctx ? ctx->engine : -1; }
+
+int w2x_ctx_set_stream(w2x_ctx *ctx, void *cuda_stream) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return W2X_OK;
+}
+
+int w2x_ctx_synchronize(w2x_ctx *ctx) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    return W2X_OK;
+}
+
+int w2x_ctx_set_log(w2x_ctx *ctx, w2x_log_fn fn, void *user) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->log = fn;
+    ctx->log_user = user;
+    return W2X_OK;
+}
+
+int w2x_ctx_set_block_walk(w2x_ctx *ctx, int mode) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (mode != W2X_WALK_FUSED && mode != W2X_WALK_BLOCKS) return fail(W2X_ERR_ARG, "unknown block walk mode %d", mode);
+    ctx->walk = mode;
+    return W2X_OK;
+}
+
+int w2x_ctx_set_scratch_limit(w2x_ctx *ctx, size_t bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->scratch_limit = bytes ? bytes : (size_t)16 << 30;
+    return W2X_OK;
+}
+
+// Probe switch (not part of the stable ABI): UMMA descriptor base_offset policy of the tcgen05 engine.
+W2X_API int w2x_debug_set_desc_mode(w2x_ctx *ctx, int mode) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->desc_mode = mode;
+    return W2X_OK;
+}
+
+int w2x_convert_plane_device(w2x_ctx *ctx, const w2x_model *model, const float *d_in, int width, int height,
+                             size_t in_stride_bytes, float *d_out, size_t out_stride_bytes, int block_splitting) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    return convert_device(ctx, model, d_in, width, height, in_stride_bytes, 0, 0, d_out, out_stride_bytes, block_splitting);
+}
+
+int w2x_convert_band_device(w2x_ctx *ctx, const w2x_model *model, const float *d_in, int width, int band_height,
+                            int rows_above, int rows_below, size_t in_stride_bytes, float *d_out, size_t out_stride_bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (rows_above < 0 || rows_below < 0) return fail(W2X_ERR_ARG, "w2x_convert_band_device: negative halo");
+    if (!d_in) return fail(W2X_ERR_ARG, "w2x_convert_band_device: NULL input");
+    const float *band0 = d_in + (size_t)rows_above * (in_stride_bytes / 4);
+    return convert_device(ctx, model, band0, width, band_height, in_stride_bytes, rows_above, rows_below, d_out,
+                          out_stride_bytes, 0);
+}
+
+int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int width, int height, size_t in_stride_bytes,
+                      float *out, size_t out_stride_bytes, int block_splitting) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!in || !out || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_convert_plane: bad argument");
+    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4)
+        return fail(W2X_ERR_ARG, "w2x_convert_plane: row stride smaller than a row");
+    DeviceGuard g(ctx->device);
+    const size_t bytes = (size_t)width * height * sizeof(float);
+    for (int i = 0; i < 2; i++) {
+        int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], bytes);
+        if (rc) return rc;
+    }
+    CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0], (size_t)width * 4, in, in_stride_bytes, (size_t)width * 4, (size_t)height,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    int rc = convert_device(ctx, model, ctx->io_buf[0], width, height, (size_t)width * 4, 0, 0, ctx->io_buf[1],
+                            (size_t)width * 4, block_splitting);
+    if (rc) return rc;
+    CU_CHECK(cudaMemcpy2DAsync(out, out_stride_bytes, ctx->io_buf[1], (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    return W2X_OK;
+}
+
+int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, const float *d_in, float *d_out, int width,
+                            int height) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model || layer < 0 || layer >= (int)model->layers.size() || !d_in || !d_out || width < 1 || height < 1)
+        return fail(W2X_ERR_ARG, "w2x_filter_layer: bad argument");
+    DeviceGuard g(ctx->device);
+    DevModel *dm = nullptr;
+    int rc = get_dev_model(ctx, model, &dm);
+    if (rc) return rc;
+    const Layer &L = model->layers[(size_t)layer];
+    int engine = ctx->engine == W2X_ENGINE_AUTO ? W2X_ENGINE_FP32 : ctx->engine;
+    if (engine == W2X_ENGINE_TC) {
+        if (!tc::layer_supported(L.n_in, L.n_out))
+            return fail(W2X_ERR_UNSUPPORTED, "tcgen05 engine does not support a %d->%d layer", L.n_in, L.n_out);
+        rc = ensure_tc(ctx);
+        if (rc) return rc;
+        // Model::filter semantics (same size, BORDER_REPLICATE): stage a frame with a replicated ring
+        // of one pixel, run the same-size tcgen05 layer on it, return the interior.
+        const int pw = width + 2, ph = height + 2;
+        rc = ensure(&ctx->buf[0], &ctx->buf_bytes[0], tc::act_bytes(L.n_in, pw, ph));
+        if (rc) return rc;
+        rc = ensure(&ctx->buf[1], &ctx->buf_bytes[1], tc::act_bytes(L.n_out, pw, ph));
+        if (rc) return rc;
+        __half *fin = static_cast<__half *>(ctx->buf[0]), *fout = static_cast<__half *>(ctx->buf[1]);
+        CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream));
+        CUtensorMap map;
+        int e = tc::make_act_tensor_map(&map, fin, L.n_in, pw, ph);
+        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", e);
+        {
+            LayerTimer t(ctx, layer);
+            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)layer], dm->b[(size_t)layer], fout, L.n_in, L.n_out, pw, ph,
+                                         dm->out_scale[(size_t)layer], ctx->desc_mode, ctx->num_sms, ctx->stream));
+        }
+        CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream));
+        note_kernel(ctx, layer, "tcgen05_f16x3");
+        ctx->launches += 3;
+        return W2X_OK;
+    }
+    {
+        LayerTimer t(ctx, layer);
+        CU_CHECK(launch_conv3x3_fp32(d_in, d_out, dm->w[(size_t)layer], dm->b[(size_t)layer], L.n_in, L.n_out, width, height,
+                                     ctx->stream));
+    }
+    note_kernel(ctx, layer, "fp32_direct");
+    ctx->launches++;
+    return W2X_OK;
+}
+
+int w2x_filter_layer(w2x_ctx *ctx, const w2x_model *model, int layer, const float *const *in_planes, int n_in_planes,
+                     float *const *out_planes, int n_out_planes, int width, int height, size_t in_stride_bytes,
+                     size_t out_stride_bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model || layer < 0 || layer >= (int)model->layers.size() || !in_planes || !out_planes || width < 1 || height < 1)
+        return fail(W2X_ERR_ARG, "w2x_filter_layer: bad argument");
+    const Layer &L = model->layers[(size_t)layer];
+    if (n_in_planes != L.n_in)   // src/modelHandler.cpp:29-35
+        return fail(W2X_ERR_ARG, "Error : Model-filter : \nnumber of input planes mismatch.\n%d,%d", n_in_planes, L.n_in);
+    if (n_out_planes != L.n_out)
+        return fail(W2X_ERR_ARG, "w2x_filter_layer: %d output planes supplied, layer produces %d", n_out_planes, L.n_out);
+    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4)
+        return fail(W2X_ERR_ARG, "w2x_filter_layer: row stride smaller than a row");
+    DeviceGuard g(ctx->device);
+    const size_t plane = (size_t)width * height * sizeof(float);
+    int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[0]), &ctx->io_bytes[0], plane * (size_t)L.n_in);
+    if (rc) return rc;
+    rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[1]), &ctx->io_bytes[1], plane * (size_t)L.n_out);
+    if (rc) return rc;
+    for (int i = 0; i < L.n_in; i++) {
+        if (!in_planes[i]) return fail(W2X_ERR_ARG, "w2x_filter_layer: NULL input plane %d", i);
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(ctx->io_buf[0]) + plane * (size_t)i, (size_t)width * 4, in_planes[i],
+                                   in_stride_bytes, (size_t)width * 4, (size_t)height, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = w2x_filter_layer_device(ctx, model, layer, ctx->io_buf[0], ctx->io_buf[1], width, height);
+    if (rc) return rc;
+    for (int i = 0; i < L.n_out; i++) {
+        if (!out_planes[i]) return fail(W2X_ERR_ARG, "w2x_filter_layer: NULL output plane %d", i);
+        CU_CHECK(cudaMemcpy2DAsync(out_planes[i], out_stride_bytes, reinterpret_cast<char *>(ctx->io_buf[1]) + plane * (size_t)i,
+                                   (size_t)width * 4, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    return W2X_OK;
+}
+
+int w2x_ctx_launch_count(const w2x_ctx *ctx, uint64_t *n_launches) {
+    if (!ctx || !n_launches) return fail(W2X_ERR_ARG, "w2x_ctx_launch_count: NULL argument");
+    *n_launches = ctx->launches;
+    return W2X_OK;
+}
+
+int w2x_ctx_set_timing(w2x_ctx *ctx, int enabled) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->timing = enabled != 0;
+    return W2X_OK;
+}
+
+int w2x_ctx_layer_times(w2x_ctx *ctx, int max_layers, float *ms, int *launches, int *n_layers_out, int reset) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (max_layers < 0 || (max_layers > 0 && (!ms || !launches))) return fail(W2X_ERR_ARG, "w2x_ctx_layer_times: bad argument");
+    DeviceGuard g(ctx->device);
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < max_layers; i++) { ms[i] = 0.f; launches[i] = 0; }
+    int top = 0;
+    for (auto &s : ctx->spans) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, s.e0, s.e1);
+        if (s.layer >= 0 && s.layer < max_layers) { ms[s.layer] += t; launches[s.layer]++; }
+        top = std::max(top, s.layer + 1);
+    }
+    if (n_layers_out) *n_layers_out = top;
+    if (reset) {
+        for (auto &s : ctx->spans) { ctx->event_pool.push_back(s.e0); ctx->event_pool.push_back(s.e1); }
+        ctx->spans.clear();
+    }
+    return W2X_OK;
+}
+
+const char *w2x_ctx_layer_kernel_name(const w2x_ctx *ctx, int layer) {
+    if (!ctx || layer < 0 || layer >= (int)ctx->layer_kernel.size()) return "";
+    return ctx->layer_kernel[(size_t)layer].c_str();
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// kernels.h -- launchers of every kernel in the library (device code lives in the .cu files).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace w2x {
+
+// ---- kernels_fp32.cu --------------------------------------------------------------------------
+cudaError_t launch_pad_replicate(const float *in, int w, int h, long in_stride_floats, int pad, int rows_above,
+                                 int rows_below, float *out, cudaStream_t s);
+cudaError_t launch_crop(const float *in, int w, int h, int pad, float *out, long out_stride_floats, cudaStream_t s);
+cudaError_t launch_copy2d(const float *in, long in_stride_floats, float *out, long out_stride_floats, int w, int h,
+                          cudaStream_t s);
+cudaError_t launch_conv3x3_fp32(const float *in, float *out, const float *wgt, const float *bias, int Cin, int Cout,
+                                int W, int H, cudaStream_t s);
+
+// ---- kernels_tc.cu ----------------------------------------------------------------------------
+namespace tc {
+constexpr int REGION = 16;          // a tile-set covers REGION x REGION output pixels (two 8x16 M-tiles)
+constexpr int HALO = REGION + 2;    // staged input footprint per side
+constexpr float ACT_SCALE = 16.0f;  // activations are stored as fp16 hi/lo of (value * ACT_SCALE)
+
+// Activation tensor between layers: [2 (hi,lo)][Hp][Wp][C] fp16.
+inline size_t act_bytes(int C, int Wp, int Hp) { return (size_t)2 * Hp * Wp * C * 2; }
+
+bool layer_supported(int cin, int cout);
+size_t layer_smem_bytes(int cin, int cout);
+// One-time per process: raise the dynamic shared memory limit of every instantiation.
+cudaError_t init_kernels();
+
+// First layer (Cin = 1): fp32 plane (ROI with stride) -> NHWC hi/lo frame of the same size (pw x ph),
+// same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
+cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
+                         const float *bias, int cout, __half *out, cudaStream_t s);
+// tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
+cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out,
+                            int cin, int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms,
+                            cudaStream_t s);
+// Last layer (Cout = 1): NHWC hi/lo frame -> fp32 plane, interior only: out(y,x) for
+// y in [crop, ph-crop), x in [crop, pw-crop) is written to dst[(y-crop)*stride + (x-crop)].
+cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt /*[C][9]*/, float bias,
+                        int crop, float *dst, long dst_stride_floats, cudaStream_t s);
+// planar fp32 [C][h][w] -> NHWC hi/lo frame (h+2) x (w+2), replicate ring of 1 (for w2x_filter_layer)
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s);
+// NHWC hi/lo frame (h+2) x (w+2) -> planar fp32 [C][h][w] (interior)
+cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s);
+
+// Host: build the 4-D TMA descriptor {C, Wp, Hp, 2} with box {kc, HALO, HALO, 1}.
+int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp);
+}  // namespace tc
+
+}  // namespace w2x
