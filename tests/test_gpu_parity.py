@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes over libw2x_b200.so), against
+the CPU oracle and the committed golden vectors.  Floating-point path: tolerances are stated.
+
+  GOLD_TOL   1e-4  the gate BASELINE.json states (max-abs vs the reference CPU path)
+  FP32_TOL   5e-6  fp32 CUDA-core engine: same association as the reference, FMA contraction only
+  TC_TOL     2e-5  tcgen05 engine: 3-pass fp16 split, fp32 TMEM accumulation (CPU emulation of the
+                   scheme measures 7e-7, tests/test_numerics_model.py; the rest is accumulation order)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+
+pytestmark = pytest.mark.gpu
+
+GOLD_TOL = 1e-4
+FP32_TOL = 5e-6
+TC_TOL = 2e-5
+ENGINES = [("fp32", 1, FP32_TOL), ("tc", 2, TC_TOL)]
+
+
+@pytest.fixture(scope="module")
+def ctxs(w2x):
+    c = {name: w2x.Context(0, engine=eng) for name, eng, _ in ENGINES}
+    yield c
+    for v in c.values():
+        v.close()
+
+
+@pytest.fixture(scope="module")
+def models(w2x, json_models):
+    # through the JSON loader, like the reference CLI does (src/main.cpp:88,120)
+    return {n: w2x.Model.load_json(p) for n, p in json_models.items()}
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+@pytest.mark.parametrize("name,kind", [("scale2.0x", "uniform"), ("scale2.0x", "smooth"),
+                                       ("noise1", "uniform"), ("noise2", "uniform")])
+def test_cfg1_256_against_reference_golden(ctxs, models, oracle_mod, engine, eng_id, tol, name, kind):
+    """Config 1 of BASELINE.json: 256x256 Y plane, against the output of the reference's OpenCV path."""
+    x = oracle_mod.seeded_plane(256, 256, 0, kind)
+    y = ctxs[engine].convert_plane(models[name], x)
+    g = np.load(golden_path(f"cfg1_{name}_{kind}.npy"))
+    err = np.abs(y - g).max()
+    assert err <= GOLD_TOL, err          # the stated gate
+    assert err <= tol, err               # what this engine is expected to reach
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_odd_and_tiny_sizes(ctxs, models, oracle_mod, engine, eng_id, tol):
+    z = np.load(golden_path("odd_sizes.npz"))
+    for (w, h) in ((1, 1), (15, 13), (37, 61)):
+        x = oracle_mod.seeded_plane(w, h, 10 + w, "uniform")
+        y = ctxs[engine].convert_plane(models["scale2.0x"], x)
+        assert y.shape == (h, w)
+        assert np.abs(y - z[f"out_{w}x{h}"]).max() <= tol, (w, h)
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_ragged_sizes_against_oracle(ctxs, models, oracle_mod, oracle_models, ncpu, engine, eng_id, tol):
+    """Sizes around the 16-pixel tile and 32x8 block edges."""
+    for i, (w, h) in enumerate(((16, 16), (17, 31), (2, 50), (129, 3), (100, 99))):
+        x = oracle_mod.seeded_plane(w, h, 20 + i, "uniform")
+        y = ctxs[engine].convert_plane(models["noise1"], x)
+        ref = oracle_models["noise1"].convert(x, n_job=ncpu)
+        assert np.abs(y - ref).max() <= tol, (w, h)
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_per_layer_filter_against_reference_golden(ctxs, models, engine, eng_id, tol):
+    """Model::filter (same size, BORDER_REPLICATE) layer by layer -- catches tap order / layout / flip bugs."""
+    z = np.load(golden_path("layers_32x24.npz"))
+    m = models["scale2.0x"]
+    for li in range(7):
+        if engine == "tc" and li in (0, 6):
+            continue          # 1->32 and 128->1 have no MMA form; covered by the whole-path tests
+        out = ctxs[engine].filter_layer(m, li, z[f"in{li}"])
+        err = np.abs(out - z[f"out{li}"]).max()
+        assert err <= tol, (li, err)
+
+
+def test_filter_plane_count_mismatch_is_an_error(w2x, ctxs, models):
+    with pytest.raises(w2x.W2xError) as ei:
+        ctxs["fp32"].filter_layer(models["scale2.0x"], 1, np.zeros((3, 8, 8), np.float32))
+    assert ei.value.status == 1 and "number of input planes mismatch" in ei.value.message   # src/modelHandler.cpp:29-35
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_block_split_path_513x768(w2x, ctxs, models, oracle_mod, engine, eng_id, tol):
+    """First size past the no-split edge; fused whole-plane pass vs the literal block walk vs golden."""
+    z = np.load(golden_path("split_513x768.npz"))
+    x = oracle_mod.seeded_plane(513, 768, 5, "uniform")
+    ctx = ctxs[engine]
+    lines = []
+    ctx.set_log(lines.append)
+    try:
+        ctx.set_block_walk(w2x.WALK_FUSED)
+        fused = ctx.convert_plane(models["scale2.0x"], x)
+        assert [l for l in lines if l.startswith("start process")] == []
+        lines.clear()
+        ctx.set_block_walk(w2x.WALK_BLOCKS)
+        walked = ctx.convert_plane(models["scale2.0x"], x)
+    finally:
+        ctx.set_block_walk(w2x.WALK_FUSED)
+        ctx.set_log(None)
+    # progress lines in the reference's order: (c,r) with c inner, 7 iterations per block
+    assert [l for l in lines if l.startswith("start")] == [f"start process block ({c},{r}) ..." for r in range(2) for c in range(2)]
+    assert lines[1:8] == [f"Iteration #{k}..." for k in range(1, 8)]
+    assert np.array_equal(fused, walked)                       # bit-exact block indexing
+    assert np.abs(fused[::16, ::16] - z["lattice"]).max() <= tol
+    assert np.abs(fused[494:502, :] - z["rows_494_502"]).max() <= tol
+    assert np.abs(fused[:, 494:502] - z["cols_494_502"]).max() <= tol
+    nosplit = ctx.convert_plane(models["scale2.0x"], x, block_splitting=False)
+    assert np.array_equal(fused, nosplit)
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_strided_host_planes(ctxs, models, oracle_mod, engine, eng_id, tol):
+    big = oracle_mod.seeded_plane(90, 70, 9, "uniform")
+    roi = big[5:55, 7:80]                                      # non-contiguous ROI, src/convertRoutine.cpp:116-131
+    dense = ctxs[engine].convert_plane(models["noise2"], np.ascontiguousarray(roi))
+    outbuf = np.full((60, 100), -7.0, np.float32)
+    view = outbuf[3:53, 11:84]
+    ctxs[engine].convert_plane(models["noise2"], roi, out=view)
+    assert np.array_equal(view, dense)
+    assert np.all(outbuf[:3] == -7.0) and np.all(outbuf[:, :11] == -7.0) and np.all(outbuf[:, 84:] == -7.0)
+
+
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_scratch_limit_bands_are_bit_identical(ctxs, models, oracle_mod, engine, eng_id, tol):
+    x = oracle_mod.seeded_plane(200, 180, 12, "uniform")
+    ctx = ctxs[engine]
+    whole = ctx.convert_plane(models["scale2.0x"], x)
+    try:
+        ctx.set_scratch_limit(128 * (200 + 14) * 4 * 40)      # ~40 rows per band
+        banded = ctx.convert_plane(models["scale2.0x"], x)
+    finally:
+        ctx.set_scratch_limit(0)
+    assert np.array_equal(whole, banded)
+
+
+def test_engines_agree_with_each_other(ctxs, models, oracle_mod):
+    x = oracle_mod.seeded_plane(300, 200, 31, "smooth")
+    a = ctxs["fp32"].convert_plane(models["noise2"], x)
+    b = ctxs["tc"].convert_plane(models["noise2"], x)
+    assert np.abs(a - b).max() <= TC_TOL
+
+
+def test_cfg5_tile_512_noise2(ctxs, models, oracle_mod, oracle_models, ncpu):
+    """Config 5 unit: one 512x512 tile, noise2 model (not split: 262144 <= 393216)."""
+    x = oracle_mod.seeded_plane(512, 512, 3, "uniform")
+    ref = oracle_models["noise2"].convert(x, n_job=ncpu)
+    for engine, _, tol in ENGINES:
+        y = ctxs[engine].convert_plane(models["noise2"], x)
+        assert np.abs(y - ref).max() <= tol, engine
+
+
+def test_device_entry_points_and_band_mode(w2x, ctxs, models, oracle_mod):
+    """w2x_convert_plane_device on torch tensors, and the row-band entry: two bands with a 7-row
+    real halo reproduce the whole-plane result bit for bit."""
+    import torch
+    x = oracle_mod.seeded_plane(160, 120, 8, "uniform")
+    for engine, _, _ in ENGINES:
+        ctx = ctxs[engine]
+        whole = ctx.convert_plane(models["scale2.0x"], x)
+        d_in = torch.from_numpy(x).cuda()
+        d_out = torch.empty_like(d_in)
+        ctx.convert_plane_device(models["scale2.0x"], d_in.data_ptr(), 160, 120, 160 * 4, d_out.data_ptr(), 160 * 4)
+        ctx.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), whole)
+        # bands [0,50) and [50,120)
+        o0 = torch.empty((50, 160), device="cuda")
+        o1 = torch.empty((70, 160), device="cuda")
+        ctx.convert_band_device(models["scale2.0x"], d_in.data_ptr(), 160, 50, 0, 7, 160 * 4, o0.data_ptr(), 160 * 4)
+        ctx.convert_band_device(models["scale2.0x"], d_in[43:].data_ptr(), 160, 70, 7, 0, 160 * 4, o1.data_ptr(), 160 * 4)
+        ctx.synchronize()
+        assert np.array_equal(torch.cat([o0, o1]).cpu().numpy(), whole), engine
+
+
+def test_full_size_4096_properties(w2x, ctxs, models, oracle_mod, oracle_models, ncpu):
+    """BASELINE.json config 3 size (4096x4096, scale2.0x) through size-independent properties:
+    (1) windows of the full output equal the oracle run on that window + its 7-pixel context,
+    (2) translation consistency: a shifted crop of the input reproduces the shifted output bit for bit,
+    (3) a constant plane maps to a constant plane."""
+    x = oracle_mod.seeded_plane(4096, 4096, 1, "uniform")
+    ctx = ctxs["tc"]
+    y = ctx.convert_plane(models["scale2.0x"], x)
+    assert np.isfinite(y).all()
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        x0, y0 = int(rng.integers(7, 4096 - 71)), int(rng.integers(7, 4096 - 71))
+        win = x[y0 - 7:y0 + 64 + 7, x0 - 7:x0 + 64 + 7]
+        ref = oracle_models["scale2.0x"].convert(win, n_job=ncpu)[7:-7, 7:-7]
+        assert np.abs(y[y0:y0 + 64, x0:x0 + 64] - ref).max() <= TC_TOL
+    # corners use the replicate padding
+    ref = oracle_models["scale2.0x"].convert(x[:71, :71], n_job=ncpu)[:64, :64]
+    assert np.abs(y[:64, :64] - ref).max() <= TC_TOL
+    ref = oracle_models["scale2.0x"].convert(x[-71:, -71:], n_job=ncpu)[-64:, -64:]
+    assert np.abs(y[-64:, -64:] - ref).max() <= TC_TOL
+    sub = ctx.convert_plane(models["scale2.0x"], x[1000:1400, 2000:2300])
+    assert np.array_equal(sub[7:-7, 7:-7], y[1007:1393, 2007:2293])
+    c = ctx.convert_plane(models["scale2.0x"], np.full((600, 700), 0.5, np.float32))
+    assert np.ptp(c) == 0.0
+
+
+def test_launch_counter_and_timing(ctxs, models, oracle_mod):
+    ctx = ctxs["tc"]
+    x = oracle_mod.seeded_plane(64, 64, 1, "uniform")
+    n0 = ctx.launch_count()
+    ctx.set_timing(True)
+    try:
+        ctx.convert_plane(models["scale2.0x"], x)
+        times = ctx.layer_times()
+    finally:
+        ctx.set_timing(False)
+    assert ctx.launch_count() - n0 == 8                        # pad + 7 layer kernels
+    assert [t[2] for t in times] == ["first_1xN"] + ["tcgen05_f16x3"] * 5 + ["last_Nx1"]
+    assert all(t[0] > 0 and t[1] == 1 for t in times)

@@ -459,6 +459,9 @@ int w2x_convert_band_device(w2x_ctx *ctx, const w2x_model *model, const float *d
                             int rows_above, int rows_below, size_t in_stride_bytes, float *d_out, size_t out_stride_bytes) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
     if (rows_above < 0 || rows_below < 0) return fail(W2X_ERR_ARG, "w2x_convert_band_device: negative halo");
+    if (model && ((rows_above && rows_above < (int)model->layers.size()) || (rows_below && rows_below < (int)model->layers.size())))
+        return fail(W2X_ERR_ARG, "w2x_convert_band_device: a halo must be 0 (image border) or >= the layer count (%zu)",
+                    model->layers.size());
     if (!d_in) return fail(W2X_ERR_ARG, "w2x_convert_band_device: NULL input");
     const float *band0 = d_in + (size_t)rows_above * (in_stride_bytes / 4);
     return convert_device(ctx, model, band0, width, band_height, in_stride_bytes, rows_above, rows_below, d_out,
