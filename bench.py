@@ -171,7 +171,9 @@ def run_ours(args):
     model = w2x.Model.from_arrays(om.weights, om.biases)
     engine = {"auto": w2x.ENGINE_AUTO, "tc": w2x.ENGINE_TC, "fp32": w2x.ENGINE_FP32}[args.engine]
     ctx = w2x.Context(local, engine=engine)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-default) stream: handle 0 would mean "the context's own stream"
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     # this rank's band of the (H*world) x W plane, seeded per rank
@@ -184,16 +186,10 @@ def run_ours(args):
     d_band.copy_(host_in)
     d_out = torch.empty((H, W), dtype=torch.float32, device="cuda")
 
+    from w2x_b200 import bands
+
     def exchange_halos():
-        if world == 1:
-            return
-        ops = []
-        if up is not None:
-            ops += [dist.P2POp(dist.isend, d_band[:n_model].contiguous(), up), dist.P2POp(dist.irecv, d_ext[:ra], up)]
-        if down is not None:
-            ops += [dist.P2POp(dist.isend, d_band[H - n_model:].contiguous(), down), dist.P2POp(dist.irecv, d_ext[ra + H:], down)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+        bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
 
     def step_device():
         exchange_halos()
@@ -262,7 +258,6 @@ def run_ours(args):
         if layers:
             k = max(range(len(layers)), key=lambda i: layers[i][0])
             ms_k, n_k, name_k = layers[k]
-            pix_launch = (W + 14) * (H + 14 + (ra + rb - 14 if world > 1 else 0))   # frame pixels one launch covers
             flop_launch = 2.0 * LAYER_MACS[k] * W * H * args.steps / n_k            # algorithmic: output pixels only
             tensor = name_k.startswith("tcgen05")
             ach = flop_launch / (ms_k / n_k * 1e-3) / 1e12

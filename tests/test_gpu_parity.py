@@ -78,7 +78,9 @@ def test_per_layer_filter_against_reference_golden(ctxs, models, engine, eng_id,
         if engine == "tc" and li in (0, 6):
             continue          # 1->32 and 128->1 have no MMA form; covered by the whole-path tests
         out = ctxs[engine].filter_layer(m, li, z[f"in{li}"])
-        err = np.abs(out - z[f"out{li}"]).max()
+        # these single-layer probes feed uniform noise into every plane, so outputs reach |5..7|:
+        # the tolerance scales with the output magnitude (the whole-path tests use the absolute gate)
+        err = np.abs(out - z[f"out{li}"]).max() / max(1.0, float(np.abs(z[f"out{li}"]).max()))
         assert err <= tol, (li, err)
 
 

@@ -97,6 +97,8 @@ def lib():
     L.w2x_ctx_layer_kernel_name.argtypes = [vp, ci]
     L.w2x_ctx_layer_kernel_name.restype = C.c_char_p
     L.w2x_debug_set_desc_mode.argtypes = [vp, ci]
+    L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
+    L.w2x_debug_tc_profile_read.argtypes = [vp, ci, C.POINTER(C.c_uint64), C.POINTER(ci)]
     L.w2x_debug_tc_pack.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(cs), C.POINTER(ci), C.POINTER(ci),
                                     C.POINTER(C.c_float)]
     _lib = L
@@ -221,6 +223,18 @@ class Context:
     def set_scratch_limit(self, nbytes): _check(lib().w2x_ctx_set_scratch_limit(self._h, nbytes))
     def set_timing(self, on): _check(lib().w2x_ctx_set_timing(self._h, int(on)))
     def debug_set_desc_mode(self, mode): _check(lib().w2x_debug_set_desc_mode(self._h, mode))
+
+    def debug_tc_profile_enable(self, on=True): _check(lib().w2x_debug_tc_profile_enable(self._h, int(on)))
+
+    def debug_tc_profile_read(self, layer):
+        """per-role cycle counters of the tcgen05 kernel of `layer`, averaged per CTA (dict)."""
+        out = (C.c_uint64 * 16)()
+        n = C.c_int()
+        _check(lib().w2x_debug_tc_profile_read(self._h, layer, out, C.byref(n)))
+        names = ["total", "mma_wait_acc", "mma_wait_a", "mma_wait_b", "aprod_wait", "bprod_wait", "epi_wait", "epi_work", "tilesets"]
+        d = {k: out[i] / max(n.value, 1) for i, k in enumerate(names)}
+        d["ctas"] = n.value
+        return d
 
     def set_log(self, fn):
         """fn(str) receives the reference's progress lines; None disables."""

@@ -65,6 +65,7 @@ struct w2x_ctx {
     float *io_buf[2] = {nullptr, nullptr};   // device staging for the host-buffer entry points
     size_t io_bytes[2] = {0, 0};
     bool tc_ready = false;
+    unsigned long long *prof_buf = nullptr;   // [16 layers][PROF_MAX_CTAS][PROF_WORDS], debug profile
 };
 
 namespace {
@@ -257,7 +258,8 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         {
             LayerTimer t(ctx, li);
             CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)li], dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph,
-                                         dm->out_scale[(size_t)li], ctx->desc_mode, ctx->num_sms, ctx->stream));
+                                         dm->out_scale[(size_t)li], ctx->desc_mode, ctx->num_sms, ctx->stream,
+                                         ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr));
         }
         note_kernel(ctx, li, "tcgen05_f16x3");
         ctx->launches++;
@@ -395,6 +397,7 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
         cudaFree(ctx->io_buf[i]);
     }
     cudaFree(ctx->pad_buf);
+    cudaFree(ctx->prof_buf);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -439,6 +442,40 @@ int w2x_ctx_set_block_walk(w2x_ctx *ctx, int mode) {
 int w2x_ctx_set_scratch_limit(w2x_ctx *ctx, size_t bytes) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
     ctx->scratch_limit = bytes ? bytes : (size_t)16 << 30;
+    return W2X_OK;
+}
+
+// Probe hooks (not part of the stable ABI): per-role wait/work cycle counters of the tcgen05 layer kernels.
+W2X_API int w2x_debug_tc_profile_enable(w2x_ctx *ctx, int on) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    const size_t bytes = (size_t)16 * tc::PROF_MAX_CTAS * tc::PROF_WORDS * sizeof(unsigned long long);
+    if (on) {
+        if (!ctx->prof_buf) CU_CHECK(cudaMalloc(&ctx->prof_buf, bytes));
+        CU_CHECK(cudaMemsetAsync(ctx->prof_buf, 0, bytes, ctx->stream));
+    } else if (ctx->prof_buf) {
+        CU_CHECK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->prof_buf);
+        ctx->prof_buf = nullptr;
+    }
+    return W2X_OK;
+}
+// out[PROF_WORDS]: counters of `layer` summed over CTAs; *n_ctas = CTAs that ran.
+W2X_API int w2x_debug_tc_profile_read(w2x_ctx *ctx, int layer, unsigned long long *out, int *n_ctas) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!ctx->prof_buf || layer < 0 || layer >= 16 || !out) return fail(W2X_ERR_ARG, "profile not enabled or bad layer");
+    DeviceGuard g(ctx->device);
+    std::vector<unsigned long long> h((size_t)tc::PROF_MAX_CTAS * tc::PROF_WORDS);
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    CU_CHECK(cudaMemcpy(h.data(), ctx->prof_buf + (size_t)layer * h.size(), h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int w = 0; w < tc::PROF_WORDS; w++) out[w] = 0;
+    for (int c = 0; c < tc::PROF_MAX_CTAS; c++) {
+        if (h[(size_t)c * tc::PROF_WORDS] == 0) continue;
+        n++;
+        for (int w = 0; w < tc::PROF_WORDS; w++) out[w] += h[(size_t)c * tc::PROF_WORDS + w];
+    }
+    if (n_ctas) *n_ctas = n;
     return W2X_OK;
 }
 

@@ -37,7 +37,9 @@ cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph,
 // tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out,
                             int cin, int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms,
-                            cudaStream_t s);
+                            cudaStream_t s, unsigned long long *prof = nullptr);
+constexpr int PROF_WORDS = 16;      // per-CTA profile record (see kernels_tc.cu PROF_*)
+constexpr int PROF_MAX_CTAS = 256;
 // Last layer (Cout = 1): NHWC hi/lo frame -> fp32 plane, interior only: out(y,x) for
 // y in [crop, ph-crop), x in [crop, pw-crop) is written to dst[(y-crop)*stride + (x-crop)].
 cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt /*[C][9]*/, float bias,

@@ -201,7 +201,22 @@ struct TcParams {
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / (wscale * ACT_SCALE)
     int desc_mode;           // 0: base_offset = 0 ; 1: base_offset = (start >> 7) & 7  (probe)
+    unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
 };
+
+// per-CTA profile record (cycles, accumulated over launches)
+enum { PROF_TOTAL = 0, PROF_MMA_WAIT_ACC, PROF_MMA_WAIT_A, PROF_MMA_WAIT_B, PROF_APROD_WAIT, PROF_BPROD_WAIT,
+       PROF_EPI_WAIT, PROF_EPI_WORK, PROF_TILESETS, PROF_N = 16 };
+
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bool on, unsigned long long &acc) {
+    if (on) {
+        long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += (unsigned long long)(clock64() - t0);
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 
 // ================================================================================================
 // The layer kernel
@@ -230,6 +245,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
     for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool prof_on = p.prof != nullptr;
+    unsigned long long *prof = prof_on ? p.prof + (size_t)blockIdx.x * PROF_N : nullptr;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
@@ -259,33 +276,37 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         // ===================== A producer: one halo'd box per (tile-set, chunk, hi|lo) ==============
         if (lane == 0) {
             uint32_t it = 0;
+            unsigned long long w_a = 0;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
                 const int ty = ts / p.tiles_x, tx = ts - ty * p.tiles_x;
                 const int x0 = tx * REGION - 1, y0 = ty * REGION - 1;   // box origin incl. ring (may be -1)
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
                     const uint32_t slot = it & 1u, round = it >> 1;
-                    mbar_wait(a_empty(slot), (round & 1u) ^ 1u);
+                    mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
                     mbar_arrive_expect_tx(a_full(slot), 2u * C::A_PLANE);
                     const uint32_t dst = a_base + slot * C::A_SLOT;
                     tma_load_4d(dst, &tmap_in, a_full(slot), c * C::KC, x0, y0, 0);
                     tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in, a_full(slot), c * C::KC, x0, y0, 1);
                 }
             }
+            if (prof_on) prof[PROF_APROD_WAIT] += w_a;
         }
     } else if (warp == 2) {
         // ===================== B producer: stream the packed weights, (chunk, tap, hi|lo) order =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            unsigned long long w_b = 0;
             constexpr int N_BLOCKS = C::NCHUNK * 9 * 2;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack);
                 for (int blk = 0; blk < N_BLOCKS; blk++) {
-                    mbar_wait(b_empty(stage), phase ^ 1u);
+                    mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
                     mbar_arrive_expect_tx(b_full(stage), C::B_STAGE);
                     bulk_load(b_base + stage * C::B_STAGE, src + (size_t)blk * C::B_STAGE, C::B_STAGE, b_full(stage));
                     if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (single thread) ============================================
@@ -294,20 +315,22 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             constexpr uint32_t A_SBO = HALO * C::ROWB;   // next output row = next halo row
             constexpr uint32_t B_SBO = 8 * C::ROWB;      // dense rows
             uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
+            unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+            const long long t_begin = clock64();
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
                 const uint32_t set = n & 1u;
-                mbar_wait(acc_empty(set), ((n >> 1) & 1u) ^ 1u);
+                mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + (set * 2u) * COUT;
                 for (int c = 0; c < C::NCHUNK; c++, a_it++) {
                     const uint32_t slot = a_it & 1u;
-                    mbar_wait(a_full(slot), (a_it >> 1) & 1u);
+                    mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                     tc_fence_after();
                     const uint32_t a_hi = a_base + slot * C::A_SLOT, a_lo = a_hi + C::A_PLANE_PAD;
                     for (int t = 0; t < 9; t++) {
                         const int ky = t / 3, kx = t - 3 * ky;
                         // ---- hi weights: xh*wh and xl*wh ----
-                        mbar_wait(b_full(stage), phase);
+                        mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                         tc_fence_after();
                         {
                             const uint32_t bs = b_base + stage * C::B_STAGE;
@@ -331,7 +354,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                         umma_commit(b_empty(stage));
                         if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         // ---- lo weights: xh*wl ----
-                        mbar_wait(b_full(stage), phase);
+                        mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                         tc_fence_after();
                         {
                             const uint32_t bs = b_base + stage * C::B_STAGE;
@@ -354,6 +377,13 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 }
                 umma_commit(acc_full(set));       // accumulators of this tile-set are final
             }
+            if (prof_on) {
+                prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
+                prof[PROF_MMA_WAIT_ACC] += w_acc;
+                prof[PROF_MMA_WAIT_A] += w_af;
+                prof[PROF_MMA_WAIT_B] += w_bf;
+                prof[PROF_TILESETS] += n;
+            }
         }
     } else {
         // ===================== epilogue warps 3..6 ====================================================
@@ -362,10 +392,12 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
         const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
         uint32_t n = 0;
+        unsigned long long w_e = 0, work_e = 0;
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
             const uint32_t set = n & 1u;
             const int ty = ts / p.tiles_x, tx = ts - ty * p.tiles_x;
-            mbar_wait(acc_full(set), (n >> 1) & 1u);
+            mbar_wait_prof(acc_full(set), (n >> 1) & 1u, prof_on, w_e);
+            const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
 #pragma unroll
             for (int j = 0; j < 2; j++) {
@@ -405,6 +437,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(set));
+            if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
+        }
+        if (prof_on && warp == 3 && lane == 0) {
+            prof[PROF_EPI_WAIT] += w_e;
+            prof[PROF_EPI_WORK] += work_e;
         }
     }
 
@@ -581,7 +618,8 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const TcParams &p, int nu
 }
 
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out, int cin,
-                            int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms, cudaStream_t s) {
+                            int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms, cudaStream_t s,
+                            unsigned long long *prof) {
     TcParams p;
     p.wpack = wpack;
     p.bias = bias;
@@ -592,6 +630,7 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, c
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale;
     p.desc_mode = desc_mode;
+    p.prof = prof;
 #define X(ci, co) \
     if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, p, num_sms, s);
     W2X_TC_SHAPES(X)
