@@ -208,6 +208,25 @@ def test_full_size_4096_properties(w2x, ctxs, models, oracle_mod, oracle_models,
     assert np.ptp(c) == 0.0
 
 
+def test_fused_and_separate_last_layer_agree(ctxs, models, oracle_mod, oracle_models, ncpu):
+    """The N->1 last layer folded into the preceding tcgen05 epilogue vs run as its own kernel."""
+    x = oracle_mod.seeded_plane(211, 97, 17, "uniform")
+    ctx = ctxs["tc"]
+    ref = oracle_models["noise1"].convert(x, n_job=ncpu)
+    fused = ctx.convert_plane(models["noise1"], x)
+    try:
+        ctx.debug_set_fuse_last(False)
+        ctx.set_timing(True)
+        sep = ctx.convert_plane(models["noise1"], x)
+        names = [t[2] for t in ctx.layer_times()]
+    finally:
+        ctx.set_timing(False)
+        ctx.debug_set_fuse_last(True)
+    assert names[-2:] == ["tcgen05_f16x3", "last_Nx1"]
+    assert np.abs(fused - ref).max() <= TC_TOL and np.abs(sep - ref).max() <= TC_TOL
+    assert np.abs(fused - sep).max() <= 5e-6
+
+
 def test_launch_counter_and_timing(ctxs, models, oracle_mod):
     ctx = ctxs["tc"]
     x = oracle_mod.seeded_plane(64, 64, 1, "uniform")
@@ -219,5 +238,5 @@ def test_launch_counter_and_timing(ctxs, models, oracle_mod):
     finally:
         ctx.set_timing(False)
     assert ctx.launch_count() - n0 == 8                        # pad + 7 layer kernels
-    assert [t[2] for t in times] == ["first_1xN"] + ["tcgen05_f16x3"] * 5 + ["last_Nx1"]
+    assert [t[2] for t in times] == ["first_1xN"] + ["tcgen05_f16x3"] * 4 + ["tcgen05_f16x3+last", "last_gather"]
     assert all(t[0] > 0 and t[1] == 1 for t in times)

@@ -97,6 +97,7 @@ def lib():
     L.w2x_ctx_layer_kernel_name.argtypes = [vp, ci]
     L.w2x_ctx_layer_kernel_name.restype = C.c_char_p
     L.w2x_debug_set_desc_mode.argtypes = [vp, ci]
+    L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_read.argtypes = [vp, ci, C.POINTER(C.c_uint64), C.POINTER(ci)]
     L.w2x_debug_tc_pack.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(cs), C.POINTER(ci), C.POINTER(ci),
@@ -224,6 +225,7 @@ class Context:
     def set_timing(self, on): _check(lib().w2x_ctx_set_timing(self._h, int(on)))
     def debug_set_desc_mode(self, mode): _check(lib().w2x_debug_set_desc_mode(self._h, mode))
 
+    def debug_set_fuse_last(self, on): _check(lib().w2x_debug_set_fuse_last(self._h, int(on)))
     def debug_tc_profile_enable(self, on=True): _check(lib().w2x_debug_tc_profile_enable(self._h, int(on)))
 
     def debug_tc_profile_read(self, layer):

@@ -33,6 +33,7 @@ struct DevModel {                       // device-resident copy of one model
     std::vector<float *> b;             // per layer [Cout] fp32  ((float)bias, src/modelHandler.cpp:147)
     std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
     std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
+    float *last_w_t = nullptr;          // last layer's weights transposed to [9][Cin] (fused last layer)
 };
 
 struct TimedSpan { int layer; cudaEvent_t e0, e1; };
@@ -46,6 +47,7 @@ struct w2x_ctx {
     int engine = W2X_ENGINE_AUTO;
     int walk = W2X_WALK_FUSED;
     int desc_mode = 0;
+    bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     size_t scratch_limit = (size_t)16 << 30;
@@ -131,6 +133,14 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
             CU_CHECK(cudaMemcpyAsync(dm.pack[i], P.bytes.data(), P.bytes.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
             dm.out_scale[i] = 1.0f / (P.wscale * tc::ACT_SCALE);
         }
+    }
+    if (m->tc_eligible) {
+        const Layer &L = m->layers.back();                // n_out == 1: w is [1][Cin][9]
+        std::vector<float> wt((size_t)9 * L.n_in);
+        for (int c = 0; c < L.n_in; c++)
+            for (int t = 0; t < 9; t++) wt[(size_t)t * L.n_in + c] = L.w[(size_t)c * 9 + t];
+        CU_CHECK(cudaMalloc(&dm.last_w_t, wt.size() * sizeof(float)));
+        CU_CHECK(cudaMemcpy(dm.last_w_t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     CU_CHECK(cudaStreamSynchronize(ctx->stream));
     auto res = ctx->models.emplace(m->uid, std::move(dm));
@@ -249,19 +259,22 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
+    const bool fuse = ctx->fuse_last && n >= 3 && dm->last_w_t != nullptr;
     for (int li = 1; li + 1 < n; li++) {
         const Layer &L = m->layers[(size_t)li];
         logf(ctx, "Iteration #%d...", li + 1);
         CUtensorMap map;
         int e = tc::make_act_tensor_map(&map, cur, L.n_in, pw, ph);
         if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, li);
+        const bool fused_here = fuse && li == n - 2;
         {
             LayerTimer t(ctx, li);
             CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)li], dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph,
                                          dm->out_scale[(size_t)li], ctx->desc_mode, ctx->num_sms, ctx->stream,
-                                         ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr));
+                                         ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
+                                         fused_here ? dm->last_w_t : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr));
         }
-        note_kernel(ctx, li, "tcgen05_f16x3");
+        note_kernel(ctx, li, fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
         ctx->launches++;
         std::swap(cur, nxt);
     }
@@ -269,9 +282,15 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         const Layer &L = m->layers[(size_t)n - 1];
         logf(ctx, "Iteration #%d...", n);
         LayerTimer t(ctx, n - 1);
-        CU_CHECK(tc::launch_last(cur, L.n_in, pw, ph, dm->w[(size_t)n - 1], static_cast<float>(L.b[0]), n, dst,
-                                 dst_stride, ctx->stream));
-        note_kernel(ctx, n - 1, "last_Nx1");
+        if (fuse) {
+            CU_CHECK(tc::launch_last_gather(reinterpret_cast<const float *>(cur), pw, ph, static_cast<float>(L.b[0]), n, dst,
+                                            dst_stride, ctx->stream));
+            note_kernel(ctx, n - 1, "last_gather");
+        } else {
+            CU_CHECK(tc::launch_last(cur, L.n_in, pw, ph, dm->w[(size_t)n - 1], static_cast<float>(L.b[0]), n, dst,
+                                     dst_stride, ctx->stream));
+            note_kernel(ctx, n - 1, "last_Nx1");
+        }
         ctx->launches++;
     }
     return W2X_OK;
@@ -391,6 +410,7 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
         for (auto p : kv.second.w) cudaFree(p);
         for (auto p : kv.second.b) cudaFree(p);
         for (auto p : kv.second.pack) cudaFree(p);
+        cudaFree(kv.second.last_w_t);
     }
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->buf[i]);
@@ -476,6 +496,13 @@ W2X_API int w2x_debug_tc_profile_read(w2x_ctx *ctx, int layer, unsigned long lon
         for (int w = 0; w < tc::PROF_WORDS; w++) out[w] += h[(size_t)c * tc::PROF_WORDS + w];
     }
     if (n_ctas) *n_ctas = n;
+    return W2X_OK;
+}
+
+// Probe switch (not part of the stable ABI): 1 = fold the last layer into the preceding tcgen05 layer (default), 0 = separate kernel.
+W2X_API int w2x_debug_set_fuse_last(w2x_ctx *ctx, int on) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->fuse_last = on != 0;
     return W2X_OK;
 }
 

@@ -37,7 +37,14 @@ cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph,
 // tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out,
                             int cin, int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms,
-                            cudaStream_t s, unsigned long long *prof = nullptr);
+                            cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
+                            float *partial = nullptr);
+// Fused last layer: launch_tc_layer(..., last_w = [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
+// tcgen05 layer emit per-pixel tap partials instead of activations; launch_last_gather sums the 3x3
+// neighbourhood of partials, adds the bias, applies the leaky-ReLU and writes the cropped fp32 plane.
+cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias, int crop, float *dst,
+                               long dst_stride_floats, cudaStream_t s);
+inline size_t partial_bytes(int Wp, int Hp) { return (size_t)Hp * Wp * 12 * sizeof(float); }
 constexpr int PROF_WORDS = 16;      // per-CTA profile record (see kernels_tc.cu PROF_*)
 constexpr int PROF_MAX_CTAS = 256;
 // Last layer (Cout = 1): NHWC hi/lo frame -> fp32 plane, interior only: out(y,x) for

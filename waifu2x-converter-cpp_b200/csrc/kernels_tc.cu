@@ -156,6 +156,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
     return d;
 }
 
+// Everything of a descriptor except the start address (compile-time part).
+__host__ __device__ constexpr uint64_t make_desc_const(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((uint64_t)1u << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1u << 46) |
+           ((uint64_t)(layout_type & 7u) << 61);
+}
+
 // Instruction descriptor (UMMA::InstrDescriptor): c_format F32 (1) at [4,6), a/b format F16 (0) at
 // [7,10)/[10,13), a/b major K (0) at 15/16, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -165,7 +171,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 // Per-layer configuration
 // ================================================================================================
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FUSE = false>
 struct Cfg {
     static constexpr int KC = CIN < 64 ? CIN : 64;      // channels per K chunk
     static constexpr int NCHUNK = CIN / KC;
@@ -178,10 +184,11 @@ struct Cfg {
     static constexpr int A_SLOTS = 2;
     static constexpr int B_STAGE = COUT * ROWB;                              // one (chunk, tap, hi|lo) tile
     static constexpr int BAR_BYTES = 1024;
+    static constexpr int W6_BYTES = FUSE ? 9 * COUT * 4 : 0;                 // fused last layer: its [tap][c] fp32 weights
     static constexpr int SMEM_MAX = 227 * 1024;
-    static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
+    static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
     static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
-    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES + W6_BYTES;
     static constexpr int ACC_COLS = 4 * COUT;                                // 2 sets x 2 M-tiles
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static_assert(NB >= 2, "need at least two weight stages");
@@ -202,6 +209,10 @@ struct TcParams {
     float out_scale;         // 1 / (wscale * ACT_SCALE)
     int desc_mode;           // 0: base_offset = 0 ; 1: base_offset = (start >> 7) & 7  (probe)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
+    // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
+    // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
+    const float *last_w;        // [9][COUT]  (tap-major)
+    float *partial;
 };
 
 // per-CTA profile record (cycles, accumulated over launches)
@@ -221,10 +232,10 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // ================================================================================================
 // The layer kernel
 // ================================================================================================
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool FUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p) {
-    using C = Cfg<CIN, COUT>;
+    using C = Cfg<CIN, COUT, FUSE>;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: swizzle patterns repeat every 1024 B (SWIZZLE_128B) / 512 B (SWIZZLE_64B)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -243,6 +254,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));   // COUT floats
     for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
+    const float *s_w6 = reinterpret_cast<const float *>(smem_raw + (bar_base + C::BAR_BYTES - smem_u32(smem_raw)));   // [9][COUT]
+    if constexpr (FUSE) {
+        float *w6 = const_cast<float *>(s_w6);
+        for (int i = threadIdx.x; i < 9 * COUT; i += NUM_THREADS) w6[i] = p.last_w[i];
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
@@ -309,11 +325,20 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) ============================================
-        if (lane == 0) {
+        // ===================== MMA issuer: the whole warp walks the loop (keeps every operand warp-uniform,
+        // i.e. in uniform registers), one elected lane issues tcgen05.mma / tcgen05.commit ==================
+        {
+            const bool leader = lane == 0;
             constexpr uint32_t idesc = make_idesc(128, COUT);
             constexpr uint32_t A_SBO = HALO * C::ROWB;   // next output row = next halo row
             constexpr uint32_t B_SBO = 8 * C::ROWB;      // dense rows
+            // Only the 14-bit start-address field of a descriptor changes between MMAs: keep the upper
+            // words constant and derive the lower word with one integer add per operand (the issue loop
+            // is a single thread -- every instruction here is on the tensor pipe's critical path).
+            constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::LAYOUT) >> 32);
+            constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::LAYOUT) >> 32);
+            constexpr uint32_t LO_FIXED = 1u << 16;      // LBO field = 1
+            auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
             uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
             unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
             const long long t_begin = clock64();
@@ -321,63 +346,61 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 const uint32_t set = n & 1u;
                 mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (set * 2u) * COUT;
+                const uint32_t d0 = tmem_base + (set * 2u) * COUT, d1 = d0 + COUT;
                 for (int c = 0; c < C::NCHUNK; c++, a_it++) {
                     const uint32_t slot = a_it & 1u;
                     mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                     tc_fence_after();
-                    const uint32_t a_hi = a_base + slot * C::A_SLOT, a_lo = a_hi + C::A_PLANE_PAD;
+                    // descriptor low words (address >> 4) of the hi / lo activation planes of this slot
+                    const uint32_t ah0 = (((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED;
+                    const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
+                    uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
                     for (int t = 0; t < 9; t++) {
-                        const int ky = t / 3, kx = t - 3 * ky;
                         // ---- hi weights: xh*wh and xl*wh ----
                         mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                         tc_fence_after();
-                        {
-                            const uint32_t bs = b_base + stage * C::B_STAGE;
+                        if (leader) {
+                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            const uint32_t ah = ah0 + tap_off, al = al0 + tap_off;
+                            const uint32_t first = (c | t) != 0 ? 1u : 0u;
 #pragma unroll
-                            for (int j = 0; j < 2; j++) {
-                                const uint32_t aoff = (uint32_t)((ky * HALO + 8 * j + kx) * C::ROWB);
-#pragma unroll
-                                for (int part = 0; part < 2; part++) {
-                                    const uint32_t ab = (part ? a_lo : a_hi) + aoff;
-#pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        const uint32_t aa = ab + 32u * s;
-                                        const uint64_t ad = make_desc(aa, A_SBO, C::LAYOUT, p.desc_mode ? (aa >> 7) : 0u);
-                                        const uint64_t bd = make_desc(bs + 32u * s, B_SBO, C::LAYOUT, 0u);
-                                        const uint32_t accum = (c | t | part | s) != 0 ? 1u : 0u;
-                                        umma_f16(d0 + (uint32_t)j * COUT, ad, bd, idesc, accum);
-                                    }
-                                }
+                            for (int s = 0; s < C::KSTEPS; s++) {
+                                umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
+                                umma_f16(d1, desc(A_HI32, ah + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
                             }
+#pragma unroll
+                            for (int s = 0; s < C::KSTEPS; s++) {
+                                umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                umma_f16(d1, desc(A_HI32, al + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                            }
+                            umma_commit(b_empty(stage));
                         }
-                        umma_commit(b_empty(stage));
+                        __syncwarp();
                         if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         // ---- lo weights: xh*wl ----
                         mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                         tc_fence_after();
-                        {
-                            const uint32_t bs = b_base + stage * C::B_STAGE;
+                        if (leader) {
+                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            const uint32_t ah = ah0 + tap_off;
 #pragma unroll
-                            for (int j = 0; j < 2; j++) {
-                                const uint32_t ab = a_hi + (uint32_t)((ky * HALO + 8 * j + kx) * C::ROWB);
-#pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    const uint32_t aa = ab + 32u * s;
-                                    const uint64_t ad = make_desc(aa, A_SBO, C::LAYOUT, p.desc_mode ? (aa >> 7) : 0u);
-                                    const uint64_t bd = make_desc(bs + 32u * s, B_SBO, C::LAYOUT, 0u);
-                                    umma_f16(d0 + (uint32_t)j * COUT, ad, bd, idesc, 1u);
-                                }
+                            for (int s = 0; s < C::KSTEPS; s++) {
+                                umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                umma_f16(d1, desc(A_HI32, ah + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
                             }
+                            umma_commit(b_empty(stage));
                         }
-                        umma_commit(b_empty(stage));
+                        __syncwarp();
                         if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                        // next tap: kx+1, or the next halo row
+                        tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                     }
-                    umma_commit(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
+                    if (leader) umma_commit(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
                 }
-                umma_commit(acc_full(set));       // accumulators of this tile-set are final
+                if (leader) umma_commit(acc_full(set));       // accumulators of this tile-set are final
+                __syncwarp();
             }
-            if (prof_on) {
+            if (prof_on && leader) {
                 prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
                 prof[PROF_MMA_WAIT_ACC] += w_acc;
                 prof[PROF_MMA_WAIT_A] += w_af;
@@ -403,34 +426,70 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             for (int j = 0; j < 2; j++) {
                 const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
                 const bool inside = fy < p.Hp && fx < p.Wp;
-                __half *dst_hi = p.out + ((size_t)fy * p.Wp + fx) * COUT;
-                __half *dst_lo = dst_hi + plane_elems;
+                if constexpr (!FUSE) {
+                    __half *dst_hi = p.out + ((size_t)fy * p.Wp + fx) * COUT;
+                    __half *dst_lo = dst_hi + plane_elems;
 #pragma unroll
-                for (int cb = 0; cb < COUT / 32; cb++) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * COUT + (uint32_t)cb * 32u, r);
-                    tmem_ld_wait();
-                    uint32_t hi[16], lo[16];
+                    for (int cb = 0; cb < COUT / 32; cb++) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * COUT + (uint32_t)cb * 32u, r);
+                        tmem_ld_wait();
+                        uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        float v0 = fmaf(__uint_as_float(r[2 * i]), p.out_scale, s_bias[cb * 32 + 2 * i]);
-                        float v1 = fmaf(__uint_as_float(r[2 * i + 1]), p.out_scale, s_bias[cb * 32 + 2 * i + 1]);
-                        v0 = (fminf(v0, 0.f) * 0.1f + fmaxf(v0, 0.f)) * ACT_SCALE;
-                        v1 = (fminf(v1, 0.f) * 0.1f + fmaxf(v1, 0.f)) * ACT_SCALE;
-                        __half2 h = __floats2half2_rn(v0, v1);
-                        float2 hf = __half22float2(h);
-                        __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                        hi[i] = *reinterpret_cast<uint32_t *>(&h);
-                        lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                        for (int i = 0; i < 16; i++) {
+                            float v0 = fmaf(__uint_as_float(r[2 * i]), p.out_scale, s_bias[cb * 32 + 2 * i]);
+                            float v1 = fmaf(__uint_as_float(r[2 * i + 1]), p.out_scale, s_bias[cb * 32 + 2 * i + 1]);
+                            v0 = (fminf(v0, 0.f) * 0.1f + fmaxf(v0, 0.f)) * ACT_SCALE;
+                            v1 = (fminf(v1, 0.f) * 0.1f + fmaxf(v1, 0.f)) * ACT_SCALE;
+                            __half2 h = __floats2half2_rn(v0, v1);
+                            float2 hf = __half22float2(h);
+                            __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+                            lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                        }
+                        if (inside) {
+                            uint4 *ph = reinterpret_cast<uint4 *>(dst_hi + cb * 32);
+                            uint4 *pl = reinterpret_cast<uint4 *>(dst_lo + cb * 32);
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
+                                pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                            }
+                        }
+                    }
+                } else {
+                    // last layer folded in: nine per-tap dot products of this pixel's fp32 activations
+                    float pt[9];
+#pragma unroll
+                    for (int t = 0; t < 9; t++) pt[t] = 0.f;
+#pragma unroll
+                    for (int cb = 0; cb < COUT / 32; cb++) {
+                        uint32_t r[32];
+                        tmem_ld32(tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * COUT + (uint32_t)cb * 32u, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 8; g++) {
+                            float a[4];
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                float v = fmaf(__uint_as_float(r[4 * g + e]), p.out_scale, s_bias[cb * 32 + 4 * g + e]);
+                                a[e] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
+                            }
+#pragma unroll
+                            for (int t = 0; t < 9; t++) {
+                                const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
+                                pt[t] = fmaf(a[0], w.x, pt[t]);
+                                pt[t] = fmaf(a[1], w.y, pt[t]);
+                                pt[t] = fmaf(a[2], w.z, pt[t]);
+                                pt[t] = fmaf(a[3], w.w, pt[t]);
+                            }
+                        }
                     }
                     if (inside) {
-                        uint4 *ph = reinterpret_cast<uint4 *>(dst_hi + cb * 32);
-                        uint4 *pl = reinterpret_cast<uint4 *>(dst_lo + cb * 32);
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                            pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
-                        }
+                        float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)fy * p.Wp + fx) * 12);
+                        dst[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
+                        dst[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
+                        dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -547,6 +606,23 @@ last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__
     dst[(long)(y - crop) * dst_stride + (x - crop)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
 }
 
+// Second half of the fused last layer: out(y,x) = leaky(bias + sum_t P[(y+ky-1, x+kx-1)][t]), taps in
+// row-major order, for the interior [crop, ph-crop) x [crop, pw-crop).
+__global__ void __launch_bounds__(256)
+last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias, int crop, float *__restrict__ dst,
+                   long dst_stride) {
+    const int x = crop + blockIdx.x * 32 + (threadIdx.x & 31), y = crop + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw - crop || y >= ph - crop) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++)
+            acc += __ldg(partial + ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * 12 + ky * 3 + kx);
+    const float r = acc + bias;
+    dst[(long)(y - crop) * dst_stride + (x - crop)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
+}
+
 __global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out) {
     const int pw = w + 2, ph = h + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,8 +662,11 @@ bool layer_supported(int cin, int cout) {
 
 template <int CIN, int COUT>
 static cudaError_t set_attr() {
-    return cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<CIN, COUT>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<CIN, COUT, false>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<CIN, COUT, true>::SMEM_BYTES);
 }
 
 #define W2X_TC_SHAPES(X) \
@@ -595,7 +674,7 @@ static cudaError_t set_attr() {
 
 size_t layer_smem_bytes(int cin, int cout) {
 #define X(ci, co) \
-    if (cin == ci && cout == co) return Cfg<ci, co>::SMEM_BYTES;
+    if (cin == ci && cout == co) return Cfg<ci, co, true>::SMEM_BYTES;
     W2X_TC_SHAPES(X)
 #undef X
     return 0;
@@ -613,13 +692,16 @@ cudaError_t init_kernels() {
 template <int CIN, int COUT>
 static cudaError_t launch_one(const CUtensorMap *tmap, const TcParams &p, int num_sms, cudaStream_t s) {
     int grid = p.n_tilesets < num_sms ? p.n_tilesets : num_sms;
-    tc_conv3x3_kernel<CIN, COUT><<<grid, NUM_THREADS, Cfg<CIN, COUT>::SMEM_BYTES, s>>>(*tmap, p);
+    if (p.partial)
+        tc_conv3x3_kernel<CIN, COUT, true><<<grid, NUM_THREADS, Cfg<CIN, COUT, true>::SMEM_BYTES, s>>>(*tmap, p);
+    else
+        tc_conv3x3_kernel<CIN, COUT, false><<<grid, NUM_THREADS, Cfg<CIN, COUT, false>::SMEM_BYTES, s>>>(*tmap, p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms, cudaStream_t s,
-                            unsigned long long *prof) {
+                            unsigned long long *prof, const float *last_w, float *partial) {
     TcParams p;
     p.wpack = wpack;
     p.bias = bias;
@@ -631,6 +713,8 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, c
     p.out_scale = out_scale;
     p.desc_mode = desc_mode;
     p.prof = prof;
+    p.last_w = last_w;
+    p.partial = partial;
 #define X(ci, co) \
     if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, p, num_sms, s);
     W2X_TC_SHAPES(X)
@@ -663,6 +747,16 @@ cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *
         case 128: last_layer_kernel<128><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias, int crop, float *dst,
+                               long dst_stride_floats, cudaStream_t s) {
+    const int ow = pw - 2 * crop, oh = ph - 2 * crop;
+    if (ow < 1 || oh < 1 || crop < 1) return cudaErrorInvalidValue;
+    dim3 grid((ow + 31) / 32, (oh + 7) / 8);
+    if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+    last_gather_kernel<<<grid, 256, 0, s>>>(partial, pw, ph, bias, crop, dst, dst_stride_floats);
     return cudaGetLastError();
 }
 
