@@ -1,6 +1,6 @@
 """gpu_probe.py -- first-contact diagnostics on a B200 (run under gpurun; writes to stdout).
 
-For each engine and each UMMA descriptor policy, runs per-layer Model::filter and the whole path on
+For each engine and each MMA issue variant, runs per-layer Model::filter and the whole path on
 small inputs and prints the max-abs error against the CPU oracle.  Each tcgen05 trial runs in its
 own subprocess with a timeout, so a trapped/hung kernel cannot take the whole probe down."""
 import json
@@ -19,11 +19,11 @@ sys.path.insert(0, %(root)r)
 import w2x_loader
 from oracle import oracle
 w2x = w2x_loader.load()
-engine, desc_mode, what = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+engine, mma_mode, what = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 om = oracle.OracleModel.golden("scale2.0x")
 m = w2x.Model.from_arrays(om.weights, om.biases)
 ctx = w2x.Context(0, engine=engine)
-ctx.debug_set_desc_mode(desc_mode)
+ctx.debug_set_mma_mode(mma_mode)
 res = {}
 if what == "layers":
     z = np.load(%(root)r + "/tests/golden/layers_32x24.npz")
@@ -35,34 +35,33 @@ if what == "layers":
 else:
     n = int(what)
     x = oracle.seeded_plane(n, n, 0, "uniform")
-    t = time.time(); y = ctx.convert_plane(m, x); dt = time.time() - t
+    y = ctx.convert_plane(m, x)
+    ctx.set_timing(True)
     t = time.time(); y = ctx.convert_plane(m, x); dt2 = time.time() - t
+    layer_ms = [round(v[0], 3) for v in ctx.layer_times()]
     ref = om.convert(x, n_job=16) if n <= 512 else None
-    res["convert%%d" %% n] = {"err": None if ref is None else float(np.abs(y - ref).max()), "first_s": dt, "second_s": dt2,
-                             "finite": bool(np.isfinite(y).all())}
+    res["convert%%d" %% n] = {"err": None if ref is None else float(np.abs(y - ref).max()), "second_s": round(dt2, 4),
+                             "layer_ms": layer_ms, "finite": bool(np.isfinite(y).all())}
 print("RESULT " + json.dumps(res))
 '''
 
 
-def run(engine, desc_mode, what, timeout=120):
+def run(engine, mma_mode, what, timeout=120):
     code = CHILD % {"root": ROOT}
     t = time.time()
     try:
-        p = subprocess.run([sys.executable, "-c", code, str(engine), str(desc_mode), what], capture_output=True, text=True, timeout=timeout)
+        p = subprocess.run([sys.executable, "-c", code, str(engine), str(mma_mode), what], capture_output=True, text=True, timeout=timeout)
         tail = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
         out = tail[-1][7:] if tail else ("rc=%d stderr=%s" % (p.returncode, p.stderr[-600:]))
     except subprocess.TimeoutExpired:
         out = "TIMEOUT"
-    print(f"engine={engine} desc_mode={desc_mode} what={what} ({time.time() - t:.1f}s): {out}", flush=True)
+    print(f"engine={engine} mma_mode={mma_mode} what={what} ({time.time() - t:.1f}s): {out}", flush=True)
 
 
 if __name__ == "__main__":
     subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total", "--format=csv"])
-    run(1, 0, "layers")
-    run(1, 0, "256")
-    for dm in (0, 1):
-        run(2, dm, "layers")
-        run(2, dm, "256")
-    run(1, 0, "2048")
-    run(2, 0, "2048")
-    run(2, 0, "4096")
+    modes = [int(a) for a in sys.argv[1:]] or [0, 1, 2]
+    for mode in modes:
+        run(2, mode, "layers")
+        run(2, mode, "256")
+        run(2, mode, "4096")

@@ -96,7 +96,7 @@ def lib():
     L.w2x_ctx_layer_times.argtypes = [vp, ci, fp, C.POINTER(ci), C.POINTER(ci), ci]
     L.w2x_ctx_layer_kernel_name.argtypes = [vp, ci]
     L.w2x_ctx_layer_kernel_name.restype = C.c_char_p
-    L.w2x_debug_set_desc_mode.argtypes = [vp, ci]
+    L.w2x_debug_set_mma_mode.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_read.argtypes = [vp, ci, C.POINTER(C.c_uint64), C.POINTER(ci)]
@@ -223,7 +223,7 @@ class Context:
     def set_block_walk(self, mode): _check(lib().w2x_ctx_set_block_walk(self._h, mode))
     def set_scratch_limit(self, nbytes): _check(lib().w2x_ctx_set_scratch_limit(self._h, nbytes))
     def set_timing(self, on): _check(lib().w2x_ctx_set_timing(self._h, int(on)))
-    def debug_set_desc_mode(self, mode): _check(lib().w2x_debug_set_desc_mode(self._h, mode))
+    def debug_set_mma_mode(self, mode): _check(lib().w2x_debug_set_mma_mode(self._h, mode))
 
     def debug_set_fuse_last(self, on): _check(lib().w2x_debug_set_fuse_last(self._h, int(on)))
     def debug_tc_profile_enable(self, on=True): _check(lib().w2x_debug_tc_profile_enable(self._h, int(on)))

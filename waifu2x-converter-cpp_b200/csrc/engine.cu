@@ -506,8 +506,9 @@ W2X_API int w2x_debug_set_fuse_last(w2x_ctx *ctx, int on) {
     return W2X_OK;
 }
 
-// Probe switch (not part of the stable ABI): UMMA descriptor base_offset policy of the tcgen05 engine.
-W2X_API int w2x_debug_set_desc_mode(w2x_ctx *ctx, int mode) {
+// Probe switch (not part of the stable ABI): MMA issue variant of the tcgen05 engine
+// (0 plain, 1 A-collector reuse, 2 weight-stationary .ws with B-collector reuse).
+W2X_API int w2x_debug_set_mma_mode(w2x_ctx *ctx, int mode) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
     ctx->desc_mode = mode;
     return W2X_OK;

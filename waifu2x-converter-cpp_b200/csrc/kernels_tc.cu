@@ -115,6 +115,23 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+// Variants with operand-collector hints (SASS: UTCHMMA gdesc.A_KEEP/.A_REUSE, UTCHMMA.WS gdesc.B_KEEP/.B_REUSE):
+//   collector::a::fill / lastuse   keep the A operand in the tensor core's collector for the next MMA
+//   .ws + collector::b0::*         weight-stationary form: the B operand stays resident across MMAs
+#define W2X_UMMA_VARIANT(NAME, OPCODE)                                                                        \
+    __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,      \
+                                         uint32_t accum) {                                                     \
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" OPCODE " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), \
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)                                            \
+                     : "memory");                                                                              \
+    }
+W2X_UMMA_VARIANT(umma_f16_a_fill, "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill")
+W2X_UMMA_VARIANT(umma_f16_a_last, "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse")
+W2X_UMMA_VARIANT(umma_f16_ws_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill")
+W2X_UMMA_VARIANT(umma_f16_ws_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use")
+W2X_UMMA_VARIANT(umma_f16_ws_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse")
+#undef W2X_UMMA_VARIANT
+
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -133,6 +150,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // ================================================================================================
 // Descriptors
@@ -185,10 +211,11 @@ struct Cfg {
     static constexpr int B_STAGE = COUT * ROWB;                              // one (chunk, tap, hi|lo) tile
     static constexpr int BAR_BYTES = 1024;
     static constexpr int W6_BYTES = FUSE ? 9 * COUT * 4 : 0;                 // fused last layer: its [tap][c] fp32 weights
+    static constexpr int STG_BYTES = FUSE ? 0 : 4 * 2048;                    // epilogue store staging, 2 KB per warp
     static constexpr int SMEM_MAX = 227 * 1024;
-    static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
+    static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
     static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
-    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES + W6_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES + W6_BYTES + STG_BYTES;
     static constexpr int ACC_COLS = 4 * COUT;                                // 2 sets x 2 M-tiles
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     static_assert(NB >= 2, "need at least two weight stages");
@@ -207,7 +234,7 @@ struct TcParams {
     int Wp, Hp;
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / (wscale * ACT_SCALE)
-    int desc_mode;           // 0: base_offset = 0 ; 1: base_offset = (start >> 7) & 7  (probe)
+    int mma_mode;            // 0 plain; 1 A-collector reuse (xh*wh, xh*wl back to back); 2 weight-stationary (.ws, B collector)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
@@ -356,42 +383,92 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                     const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
                     uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
                     for (int t = 0; t < 9; t++) {
-                        // ---- hi weights: xh*wh and xl*wh ----
-                        mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-                        tc_fence_after();
-                        if (leader) {
-                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                            const uint32_t ah = ah0 + tap_off, al = al0 + tap_off;
-                            const uint32_t first = (c | t) != 0 ? 1u : 0u;
+                        const uint32_t ah = ah0 + tap_off, al = al0 + tap_off;
+                        const uint32_t first = (c | t) != 0 ? 1u : 0u;
+                        constexpr uint32_t J1 = 8u * C::ROWB >> 4;     // second M-tile: 8 pixels to the right
+                        if (p.mma_mode == 1) {
+                            // ---- A-collector reuse: both weight stages resident; xh slice read once for wh and wl ----
+                            const uint32_t st_h = stage, ph_h = phase;
+                            uint32_t st_l = stage + 1, ph_l = phase;
+                            if (st_l == (uint32_t)C::NB) { st_l = 0; ph_l ^= 1u; }
+                            mbar_wait_prof(b_full(st_h), ph_h, prof_on, w_bf);
+                            mbar_wait_prof(b_full(st_l), ph_l, prof_on, w_bf);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t bh = (((b_base + st_h * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                                const uint32_t bl = (((b_base + st_l * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
 #pragma unroll
-                            for (int s = 0; s < C::KSTEPS; s++) {
-                                umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                                umma_f16(d1, desc(A_HI32, ah + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                            }
+                                for (int s = 0; s < C::KSTEPS; s++) {
+                                    umma_f16_a_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first);
+                                    umma_f16_a_last(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u);
+                                    umma_f16_a_fill(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first);
+                                    umma_f16_a_last(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u);
+                                }
 #pragma unroll
-                            for (int s = 0; s < C::KSTEPS; s++) {
-                                umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                umma_f16(d1, desc(A_HI32, al + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                for (int s = 0; s < C::KSTEPS; s++) {
+                                    umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u);
+                                    umma_f16(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u);
+                                }
+                                umma_commit(b_empty(st_h));
+                                umma_commit(b_empty(st_l));
                             }
-                            umma_commit(b_empty(stage));
+                            __syncwarp();
+                            stage = st_l; phase = ph_l;
+                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                        } else {
+                            // ---- hi weights: xh*wh and xl*wh ----
+                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                                if (p.mma_mode == 2) {
+                                    // weight-stationary: each 16-channel weight slice is fetched once for the four MMAs using it
+#pragma unroll
+                                    for (int s = 0; s < C::KSTEPS; s++) {
+                                        umma_f16_ws_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
+                                        umma_f16_ws_use(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
+                                        umma_f16_ws_use(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                        umma_f16_ws_last(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int s = 0; s < C::KSTEPS; s++) {
+                                        umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
+                                        umma_f16(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
+                                    }
+#pragma unroll
+                                    for (int s = 0; s < C::KSTEPS; s++) {
+                                        umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                        umma_f16(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                    }
+                                }
+                                umma_commit(b_empty(stage));
+                            }
+                            __syncwarp();
+                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                            // ---- lo weights: xh*wl ----
+                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                                if (p.mma_mode == 2) {
+#pragma unroll
+                                    for (int s = 0; s < C::KSTEPS; s++) {
+                                        umma_f16_ws_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                        umma_f16_ws_last(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int s = 0; s < C::KSTEPS; s++) {
+                                        umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                        umma_f16(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
+                                    }
+                                }
+                                umma_commit(b_empty(stage));
+                            }
+                            __syncwarp();
+                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
-                        // ---- lo weights: xh*wl ----
-                        mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-                        tc_fence_after();
-                        if (leader) {
-                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                            const uint32_t ah = ah0 + tap_off;
-#pragma unroll
-                            for (int s = 0; s < C::KSTEPS; s++) {
-                                umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                umma_f16(d1, desc(A_HI32, ah + (8u * C::ROWB >> 4) + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                            }
-                            umma_commit(b_empty(stage));
-                        }
-                        __syncwarp();
-                        if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         // next tap: kx+1, or the next halo row
                         tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                     }
@@ -414,6 +491,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         const uint32_t row = q * 32u + (uint32_t)lane;   // GEMM row = pixel inside the 8x16 M-tile
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
         const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
+        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + q * 2048u;   // this warp's staging tile (non-FUSE only)
         uint32_t n = 0;
         unsigned long long w_e = 0, work_e = 0;
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
@@ -427,8 +505,6 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
                 const bool inside = fy < p.Hp && fx < p.Wp;
                 if constexpr (!FUSE) {
-                    __half *dst_hi = p.out + ((size_t)fy * p.Wp + fx) * COUT;
-                    __half *dst_lo = dst_hi + plane_elems;
 #pragma unroll
                     for (int cb = 0; cb < COUT / 32; cb++) {
                         uint32_t r[32];
@@ -447,14 +523,28 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                             hi[i] = *reinterpret_cast<uint32_t *>(&h);
                             lo[i] = *reinterpret_cast<uint32_t *>(&l);
                         }
-                        if (inside) {
-                            uint4 *ph = reinterpret_cast<uint4 *>(dst_hi + cb * 32);
-                            uint4 *pl = reinterpret_cast<uint4 *>(dst_lo + cb * 32);
+                        // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
+                        // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
+                        // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
 #pragma unroll
-                            for (int v = 0; v < 4; v++) {
-                                ph[v] = make_uint4(hi[4 * v], hi[4 * v + 1], hi[4 * v + 2], hi[4 * v + 3]);
-                                pl[v] = make_uint4(lo[4 * v], lo[4 * v + 1], lo[4 * v + 2], lo[4 * v + 3]);
+                        for (int plane = 0; plane < 2; plane++) {
+                            const uint32_t *src = plane ? lo : hi;
+#pragma unroll
+                            for (int v = 0; v < 4; v++)
+                                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+                            __syncwarp();
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+                                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+                                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+                                if (gy < p.Hp && gx < p.Wp) {
+                                    __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
+                                    *reinterpret_cast<uint4 *>(dst) = val;
+                                }
                             }
+                            __syncwarp();
                         }
                     }
                 } else {
@@ -711,7 +801,7 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, c
     p.tiles_x = (pw + REGION - 1) / REGION;
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale;
-    p.desc_mode = desc_mode;
+    p.mma_mode = desc_mode;
     p.prof = prof;
     p.last_w = last_w;
     p.partial = partial;
