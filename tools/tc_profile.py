@@ -20,13 +20,18 @@ om = oracle.OracleModel.golden("scale2.0x")
 m = w2x.Model.from_arrays(om.weights, om.biases)
 ctx = w2x.Context(0, engine=w2x.ENGINE_TC)
 x = oracle.seeded_plane(size, size, 1, "uniform")
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+ctx.debug_set_mma_mode(mode)
 ctx.convert_plane(m, x)
 ctx.convert_plane(m, x)
 ctx.set_timing(True)
+ctx.convert_plane(m, x)
+clean = ctx.layer_times()
+print(f"size {size}x{size} mma_mode {mode}; per-layer ms without counters:", [round(t[0], 3) for t in clean], "sum", round(sum(t[0] for t in clean), 3))
 ctx.debug_tc_profile_enable(True)
 ctx.convert_plane(m, x)
 times = ctx.layer_times()
-print(f"size {size}x{size}; per-layer ms:", [round(t[0], 3) for t in times])
+print(f"per-layer ms with counters:", [round(t[0], 3) for t in times])
 print("layer  ms     cyc/tileset  mma_wait_acc  mma_wait_a  mma_wait_b  issue+other | aprod_wait bprod_wait | epi_wait epi_work  (cycles per tile-set, per-CTA average)")
 for li in range(1, 6):
     d = ctx.debug_tc_profile_read(li)

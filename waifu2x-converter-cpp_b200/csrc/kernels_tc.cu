@@ -105,32 +105,26 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// Variants with operand-collector hints (SASS: UTCHMMA gdesc.A_KEEP/.A_REUSE, UTCHMMA.WS gdesc.B_KEEP/.B_REUSE):
-//   collector::a::fill / lastuse   keep the A operand in the tensor core's collector for the next MMA
-//   .ws + collector::b0::*         weight-stationary form: the B operand stays resident across MMAs
+// All tcgen05.mma wrappers take an `issue` flag and predicate the instruction inside the asm block instead of
+// sitting under a divergent `if (lane == 0)`: with uniform control flow ptxas keeps the descriptors in uniform
+// registers, without a per-MMA R2UR waterfall (the issue loop is on the tensor pipe's critical path).
 #define W2X_UMMA_VARIANT(NAME, OPCODE)                                                                        \
     __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,      \
-                                         uint32_t accum) {                                                     \
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t" OPCODE " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), \
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)                                            \
+                                         uint32_t accum, uint32_t issue) {                                     \
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q " OPCODE      \
+                     " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),                                                \
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(issue)                                \
                      : "memory");                                                                              \
     }
+W2X_UMMA_VARIANT(umma_f16, "tcgen05.mma.cta_group::1.kind::f16")
+// operand-collector hints (SASS: UTCHMMA gdesc.A_KEEP / .A_REUSE): keep the A operand in the tensor core's
+// collector for the next MMA that uses the same activation slice
 W2X_UMMA_VARIANT(umma_f16_a_fill, "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill")
 W2X_UMMA_VARIANT(umma_f16_a_last, "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse")
-W2X_UMMA_VARIANT(umma_f16_ws_fill, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill")
-W2X_UMMA_VARIANT(umma_f16_ws_use, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use")
-W2X_UMMA_VARIANT(umma_f16_ws_last, "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse")
 #undef W2X_UMMA_VARIANT
+__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t issue) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue) : "memory");
+}
 
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -225,7 +219,7 @@ struct Cfg {
     static_assert(CIN % KC == 0 && KC % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "shape");
 };
 
-constexpr int NUM_THREADS = 7 * 32;
+constexpr int NUM_THREADS = 8 * 32;   // warps: 0 A producer, 1 + 7 MMA issuers (one M-tile each), 2 B producer, 3-6 epilogue
 
 struct TcParams {
     const uint16_t *wpack;   // [chunk][tap][hi|lo][COUT x ROWB bytes], pre-swizzled
@@ -234,7 +228,7 @@ struct TcParams {
     int Wp, Hp;
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / (wscale * ACT_SCALE)
-    int mma_mode;            // 0 plain; 1 A-collector reuse (xh*wh, xh*wl back to back); 2 weight-stationary (.ws, B collector)
+    int mma_mode;            // 0 plain; 1 A-collector reuse (xh*wh, xh*wl back to back on one fetched activation slice)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
@@ -294,13 +288,13 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(a_full(i), 1);
-            mbar_init(a_empty(i), 1);
-            mbar_init(acc_full(i), 1);
+            mbar_init(a_empty(i), 2);     // one tcgen05.commit per MMA issuer
+            mbar_init(acc_full(i), 2);
             mbar_init(acc_empty(i), 4);   // one arrive per epilogue warp
         }
         for (int i = 0; i < C::NB; i++) {
             mbar_init(b_full(i), 1);
-            mbar_init(b_empty(i), 1);
+            mbar_init(b_empty(i), 2);
         }
         fence_barrier_init();
         fence_proxy_async();
@@ -351,11 +345,12 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             }
             if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer: the whole warp walks the loop (keeps every operand warp-uniform,
+    } else if (warp == 1 || warp == 7) {
+        // ===================== MMA issuers (warp 1: M-tile 0, warp 7: M-tile 1): the whole warp walks the loop (keeps every operand warp-uniform,
         // i.e. in uniform registers), one elected lane issues tcgen05.mma / tcgen05.commit ==================
         {
-            const bool leader = lane == 0;
+            const uint32_t leader = lane == 0 ? 1u : 0u;
+            const uint32_t jt = warp == 1 ? 0u : 1u;           // which of the two M-tiles (8 px apart) this warp issues for
             constexpr uint32_t idesc = make_idesc(128, COUT);
             constexpr uint32_t A_SBO = HALO * C::ROWB;   // next output row = next halo row
             constexpr uint32_t B_SBO = 8 * C::ROWB;      // dense rows
@@ -373,111 +368,79 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 const uint32_t set = n & 1u;
                 mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + (set * 2u) * COUT, d1 = d0 + COUT;
+                const uint32_t dj = tmem_base + (set * 2u + jt) * COUT;   // this issuer's accumulator
                 for (int c = 0; c < C::NCHUNK; c++, a_it++) {
                     const uint32_t slot = a_it & 1u;
                     mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                     tc_fence_after();
                     // descriptor low words (address >> 4) of the hi / lo activation planes of this slot
-                    const uint32_t ah0 = (((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED;
+                    const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
                     const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
                     uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
                     for (int t = 0; t < 9; t++) {
                         const uint32_t ah = ah0 + tap_off, al = al0 + tap_off;
                         const uint32_t first = (c | t) != 0 ? 1u : 0u;
-                        constexpr uint32_t J1 = 8u * C::ROWB >> 4;     // second M-tile: 8 pixels to the right
                         if (p.mma_mode == 1) {
-                            // ---- A-collector reuse: both weight stages resident; xh slice read once for wh and wl ----
+                            // ---- A-collector reuse: both weight stages resident; each xh slice is fetched once for wh and wl ----
                             const uint32_t st_h = stage, ph_h = phase;
                             uint32_t st_l = stage + 1, ph_l = phase;
                             if (st_l == (uint32_t)C::NB) { st_l = 0; ph_l ^= 1u; }
                             mbar_wait_prof(b_full(st_h), ph_h, prof_on, w_bf);
                             mbar_wait_prof(b_full(st_l), ph_l, prof_on, w_bf);
                             tc_fence_after();
-                            if (leader) {
-                                const uint32_t bh = (((b_base + st_h * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                                const uint32_t bl = (((b_base + st_l * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            const uint32_t bh = (((b_base + st_h * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            const uint32_t bl = (((b_base + st_l * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
 #pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    umma_f16_a_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first);
-                                    umma_f16_a_last(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u);
-                                    umma_f16_a_fill(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first);
-                                    umma_f16_a_last(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u);
-                                }
-#pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u);
-                                    umma_f16(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u);
-                                }
-                                umma_commit(b_empty(st_h));
-                                umma_commit(b_empty(st_l));
+                            for (int s = 0; s < C::KSTEPS; s++) {
+                                umma_f16_a_fill(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first, leader);
+                                umma_f16_a_last(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u, leader);
                             }
-                            __syncwarp();
+#pragma unroll
+                            for (int s = 0; s < C::KSTEPS; s++) {
+                                umma_f16(dj, desc(A_HI32, al + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u, leader);
+                            }
+                            umma_commit_if(b_empty(st_h), leader);
+                            umma_commit_if(b_empty(st_l), leader);
                             stage = st_l; phase = ph_l;
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         } else {
                             // ---- hi weights: xh*wh and xl*wh ----
                             mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                             tc_fence_after();
-                            if (leader) {
+                            {
                                 const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                                if (p.mma_mode == 2) {
-                                    // weight-stationary: each 16-channel weight slice is fetched once for the four MMAs using it
 #pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        umma_f16_ws_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                                        umma_f16_ws_use(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                                        umma_f16_ws_use(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                        umma_f16_ws_last(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                                        umma_f16(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first);
-                                    }
-#pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        umma_f16(d0, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                        umma_f16(d1, desc(A_HI32, al + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                    }
+                                for (int s = 0; s < C::KSTEPS; s++) {
+                                    umma_f16(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first, leader);
                                 }
-                                umma_commit(b_empty(stage));
+#pragma unroll
+                                for (int s = 0; s < C::KSTEPS; s++) {
+                                    umma_f16(dj, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u, leader);
+                                }
+                                umma_commit_if(b_empty(stage), leader);
                             }
-                            __syncwarp();
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                             // ---- lo weights: xh*wl ----
                             mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                             tc_fence_after();
-                            if (leader) {
+                            {
                                 const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                                if (p.mma_mode == 2) {
 #pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        umma_f16_ws_fill(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                        umma_f16_ws_last(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int s = 0; s < C::KSTEPS; s++) {
-                                        umma_f16(d0, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                        umma_f16(d1, desc(A_HI32, ah + J1 + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u);
-                                    }
+                                for (int s = 0; s < C::KSTEPS; s++) {
+                                    umma_f16(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u, leader);
                                 }
-                                umma_commit(b_empty(stage));
+                                umma_commit_if(b_empty(stage), leader);
                             }
-                            __syncwarp();
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         }
                         // next tap: kx+1, or the next halo row
                         tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                     }
-                    if (leader) umma_commit(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
+                    umma_commit_if(a_empty(slot), leader);   // the staged boxes may be overwritten once these MMAs retire
                 }
-                if (leader) umma_commit(acc_full(set));       // accumulators of this tile-set are final
-                __syncwarp();
+                umma_commit_if(acc_full(set), leader);       // accumulators of this tile-set are final
             }
-            if (prof_on && leader) {
+            if (prof_on && leader && jt == 0) {
                 prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
                 prof[PROF_MMA_WAIT_ACC] += w_acc;
                 prof[PROF_MMA_WAIT_A] += w_af;
