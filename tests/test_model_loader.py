@@ -92,27 +92,30 @@ def _swizzle(off, row_bytes):
 
 
 def test_tc_operand_pack_layout_and_split(w2x, oracle_models):
-    """[chunk][tap][hi|lo][n_out x kc] fp16, K-major rows, 16-byte units XOR-swizzled; hi+lo == w*scale."""
+    """[chunk][tap][32-ch block][hi|lo][n_out x 32] fp16, K-major rows of 64 B, 16-byte units XOR-swizzled
+    (SWIZZLE_64B); hi+lo == w*scale to ~22 bits."""
     m = w2x.Model.from_arrays(oracle_models["scale2.0x"].weights, oracle_models["scale2.0x"].biases)
     assert m.debug_tc_pack(0)[0] is None and m.debug_tc_pack(6)[0] is None      # 1->32 and 128->1 are not MMA layers
     for li in range(1, 6):
-        data, kc, nch, ws = m.debug_tc_pack(li)
+        data, nch, kbl, ws = m.debug_tc_pack(li)
         w = oracle_models["scale2.0x"].weights[li]
         co, ci = w.shape[:2]
-        assert kc == min(ci, 64) and nch == ci // kc and ws == 2.0 ** np.floor(np.log2(1024.0 / np.abs(w).max()))
-        rowb = kc * 2
-        data = data.view(np.float16).reshape(nch, 9, 2, co * kc)
+        kc_a = min(ci, 64)
+        assert nch == ci // kc_a and kbl == kc_a // 32 and ws == 2.0 ** np.floor(np.log2(1024.0 / np.abs(w).max()))
+        data = data.view(np.float16).reshape(nch, 9, kbl, 2, co * 32)
         ws_w = (w * np.float32(ws)).astype(np.float32)
         hi = ws_w.astype(np.float16)
         lo = (ws_w - hi.astype(np.float32)).astype(np.float16)
-        n_idx, k_idx = np.meshgrid(np.arange(co), np.arange(kc), indexing="ij")
-        off = np.vectorize(_swizzle)(n_idx * rowb + 2 * k_idx, rowb) // 2
+        n_idx, k_idx = np.meshgrid(np.arange(co), np.arange(32), indexing="ij")
+        off = np.vectorize(_swizzle)(n_idx * 64 + 2 * k_idx, 64) // 2
         for c in range(nch):
             for t in range(9):
-                exp_hi = hi[:, c * kc:(c + 1) * kc, t // 3, t % 3]
-                exp_lo = lo[:, c * kc:(c + 1) * kc, t // 3, t % 3]
-                assert np.array_equal(data[c, t, 0][off].view(np.uint16), exp_hi.view(np.uint16)), (li, c, t)
-                assert np.array_equal(data[c, t, 1][off].view(np.uint16), exp_lo.view(np.uint16)), (li, c, t)
+                for kb in range(kbl):
+                    c0 = c * kc_a + kb * 32
+                    exp_hi = hi[:, c0:c0 + 32, t // 3, t % 3]
+                    exp_lo = lo[:, c0:c0 + 32, t // 3, t % 3]
+                    assert np.array_equal(data[c, t, kb, 0][off].view(np.uint16), exp_hi.view(np.uint16)), (li, c, t, kb)
+                    assert np.array_equal(data[c, t, kb, 1][off].view(np.uint16), exp_lo.view(np.uint16)), (li, c, t, kb)
         # the split keeps ~22 significant bits: |w*s - (hi+lo)| <= 2^-22 |w*s| + 2^-25
         res = np.abs(ws_w.astype(np.float64) - hi.astype(np.float64) - lo.astype(np.float64))
         assert np.all(res <= 2.0 ** -22 * np.abs(ws_w) + 2.0 ** -25)
@@ -133,8 +136,8 @@ def test_f16_rounding_edge_cases_via_pack(w2x):
     first = np.zeros((32, 1, 3, 3), np.float32)
     last = np.zeros((1, 32, 3, 3), np.float32)
     m = w2x.Model.from_arrays([first, w, last], [np.zeros(32), np.zeros(32), np.zeros(1)])
-    data, kc, nch, ws = m.debug_tc_pack(1)
-    assert ws == 1.0 and kc == 32 and nch == 1
+    data, nch, kbl, ws = m.debug_tc_pack(1)
+    assert ws == 1.0 and nch == 1 and kbl == 1
     data = data.reshape(1, 9, 2, 32 * 32)
     hi = w.astype(np.float16)
     lo = (w - hi.astype(np.float32)).astype(np.float16)

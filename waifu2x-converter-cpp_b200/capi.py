@@ -101,7 +101,7 @@ def lib():
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_read.argtypes = [vp, ci, C.POINTER(C.c_uint64), C.POINTER(ci)]
     L.w2x_debug_tc_pack.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(cs), C.POINTER(ci), C.POINTER(ci),
-                                    C.POINTER(C.c_float)]
+                                    C.POINTER(C.c_float), C.POINTER(ci)]
     _lib = L
     return L
 
@@ -191,13 +191,14 @@ class Model:
 
 
     def debug_tc_pack(self, layer):
-        """(fp16 bit patterns [chunk][tap][hi|lo][n_out*kc], kc, n_chunk, wscale) -- packing tests only."""
+        """(fp16 bit patterns [chunk][tap][kblock][hi|lo][n_out*32], n_chunk, kblocks, wscale) -- packing tests only."""
         dp, n = C.POINTER(C.c_uint16)(), C.c_size_t()
-        kc, nch, ws = C.c_int(), C.c_int(), C.c_float()
-        _check(lib().w2x_debug_tc_pack(self._h, layer, C.byref(dp), C.byref(n), C.byref(kc), C.byref(nch), C.byref(ws)))
+        kc, nch, ws, kbl = C.c_int(), C.c_int(), C.c_float(), C.c_int()
+        _check(lib().w2x_debug_tc_pack(self._h, layer, C.byref(dp), C.byref(n), C.byref(kc), C.byref(nch), C.byref(ws), C.byref(kbl)))
         if n.value == 0:
-            return None, kc.value, nch.value, ws.value
-        return np.ctypeslib.as_array(dp, shape=(n.value,)).copy(), kc.value, nch.value, ws.value
+            return None, nch.value, kbl.value, ws.value
+        assert kc.value == 32
+        return np.ctypeslib.as_array(dp, shape=(n.value,)).copy(), nch.value, kbl.value, ws.value
 
 
 # ---- Context ------------------------------------------------------------------------------------

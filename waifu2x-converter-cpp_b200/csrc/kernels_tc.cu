@@ -193,42 +193,56 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 template <int CIN, int COUT, bool FUSE = false>
 struct Cfg {
-    static constexpr int KC = CIN < 64 ? CIN : 64;      // channels per K chunk
+    // ---- A operand (activations): one TMA box per (tile-set, 64-channel chunk, hi|lo) ----
+    static constexpr int KC = CIN < 64 ? CIN : 64;      // channels per activation chunk
     static constexpr int NCHUNK = CIN / KC;
     static constexpr int ROWB = KC * 2;                 // bytes per pixel per chunk (= swizzle span)
-    static constexpr int KSTEPS = KC / 16;              // MMAs (K=16) per chunk per tap
-    static constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : 4u;
+    static constexpr uint32_t A_LAYOUT = ROWB == 128 ? 2u : 4u;                // SWIZZLE_128B : SWIZZLE_64B
     static constexpr int A_PLANE = HALO * HALO * ROWB;                       // bytes one TMA box delivers
     static constexpr int A_PLANE_PAD = (A_PLANE + 1023) / 1024 * 1024;
     static constexpr int A_SLOT = 2 * A_PLANE_PAD;                           // hi + lo
     static constexpr int A_SLOTS = 2;
-    static constexpr int B_STAGE = COUT * ROWB;                              // one (chunk, tap, hi|lo) tile
+    // ---- B operand (weights): stages of 32 input channels (two K=16 steps), SWIZZLE_64B rows of 64 B ----
+    static constexpr int KB = 32;
+    static constexpr int KBLOCKS = KC / KB;             // weight stages per (chunk, tap, part)
+    static constexpr int B_ROWB = KB * 2;
+    static constexpr uint32_t B_LAYOUT = 4u;
+    // Cout <= 64: hi and lo weights form ONE stage of 2*Cout rows, so xh*[wh;wl] is a single N = 2*Cout MMA
+    // (accumulators D1 | D2 side by side, summed in the epilogue) -- two MMAs per K step instead of three.
+    static constexpr bool STACK = COUT <= 64;
+    static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
+    static constexpr int B_STAGE = STACK ? 2 * B_BLOCK : B_BLOCK;
+    static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * (STACK ? 1 : 2);
+    // ---- accumulators ----
+    static constexpr int TILE_COLS = STACK ? 2 * COUT : COUT;                // TMEM columns per M-tile
+    static constexpr int ACC_COLS = 4 * TILE_COLS;                           // 2 sets x 2 M-tiles
+    static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
+    // ---- shared memory map: [A slots][B stages][barriers + bias (1 KB)][last-layer weights][store staging] ----
     static constexpr int BAR_BYTES = 1024;
     static constexpr int W6_BYTES = FUSE ? 9 * COUT * 4 : 0;                 // fused last layer: its [tap][c] fp32 weights
-    static constexpr int STG_BYTES = FUSE ? 0 : 4 * 2048;                    // epilogue store staging, 2 KB per warp
+    static constexpr int STG_BYTES = FUSE ? 0 : 8 * 2048;                    // epilogue store staging, 2 KB per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
     static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
     static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES + W6_BYTES + STG_BYTES;
-    static constexpr int ACC_COLS = 4 * COUT;                                // 2 sets x 2 M-tiles
-    static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-    static_assert(NB >= 2, "need at least two weight stages");
+    static_assert(NB >= 3, "need at least three weight stages");
     static_assert((8 + 2 * NB) * 8 + 4 <= 512 && COUT * 4 <= 512, "barrier/bias area overflow");
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
-    static_assert(B_STAGE % 1024 == 0, "weight stage must keep 1024-byte alignment");
-    static_assert(CIN % KC == 0 && KC % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "shape");
+    static_assert(B_STAGE % 512 == 0, "weight stage must keep the 512-byte SWIZZLE_64B pattern alignment");
+    static_assert(CIN % KC == 0 && KC % KB == 0 && COUT % 16 == 0 && COUT <= 128, "shape");
 };
 
-constexpr int NUM_THREADS = 8 * 32;   // warps: 0 A producer, 1 + 7 MMA issuers (one M-tile each), 2 B producer, 3-6 epilogue
+// warps: 0 A producer | 1, 7 MMA issuers (M-tile 0, 1) | 2 B producer + TMEM owner | 3-6 epilogue of M-tile 0 | 8-11 epilogue of M-tile 1
+constexpr int NUM_THREADS = 12 * 32;
 
 struct TcParams {
-    const uint16_t *wpack;   // [chunk][tap][hi|lo][COUT x ROWB bytes], pre-swizzled
+    const uint16_t *wpack;   // [chunk][tap][kblock][hi|lo][COUT rows x 64 B], pre-swizzled (see model.cpp)
     const float *bias;       // [COUT] (float)bias
     __half *out;             // [2][Hp][Wp][COUT]
     int Wp, Hp;
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / (wscale * ACT_SCALE)
-    int mma_mode;            // 0 plain; 1 A-collector reuse (xh*wh, xh*wl back to back on one fetched activation slice)
+    int mma_mode;            // reserved probe switch (unused)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
@@ -271,8 +285,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
     auto b_full = [&](int i) { return bar_base + 8u * (uint32_t)(8 + i); };
     auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(8 + C::NB + i); };
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NB);   // 4 bytes: TMEM base address
-    uint32_t *tmem_slot_ptr =
-        reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));   // COUT floats
     for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
     const float *s_w6 = reinterpret_cast<const float *>(smem_raw + (bar_base + C::BAR_BYTES - smem_u32(smem_raw)));   // [9][COUT]
@@ -290,7 +303,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             mbar_init(a_full(i), 1);
             mbar_init(a_empty(i), 2);     // one tcgen05.commit per MMA issuer
             mbar_init(acc_full(i), 2);
-            mbar_init(acc_empty(i), 4);   // one arrive per epilogue warp
+            mbar_init(acc_empty(i), 8);   // one arrive per epilogue warp
         }
         for (int i = 0; i < C::NB; i++) {
             mbar_init(b_full(i), 1);
@@ -329,14 +342,13 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             if (prof_on) prof[PROF_APROD_WAIT] += w_a;
         }
     } else if (warp == 2) {
-        // ===================== B producer: stream the packed weights, (chunk, tap, hi|lo) order =====
+        // ===================== B producer: stream the packed weights in consumption order ============
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             unsigned long long w_b = 0;
-            constexpr int N_BLOCKS = C::NCHUNK * 9 * 2;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack);
-                for (int blk = 0; blk < N_BLOCKS; blk++) {
+                for (int blk = 0; blk < C::STAGES_PER_TILESET; blk++) {
                     mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
                     mbar_arrive_expect_tx(b_full(stage), C::B_STAGE);
                     bulk_load(b_base + stage * C::B_STAGE, src + (size_t)blk * C::B_STAGE, C::B_STAGE, b_full(stage));
@@ -346,62 +358,50 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1 || warp == 7) {
-        // ===================== MMA issuers (warp 1: M-tile 0, warp 7: M-tile 1): the whole warp walks the loop (keeps every operand warp-uniform,
-        // i.e. in uniform registers), one elected lane issues tcgen05.mma / tcgen05.commit ==================
-        {
-            const uint32_t leader = lane == 0 ? 1u : 0u;
-            const uint32_t jt = warp == 1 ? 0u : 1u;           // which of the two M-tiles (8 px apart) this warp issues for
-            constexpr uint32_t idesc = make_idesc(128, COUT);
-            constexpr uint32_t A_SBO = HALO * C::ROWB;   // next output row = next halo row
-            constexpr uint32_t B_SBO = 8 * C::ROWB;      // dense rows
-            // Only the 14-bit start-address field of a descriptor changes between MMAs: keep the upper
-            // words constant and derive the lower word with one integer add per operand (the issue loop
-            // is a single thread -- every instruction here is on the tensor pipe's critical path).
-            constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::LAYOUT) >> 32);
-            constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::LAYOUT) >> 32);
-            constexpr uint32_t LO_FIXED = 1u << 16;      // LBO field = 1
-            auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
-            uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
-            unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
-            const long long t_begin = clock64();
-            for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
-                const uint32_t set = n & 1u;
-                mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
+        // ===================== MMA issuers (warp 1: M-tile 0, warp 7: M-tile 1) ========================
+        // The whole warp walks the loop, lane 0's instructions are predicated inside the asm blocks.
+        const uint32_t leader = lane == 0 ? 1u : 0u;
+        const uint32_t jt = warp == 1 ? 0u : 1u;
+        constexpr uint32_t idesc_c = make_idesc(128, COUT);          // N = Cout
+        constexpr uint32_t idesc_2c = make_idesc(128, 2 * COUT);     // N = 2*Cout (stacked [wh;wl]); only used when STACK
+        constexpr uint32_t A_SBO = HALO * C::ROWB;                   // next output row = next halo row
+        constexpr uint32_t B_SBO = 8 * C::B_ROWB;                    // dense rows
+        constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::A_LAYOUT) >> 32);
+        constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::B_LAYOUT) >> 32);
+        constexpr uint32_t LO_FIXED = 1u << 16;                      // LBO field = 1
+        auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
+        uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
+        unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+        const long long t_begin = clock64();
+        for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
+            const uint32_t set = n & 1u;
+            mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
+            tc_fence_after();
+            const uint32_t dj = tmem_base + (set * 2u + jt) * C::TILE_COLS;   // this issuer's accumulator columns
+            for (int c = 0; c < C::NCHUNK; c++, a_it++) {
+                const uint32_t slot = a_it & 1u;
+                mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                 tc_fence_after();
-                const uint32_t dj = tmem_base + (set * 2u + jt) * COUT;   // this issuer's accumulator
-                for (int c = 0; c < C::NCHUNK; c++, a_it++) {
-                    const uint32_t slot = a_it & 1u;
-                    mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
-                    tc_fence_after();
-                    // descriptor low words (address >> 4) of the hi / lo activation planes of this slot
-                    const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
-                    const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
-                    uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
-                    for (int t = 0; t < 9; t++) {
-                        const uint32_t ah = ah0 + tap_off, al = al0 + tap_off;
-                        const uint32_t first = (c | t) != 0 ? 1u : 0u;
-                        if (p.mma_mode == 1) {
-                            // ---- A-collector reuse: both weight stages resident; each xh slice is fetched once for wh and wl ----
-                            const uint32_t st_h = stage, ph_h = phase;
-                            uint32_t st_l = stage + 1, ph_l = phase;
-                            if (st_l == (uint32_t)C::NB) { st_l = 0; ph_l ^= 1u; }
-                            mbar_wait_prof(b_full(st_h), ph_h, prof_on, w_bf);
-                            mbar_wait_prof(b_full(st_l), ph_l, prof_on, w_bf);
+                // descriptor low words (address >> 4) of this issuer's window into the hi / lo activation planes
+                const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
+                const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
+                uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
+                for (int t = 0; t < 9; t++) {
+                    const uint32_t first = (c | t) != 0 ? 1u : 0u;
+#pragma unroll
+                    for (int kb = 0; kb < C::KBLOCKS; kb++) {
+                        const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;   // 32 channels = 64 B = 4 units
+                        const uint32_t acc0 = kb ? 1u : first;
+                        if constexpr (C::STACK) {
+                            // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
+                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                             tc_fence_after();
-                            const uint32_t bh = (((b_base + st_h * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                            const uint32_t bl = (((b_base + st_l * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-#pragma unroll
-                            for (int s = 0; s < C::KSTEPS; s++) {
-                                umma_f16_a_fill(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, bh + 2u * s), idesc, s ? 1u : first, leader);
-                                umma_f16_a_last(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, bl + 2u * s), idesc, 1u, leader);
-                            }
-#pragma unroll
-                            for (int s = 0; s < C::KSTEPS; s++) {
-                                umma_f16(dj, desc(A_HI32, al + 2u * s), desc(B_HI32, bh + 2u * s), idesc, 1u, leader);
-                            }
-                            umma_commit_if(b_empty(st_h), leader);
-                            umma_commit_if(b_empty(st_l), leader);
-                            stage = st_l; phase = ph_l;
+                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_2c, acc0, leader);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_2c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_commit_if(b_empty(stage), leader);
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         } else {
                             // ---- hi weights: xh*wh and xl*wh ----
@@ -409,14 +409,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                             tc_fence_after();
                             {
                                 const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-#pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    umma_f16(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, s ? 1u : first, leader);
-                                }
-#pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    umma_f16(dj, desc(A_HI32, al + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u, leader);
-                                }
+                                umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                                umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                                umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
+                                umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
                                 umma_commit_if(b_empty(stage), leader);
                             }
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
@@ -425,36 +421,35 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                             tc_fence_after();
                             {
                                 const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-#pragma unroll
-                                for (int s = 0; s < C::KSTEPS; s++) {
-                                    umma_f16(dj, desc(A_HI32, ah + 2u * s), desc(B_HI32, b0 + 2u * s), idesc, 1u, leader);
-                                }
+                                umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
+                                umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
                                 umma_commit_if(b_empty(stage), leader);
                             }
                             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                         }
-                        // next tap: kx+1, or the next halo row
-                        tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                     }
-                    umma_commit_if(a_empty(slot), leader);   // the staged boxes may be overwritten once these MMAs retire
+                    // next tap: kx+1, or the next halo row
+                    tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                 }
-                umma_commit_if(acc_full(set), leader);       // accumulators of this tile-set are final
+                umma_commit_if(a_empty(slot), leader);   // the staged boxes may be overwritten once these MMAs retire
             }
-            if (prof_on && leader && jt == 0) {
-                prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
-                prof[PROF_MMA_WAIT_ACC] += w_acc;
-                prof[PROF_MMA_WAIT_A] += w_af;
-                prof[PROF_MMA_WAIT_B] += w_bf;
-                prof[PROF_TILESETS] += n;
-            }
+            umma_commit_if(acc_full(set), leader);       // this issuer's accumulators of the tile-set are final
+        }
+        if (prof_on && leader && jt == 0) {
+            prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
+            prof[PROF_MMA_WAIT_ACC] += w_acc;
+            prof[PROF_MMA_WAIT_A] += w_af;
+            prof[PROF_MMA_WAIT_B] += w_bf;
+            prof[PROF_TILESETS] += n;
         }
     } else {
-        // ===================== epilogue warps 3..6 ====================================================
+        // ===================== epilogue: warps 3..6 drain M-tile 0, warps 8..11 drain M-tile 1 ==========
         const uint32_t q = (uint32_t)warp & 3u;          // TMEM lane quarter this warp may access
+        const int j = warp >= 8 ? 1 : 0;                 // M-tile
         const uint32_t row = q * 32u + (uint32_t)lane;   // GEMM row = pixel inside the 8x16 M-tile
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
         const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
-        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + q * 2048u;   // this warp's staging tile (non-FUSE only)
+        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q) * 2048u;   // this warp's staging tile
         uint32_t n = 0;
         unsigned long long w_e = 0, work_e = 0;
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
@@ -463,87 +458,91 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
             mbar_wait_prof(acc_full(set), (n >> 1) & 1u, prof_on, w_e);
             const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
+            const uint32_t tcol = tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
+            const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
+            const bool inside = fy < p.Hp && fx < p.Wp;
+            float pt[9];                                   // FUSE: nine per-tap dot products of this pixel
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
-                const bool inside = fy < p.Hp && fx < p.Wp;
-                if constexpr (!FUSE) {
+            for (int t = 0; t < 9; t++) pt[t] = 0.f;
 #pragma unroll
-                    for (int cb = 0; cb < COUT / 32; cb++) {
-                        uint32_t r[32];
-                        tmem_ld32(tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * COUT + (uint32_t)cb * 32u, r);
+            for (int cb = 0; cb < COUT / 32; cb++) {
+                // ---- 32 output channels of this pixel: accumulator -> scale, bias, leaky-ReLU ----
+                float act[32];
+                {
+                    uint32_t r[32];
+                    tmem_ld32(tcol + (uint32_t)cb * 32u, r);
+                    if constexpr (C::STACK) {
+                        uint32_t r2[32];
+                        tmem_ld32(tcol + (uint32_t)(COUT + cb * 32), r2);
                         tmem_ld_wait();
-                        uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            float v0 = fmaf(__uint_as_float(r[2 * i]), p.out_scale, s_bias[cb * 32 + 2 * i]);
-                            float v1 = fmaf(__uint_as_float(r[2 * i + 1]), p.out_scale, s_bias[cb * 32 + 2 * i + 1]);
-                            v0 = (fminf(v0, 0.f) * 0.1f + fmaxf(v0, 0.f)) * ACT_SCALE;
-                            v1 = (fminf(v1, 0.f) * 0.1f + fmaxf(v1, 0.f)) * ACT_SCALE;
-                            __half2 h = __floats2half2_rn(v0, v1);
-                            float2 hf = __half22float2(h);
-                            __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                            hi[i] = *reinterpret_cast<uint32_t *>(&h);
-                            lo[i] = *reinterpret_cast<uint32_t *>(&l);
-                        }
-                        // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
-                        // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
-                        // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
+                        for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+                    } else {
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int plane = 0; plane < 2; plane++) {
-                            const uint32_t *src = plane ? lo : hi;
+                        for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]);
+                    }
+                }
 #pragma unroll
-                            for (int v = 0; v < 4; v++)
-                                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-                            __syncwarp();
+                for (int i = 0; i < 32; i++) {
+                    const float v = fmaf(act[i], p.out_scale, s_bias[cb * 32 + i]);
+                    act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
+                }
+                if constexpr (!FUSE) {
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-                                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-                                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-                                if (gy < p.Hp && gx < p.Wp) {
-                                    __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
-                                    *reinterpret_cast<uint4 *>(dst) = val;
-                                }
+                    for (int i = 0; i < 16; i++) {
+                        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+                        __half2 h = __floats2half2_rn(v0, v1);
+                        float2 hf = __half22float2(h);
+                        __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                        hi[i] = *reinterpret_cast<uint32_t *>(&h);
+                        lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                    }
+                    // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
+                    // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
+                    // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
+#pragma unroll
+                    for (int plane = 0; plane < 2; plane++) {
+                        const uint32_t *src = plane ? lo : hi;
+#pragma unroll
+                        for (int v = 0; v < 4; v++)
+                            sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+                            const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+                            const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+                            if (gy < p.Hp && gx < p.Wp) {
+                                __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
+                                *reinterpret_cast<uint4 *>(dst) = val;
                             }
-                            __syncwarp();
                         }
+                        __syncwarp();
                     }
                 } else {
-                    // last layer folded in: nine per-tap dot products of this pixel's fp32 activations
-                    float pt[9];
+                    // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll
-                    for (int t = 0; t < 9; t++) pt[t] = 0.f;
+                    for (int g = 0; g < 8; g++) {
 #pragma unroll
-                    for (int cb = 0; cb < COUT / 32; cb++) {
-                        uint32_t r[32];
-                        tmem_ld32(tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * COUT + (uint32_t)cb * 32u, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < 8; g++) {
-                            float a[4];
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                float v = fmaf(__uint_as_float(r[4 * g + e]), p.out_scale, s_bias[cb * 32 + 4 * g + e]);
-                                a[e] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
-                            }
-#pragma unroll
-                            for (int t = 0; t < 9; t++) {
-                                const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
-                                pt[t] = fmaf(a[0], w.x, pt[t]);
-                                pt[t] = fmaf(a[1], w.y, pt[t]);
-                                pt[t] = fmaf(a[2], w.z, pt[t]);
-                                pt[t] = fmaf(a[3], w.w, pt[t]);
-                            }
+                        for (int t = 0; t < 9; t++) {
+                            const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
+                            pt[t] = fmaf(act[4 * g + 0], w.x, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 1], w.y, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 2], w.z, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 3], w.w, pt[t]);
                         }
                     }
-                    if (inside) {
-                        float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)fy * p.Wp + fx) * 12);
-                        dst[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
-                        dst[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
-                        dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
-                    }
+                }
+            }
+            if constexpr (FUSE) {
+                if (inside) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)fy * p.Wp + fx) * 12);
+                    dst[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
+                    dst[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
+                    dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
                 }
             }
             tc_fence_before();

@@ -291,18 +291,21 @@ int parse_model_json(const char *path, w2x_model **out) {
 }
 
 // ---- tcgen05 operand packing ------------------------------------------------------------------
-// Shared-memory image of one B tile: n_out rows (one per output plane) of KC fp16 values, K-major.
-// Byte address of element (n, k) before swizzling: n*ROWB + 2k; the 16-byte unit index is then
-// XORed with address bits [7, 7+log2(ROWB/16)) -- CUTLASS Swizzle<2,4,3> (64 B rows) or
-// Swizzle<3,4,3> (128 B rows), the patterns TMA and the UMMA descriptors use.
+// Shared-memory image of one B block: n_out rows (one per output plane) of 32 fp16 values, K-major.
+// Byte address of element (n, k) before swizzling: n*64 + 2k; the 16-byte unit index is then XORed
+// with address bits [7,9) -- CUTLASS Swizzle<2,4,3>, the SWIZZLE_64B pattern of TMA / UMMA descriptors.
 static inline size_t swizzled_offset(size_t logical, int row_bytes) {
     size_t mask = (size_t)(row_bytes / 16 - 1);  // 3 or 7
     return logical ^ (((logical >> 7) & mask) << 4);
 }
 
 static void pack_tc_layer(const Layer &L, TcPack &P) {
-    P.kc = L.n_in < 64 ? L.n_in : 64;
-    P.n_chunk = L.n_in / P.kc;
+    // Blocks of 32 input channels (two K=16 MMA steps), rows of 64 B, SWIZZLE_64B, in the kernel's consumption
+    // order: [activation chunk c (64 ch, or 32 when Cin = 32)][tap][32-ch block inside the chunk][hi | lo].
+    const int kc_a = L.n_in < 64 ? L.n_in : 64;
+    P.kc = 32;
+    P.n_chunk = L.n_in / kc_a;
+    P.kblocks = kc_a / 32;
     P.row_bytes = P.kc * 2;
     float mx = 0.f;
     for (float v : L.w) mx = std::fmax(mx, std::fabs(v));
@@ -313,23 +316,25 @@ static void pack_tc_layer(const Layer &L, TcPack &P) {
         if (e > 14) e = 14;
     }
     P.wscale = std::ldexp(1.0f, e);
-    const size_t tile_elems = (size_t)L.n_out * P.kc;  // one (chunk, tap, part) block
-    P.bytes.assign((size_t)P.n_chunk * 9 * 2 * tile_elems, 0);
+    const size_t block_elems = (size_t)L.n_out * P.kc;  // one (chunk, tap, kblock, part) block
+    P.bytes.assign((size_t)P.n_chunk * 9 * P.kblocks * 2 * block_elems, 0);
     for (int c = 0; c < P.n_chunk; c++)
-        for (int t = 0; t < 9; t++) {
-            uint16_t *hi = P.bytes.data() + (((size_t)c * 9 + t) * 2 + 0) * tile_elems;
-            uint16_t *lo = P.bytes.data() + (((size_t)c * 9 + t) * 2 + 1) * tile_elems;
-            for (int n = 0; n < L.n_out; n++)
-                for (int k = 0; k < P.kc; k++) {
-                    int ci = c * P.kc + k;
-                    float w = L.w[((size_t)n * L.n_in + ci) * 9 + t] * P.wscale;  // exact (power of two)
-                    uint16_t h = f32_to_f16_rn(w);
-                    uint16_t l = f32_to_f16_rn(w - f16_to_f32(h));              // exact difference
-                    size_t off = swizzled_offset((size_t)n * P.row_bytes + 2 * (size_t)k, P.row_bytes) / 2;
-                    hi[off] = h;
-                    lo[off] = l;
-                }
-        }
+        for (int t = 0; t < 9; t++)
+            for (int kb = 0; kb < P.kblocks; kb++) {
+                const size_t blk = (((size_t)c * 9 + t) * P.kblocks + kb) * 2;
+                uint16_t *hi = P.bytes.data() + (blk + 0) * block_elems;
+                uint16_t *lo = P.bytes.data() + (blk + 1) * block_elems;
+                for (int n = 0; n < L.n_out; n++)
+                    for (int k = 0; k < P.kc; k++) {
+                        int ci = c * kc_a + kb * 32 + k;
+                        float w = L.w[((size_t)n * L.n_in + ci) * 9 + t] * P.wscale;  // exact (power of two)
+                        uint16_t h = f32_to_f16_rn(w);
+                        uint16_t l = f32_to_f16_rn(w - f16_to_f32(h));              // exact difference
+                        size_t off = swizzled_offset((size_t)n * P.row_bytes + 2 * (size_t)k, P.row_bytes) / 2;
+                        hi[off] = h;
+                        lo[off] = l;
+                    }
+            }
 }
 
 int finalize_model(w2x_model *m) {
@@ -426,7 +431,7 @@ int w2x_model_layer_params(const w2x_model *model, int layer, const float **weig
 
 // Probe hook (not part of the stable ABI): the tcgen05 operand image of one layer, for the packing tests.
 W2X_API int w2x_debug_tc_pack(const w2x_model *model, int layer, const uint16_t **data, size_t *n_elems, int *kc,
-                              int *n_chunk, float *wscale) {
+                              int *n_chunk, float *wscale, int *kblocks) {
     if (!model || layer < 0 || layer >= (int)model->tc.size())
         return w2x::fail(W2X_ERR_ARG, "w2x_debug_tc_pack: bad model or layer index");
     const w2x::TcPack &P = model->tc[(size_t)layer];
@@ -435,6 +440,7 @@ W2X_API int w2x_debug_tc_pack(const w2x_model *model, int layer, const uint16_t 
     if (kc) *kc = P.kc;
     if (n_chunk) *n_chunk = P.n_chunk;
     if (wscale) *wscale = P.wscale;
+    if (kblocks) *kblocks = P.kblocks;
     return W2X_OK;
 }
 

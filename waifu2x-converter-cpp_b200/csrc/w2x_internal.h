@@ -23,11 +23,11 @@ struct Layer {
 };
 
 // Packed operands of one layer for the tcgen05 path (built once per model, host side):
-//   bytes = [chunk c][tap t][part hi|lo][n_out rows x ROWB bytes], every block an exact shared
-//   memory image: K-major rows of KC fp16 channels, 16-byte units XOR-swizzled (SWIZZLE_64B for
-//   KC=32, SWIZZLE_128B for KC=64).  hi = fp16(w * wscale), lo = fp16(w * wscale - hi).
+//   bytes = [activation chunk c][tap t][32-channel block kb][part hi|lo][n_out rows x 64 bytes], every
+//   block an exact shared memory image: K-major rows of 32 fp16 channels, 16-byte units XOR-swizzled
+//   (SWIZZLE_64B).  hi = fp16(w * wscale), lo = fp16(w * wscale - hi).
 struct TcPack {
-    int kc = 0, n_chunk = 0, row_bytes = 0;
+    int kc = 0, n_chunk = 0, kblocks = 0, row_bytes = 0;
     float wscale = 1.0f;          // power of two
     std::vector<uint16_t> bytes;  // fp16 bit patterns
 };
