@@ -72,6 +72,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Non-blocking probe of a phase: issued EARLY (before the MMAs of the current stage) so that the ~100-cycle
+// mbarrier round trip of the next stage's wait overlaps with issue work instead of draining the tensor queue.
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -371,8 +386,22 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         constexpr uint32_t LO_FIXED = 1u << 16;                      // LBO field = 1
         auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
         uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
+        uint32_t b_ready = 0;                         // result of the early probe of b_full(stage)
         unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
         const long long t_begin = clock64();
+        // wait for the current weight stage (usually already known to be full), then probe the NEXT one
+        auto acquire_b = [&](uint32_t &b0_out) {
+            if (!b_ready) mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
+            tc_fence_after();
+            b0_out = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+            uint32_t ns = stage + 1, np = phase;
+            if (ns == (uint32_t)C::NB) { ns = 0; np ^= 1u; }
+            b_ready = mbar_test(b_full(ns), np);      // consumed at the next acquire_b
+        };
+        auto release_b = [&]() {
+            umma_commit_if(b_empty(stage), leader);
+            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+        };
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
             const uint32_t set = n & 1u;
             mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
@@ -392,40 +421,28 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                     for (int kb = 0; kb < C::KBLOCKS; kb++) {
                         const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;   // 32 channels = 64 B = 4 units
                         const uint32_t acc0 = kb ? 1u : first;
+                        uint32_t b0;
                         if constexpr (C::STACK) {
                             // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
-                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-                            tc_fence_after();
-                            const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                            acquire_b(b0);
                             umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_2c, acc0, leader);
                             umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_2c, 1u, leader);
                             umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
                             umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                            umma_commit_if(b_empty(stage), leader);
-                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                            release_b();
                         } else {
                             // ---- hi weights: xh*wh and xl*wh ----
-                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-                            tc_fence_after();
-                            {
-                                const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                                umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                                umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
-                                umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma_commit_if(b_empty(stage), leader);
-                            }
-                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                            acquire_b(b0);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            release_b();
                             // ---- lo weights: xh*wl ----
-                            mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-                            tc_fence_after();
-                            {
-                                const uint32_t b0 = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-                                umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
-                                umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma_commit_if(b_empty(stage), leader);
-                            }
-                            if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
+                            acquire_b(b0);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            release_b();
                         }
                     }
                     // next tap: kx+1, or the next halo row
