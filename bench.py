@@ -191,7 +191,20 @@ def run_ours(args):
     def exchange_halos():
         bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
 
+    band = None
+    if world > 1 and args.halo == "per-layer":
+        band = w2x.Band(ctx, model, W, H, up is not None, down is not None)
+        one_up, one_dn = (1 if up is not None else 0), (1 if down is not None else 0)
+
+    def step_per_layer():
+        # the same 7-row buffer is reused: only the row adjacent to the band is needed here
+        bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
+        first = d_ext[ra - one_up:]
+        bands.run_band_per_layer(band, first.data_ptr(), W * 4, d_out.data_ptr(), W * 4, rank, world, dist, torch)
+
     def step_device():
+        if band is not None:
+            return step_per_layer()
         exchange_halos()
         if world == 1:
             ctx.convert_plane_device(model, d_band.data_ptr(), W, H, W * 4, d_out.data_ptr(), W * 4, True)
@@ -203,8 +216,11 @@ def run_ours(args):
             ctx.convert_plane(model, host_in.numpy(), True, out=host_out.numpy())
         else:
             d_band.copy_(host_in, non_blocking=True)
-            exchange_halos()
-            ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
+            if band is not None:
+                step_per_layer()
+            else:
+                exchange_halos()
+                ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
             host_out.copy_(d_out, non_blocking=True)
             stream.synchronize()
 
@@ -288,7 +304,8 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"{W}x{H} fp32 Y plane per GPU, scale2.0x_model.json weights (7x conv3x3 + bias + leaky-ReLU 0.1), "
                                        f"block_splitting=on; plane {W}x{H * world} in {world} row band(s)",
-                           "model": MODEL, "engine": args.engine, "halo_exchange": "7 input rows per neighbour, NCCL send/recv" if world > 1 else "none",
+                           "model": MODEL, "engine": args.engine, "halo_exchange": ("none" if world == 1 else "7 input rows per neighbour once, NCCL send/recv" if band is None
+                                             else "1 row of every intermediate activation per neighbour after every layer, NCCL send/recv"),
                            "l2": "no explicit flush: each step streams ~17 GB of activations per GPU, far beyond the 126 MB L2"},
                 "e2e": {"value": mpix_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
                         "timing": "host wall clock around K calls of the host-buffer C-ABI entry (sync inside the call), max over ranks"},
@@ -308,6 +325,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--halo", default="input", choices=["input", "per-layer"],
+                    help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

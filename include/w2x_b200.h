@@ -157,6 +157,29 @@ W2X_API int w2x_convert_band_device(w2x_ctx *ctx, const w2x_model *model, const 
                                     int width, int band_height, int rows_above, int rows_below,
                                     size_t in_stride_bytes, float *d_out, size_t out_stride_bytes);
 
+/* ---- multi-GPU row-band mode with a halo exchange BETWEEN LAYERS ------------------------------ */
+/* The variant BASELINE.json's north_star names: each rank keeps only its own rows (+1 halo row per
+ * neighbour side) of every intermediate activation and trades ONE boundary row with each neighbour
+ * after every layer (the caller moves the bytes, e.g. ncclSend/ncclRecv or torch.distributed P2P).
+ * Sequence per band (n = layer count, all calls asynchronous on the context's stream):
+ *     w2x_band_load(band, d_in, stride)            input: band rows + 1 real row per neighbour side
+ *     for k in 0 .. n-2:  w2x_band_step(band, k);  w2x_band_halo(band, k, ...) -> exchange the segments
+ *     w2x_band_finish(band, d_out, stride)         last layer's gather -> band_rows output rows
+ * Step n-2 is the tcgen05 layer with the last layer folded into its epilogue; its halo segments are
+ * rows of per-pixel tap partials instead of activations.  Requires the tcgen05 engine. */
+typedef struct w2x_band w2x_band;
+W2X_API int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows,
+                            int has_up_neighbour, int has_down_neighbour, w2x_band **out_band);
+W2X_API void w2x_band_destroy(w2x_band *band);
+W2X_API int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes);
+W2X_API int w2x_band_step(w2x_band *band, int step);
+/* Segments to exchange after `step` was queued: n_segments (<= 2) contiguous device ranges of
+ * seg_bytes each per direction; send_* hold this rank's boundary row, recv_* its halo row.
+ * Pointers for a missing neighbour are NULL.  Arrays must have room for 2 entries. */
+W2X_API int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up,
+                          void **send_down, void **recv_down, size_t *seg_bytes);
+W2X_API int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Number of kernels of THIS library launched by the context so far. */
 W2X_API int w2x_ctx_launch_count(const w2x_ctx *ctx, uint64_t *n_launches);

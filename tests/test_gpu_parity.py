@@ -182,6 +182,52 @@ def test_device_entry_points_and_band_mode(w2x, ctxs, models, oracle_mod):
         assert np.array_equal(torch.cat([o0, o1]).cpu().numpy(), whole), engine
 
 
+def test_band_sessions_with_per_layer_halo_exchange(w2x, ctxs, models, oracle_mod):
+    """The north_star multi-GPU scheme on one device: three row bands, ONE boundary row of every intermediate
+    activation traded with each neighbour after every layer (here a device-to-device copy stands in for
+    ncclSend/ncclRecv).  Must reproduce the whole-plane result bit for bit."""
+    import torch
+    W, H = 150, 130
+    x = oracle_mod.seeded_plane(W, H, 23, "uniform")
+    ctx = ctxs["tc"]
+    m = models["noise2"]
+    whole = ctx.convert_plane(m, x)
+    d_in = torch.from_numpy(x).cuda()
+    cuts = [0, 40, 97, H]
+    bands, outs = [], []
+    for b in range(3):
+        r0, r1 = cuts[b], cuts[b + 1]
+        up, down = b > 0, b < 2
+        band = w2x.Band(ctx, m, W, r1 - r0, up, down)
+        band.load(d_in[r0 - (1 if up else 0):].data_ptr(), W * 4)
+        bands.append(band)
+        outs.append(torch.empty((r1 - r0, W), device="cuda"))
+
+    def dev(ptr, n):
+        return torch.as_tensor(w2x.DevBytes(ptr, n), device="cuda")
+
+    for k in range(bands[0].steps):
+        for band in bands:
+            band.step(k)
+        halos = [band.halo(k) for band in bands]
+        ctx.synchronize()
+        for b in range(2):                      # boundary between band b and b+1
+            for seg in range(len(halos[b])):
+                _, _, sd, rd, nb = halos[b][seg]
+                su, ru, _, _, nb2 = halos[b + 1][seg]
+                assert nb == nb2 and sd and rd and su and ru
+                dev(ru, nb).copy_(dev(sd, nb))   # lower band's halo row above <- upper band's last owned row
+                dev(rd, nb).copy_(dev(su, nb))   # upper band's halo row below <- lower band's first owned row
+        torch.cuda.synchronize()
+    for band, o in zip(bands, outs):
+        band.finish(o.data_ptr(), W * 4)
+    ctx.synchronize()
+    got = torch.cat(outs).cpu().numpy()
+    assert np.array_equal(got, whole)
+    for band in bands:
+        band.close()
+
+
 def test_full_size_4096_properties(w2x, ctxs, models, oracle_mod, oracle_models, ncpu):
     """BASELINE.json config 3 size (4096x4096, scale2.0x) through size-independent properties:
     (1) windows of the full output equal the oracle run on that window + its 7-pixel context,

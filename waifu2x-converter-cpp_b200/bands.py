@@ -49,3 +49,32 @@ def exchange_halos(ext, band_rows: int, rank: int, world: int, n_model: int = 7,
         ops.append(dist.P2POp(dist.irecv, ext[ra + band_rows:], rank + 1))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+def run_band_per_layer(band, ext_in, ext_stride_bytes, d_out, out_stride_bytes, rank, world, dist=None, torch=None):
+    """The per-layer variant (north_star): `band` is a w2x Band session; ext_in = device pointer of this rank's band
+    input preceded / followed by ONE real neighbour row where a neighbour exists.  After every layer each rank
+    sends its boundary row of the fresh activation to the neighbour and receives the neighbour's into its halo row."""
+    if dist is None:
+        import torch.distributed as dist
+    if torch is None:
+        import torch
+    from .capi import DevBytes
+    band.load(ext_in, ext_stride_bytes)
+    for k in range(band.steps):
+        band.step(k)
+        if world == 1:
+            continue
+        ops, keep = [], []
+        for (su, ru, sd, rd, nb) in band.halo(k):
+            if rank > 0:
+                ts, tr = torch.as_tensor(DevBytes(su, nb), device="cuda"), torch.as_tensor(DevBytes(ru, nb), device="cuda")
+                ops += [dist.P2POp(dist.isend, ts, rank - 1), dist.P2POp(dist.irecv, tr, rank - 1)]
+                keep += [ts, tr]
+            if rank < world - 1:
+                ts, tr = torch.as_tensor(DevBytes(sd, nb), device="cuda"), torch.as_tensor(DevBytes(rd, nb), device="cuda")
+                ops += [dist.P2POp(dist.isend, ts, rank + 1), dist.P2POp(dist.irecv, tr, rank + 1)]
+                keep += [ts, tr]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    band.finish(d_out, out_stride_bytes)

@@ -30,7 +30,8 @@ ABI_SYMBOLS = (
     "w2x_ctx_set_stream", "w2x_ctx_synchronize", "w2x_ctx_set_log", "w2x_ctx_set_block_walk",
     "w2x_ctx_set_scratch_limit", "w2x_convert_plane", "w2x_convert_plane_device", "w2x_filter_layer",
     "w2x_filter_layer_device", "w2x_convert_band_device", "w2x_ctx_launch_count", "w2x_ctx_set_timing",
-    "w2x_ctx_layer_times", "w2x_ctx_layer_kernel_name",
+    "w2x_ctx_layer_times", "w2x_ctx_layer_kernel_name", "w2x_band_create", "w2x_band_destroy", "w2x_band_load",
+    "w2x_band_step", "w2x_band_halo", "w2x_band_finish",
 )
 
 
@@ -96,6 +97,13 @@ def lib():
     L.w2x_ctx_layer_times.argtypes = [vp, ci, fp, C.POINTER(ci), C.POINTER(ci), ci]
     L.w2x_ctx_layer_kernel_name.argtypes = [vp, ci]
     L.w2x_ctx_layer_kernel_name.restype = C.c_char_p
+    L.w2x_band_create.argtypes = [vp, vp, ci, ci, ci, ci, C.POINTER(vp)]
+    L.w2x_band_destroy.argtypes = [vp]
+    L.w2x_band_destroy.restype = None
+    L.w2x_band_load.argtypes = [vp, vp, cs]
+    L.w2x_band_step.argtypes = [vp, ci]
+    L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
+    L.w2x_band_finish.argtypes = [vp, vp, cs]
     L.w2x_debug_set_mma_mode.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
@@ -297,3 +305,39 @@ class Context:
 
     def filter_layer_device(self, model: Model, layer, d_in, d_out, w, h):
         _check(lib().w2x_filter_layer_device(self._h, model._h, layer, C.c_void_p(d_in), C.c_void_p(d_out), w, h))
+
+
+# ---- row-band session with a halo exchange between layers ---------------------------------------
+class DevBytes:
+    """Zero-copy view of a device range for torch.as_tensor (CUDA array interface, uint8)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class Band:
+    """w2x_band_*: one rank's rows of a plane, intermediate activations exchanged row-wise between layers."""
+
+    def __init__(self, ctx: Context, model: Model, width, band_rows, has_up, has_down):
+        h = C.c_void_p()
+        _check(lib().w2x_band_create(ctx._h, model._h, width, band_rows, int(has_up), int(has_down), C.byref(h)))
+        self._h, self._ctx, self._model = h, ctx, model
+        self.steps = len(model) - 1          # w2x_band_step(0 .. n-2), then finish
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.w2x_band_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def load(self, d_in, in_stride_bytes): _check(lib().w2x_band_load(self._h, C.c_void_p(d_in), in_stride_bytes))
+    def step(self, k): _check(lib().w2x_band_step(self._h, k))
+    def finish(self, d_out, out_stride_bytes): _check(lib().w2x_band_finish(self._h, C.c_void_p(d_out), out_stride_bytes))
+
+    def halo(self, k):
+        """-> list of (send_up, recv_up, send_down, recv_down, nbytes) device-pointer tuples (None = no neighbour)."""
+        n, nb = C.c_int(), C.c_size_t()
+        su, ru, sd, rd = ((C.c_void_p * 2)() for _ in range(4))
+        _check(lib().w2x_band_halo(self._h, k, C.byref(n), su, ru, sd, rd, C.byref(nb)))
+        return [(su[i], ru[i], sd[i], rd[i], nb.value) for i in range(n.value)]

@@ -370,6 +370,180 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
 }  // namespace
 
 // ================================================================================================
+// Row-band session with per-layer halo exchange
+// ================================================================================================
+struct w2x_band {
+    w2x_ctx *ctx = nullptr;
+    const w2x_model *model = nullptr;
+    DevModel *dm = nullptr;
+    int width = 0, rows = 0, n = 0;
+    bool up = false, down = false;
+    int pt = 0, pb = 0;            // frame rows above / below the band: 1 (neighbour halo) or n (replicated image border)
+    int pw = 0, hf = 0;            // frame width / height
+    float *pad = nullptr;          // padded fp32 input frame
+    __half *act[2] = {nullptr, nullptr};
+    size_t act_bytes = 0;
+    int cur = 0;                   // act[cur] holds the output of the last queued step
+    int last_step = -1;
+};
+
+namespace {
+int band_check(w2x_band *b) {
+    if (!b || !b->ctx || !b->model) return fail(W2X_ERR_ARG, "NULL band session");
+    return W2X_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows, int has_up, int has_down,
+                    w2x_band **out_band) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model || !out_band || width < 1 || band_rows < 1) return fail(W2X_ERR_ARG, "w2x_band_create: bad argument");
+    *out_band = nullptr;
+    if (!model->tc_eligible || ctx->engine == W2X_ENGINE_FP32)
+        return fail(W2X_ERR_UNSUPPORTED, "w2x_band_create: the per-layer halo mode needs the tcgen05 engine and a 1->{32,64,128}..->1 model");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_tc(ctx);
+    if (rc) return rc;
+    auto b = std::make_unique<w2x_band>();
+    b->ctx = ctx;
+    b->model = model;
+    rc = get_dev_model(ctx, model, &b->dm);
+    if (rc) return rc;
+    b->n = (int)model->layers.size();
+    b->width = width;
+    b->rows = band_rows;
+    b->up = has_up != 0;
+    b->down = has_down != 0;
+    b->pt = b->up ? 1 : b->n;
+    b->pb = b->down ? 1 : b->n;
+    b->pw = width + 2 * b->n;
+    b->hf = band_rows + b->pt + b->pb;
+    int maxc = 1;
+    for (auto &L : model->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
+    b->act_bytes = tc::act_bytes(maxc, b->pw, b->hf);
+    CU_CHECK(cudaMalloc(&b->pad, (size_t)b->pw * b->hf * sizeof(float)));
+    for (int i = 0; i < 2; i++) CU_CHECK(cudaMalloc(&b->act[i], b->act_bytes));
+    *out_band = b.release();
+    return W2X_OK;
+}
+
+void w2x_band_destroy(w2x_band *band) {
+    if (!band) return;
+    if (band->ctx) {
+        DeviceGuard g(band->ctx->device);
+        cudaStreamSynchronize(band->ctx->stream);
+        cudaFree(band->pad);
+        cudaFree(band->act[0]);
+        cudaFree(band->act[1]);
+    }
+    delete band;
+}
+
+int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load: bad input");
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const long stride = (long)(in_stride_bytes / 4);
+    const float *band0 = d_in + (band->up ? stride : 0);
+    CU_CHECK(launch_pad_replicate_xy(band0, band->width, band->rows, stride, band->n, band->pt, band->pb, band->up ? 1 : 0,
+                                     band->down ? 1 : 0, band->pad, ctx->stream));
+    ctx->launches++;
+    band->last_step = -1;
+    band->cur = 0;
+    return W2X_OK;
+}
+
+int w2x_band_step(w2x_band *band, int step) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (step != band->last_step + 1 || step < 0 || step > band->n - 2)
+        return fail(W2X_ERR_ARG, "w2x_band_step: steps must run in order 0..%d (got %d after %d)", band->n - 2, step, band->last_step);
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const w2x_model *m = band->model;
+    DevModel *dm = band->dm;
+    const Layer &L = m->layers[(size_t)step];
+    if (step == 0) {
+        LayerTimer t(ctx, 0);
+        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, dm->w[0], dm->b[0], L.n_out, band->act[0], ctx->stream));
+        band->cur = 0;
+        note_kernel(ctx, 0, "first_1xN");
+    } else {
+        __half *in = band->act[band->cur], *out = band->act[band->cur ^ 1];
+        CUtensorMap map;
+        int e = tc::make_act_tensor_map(&map, in, L.n_in, band->pw, band->hf);
+        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, step);
+        const bool fused = step == band->n - 2;
+        {
+            LayerTimer t(ctx, step);
+            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)step], dm->b[(size_t)step], out, L.n_in, L.n_out, band->pw, band->hf,
+                                         dm->out_scale[(size_t)step], 0, ctx->num_sms, ctx->stream, nullptr,
+                                         fused ? dm->last_w_t : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr));
+        }
+        note_kernel(ctx, step, fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
+        band->cur ^= 1;
+    }
+    ctx->launches++;
+    band->last_step = step;
+    return W2X_OK;
+}
+
+int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up, void **send_down,
+                  void **recv_down, size_t *seg_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (step != band->last_step || !n_segments || !send_up || !recv_up || !send_down || !recv_down || !seg_bytes)
+        return fail(W2X_ERR_ARG, "w2x_band_halo: call it for the step that was queued last");
+    const int n = band->n;
+    char *base = reinterpret_cast<char *>(band->act[band->cur]);
+    size_t row_bytes, plane_bytes;
+    int nseg;
+    if (step == n - 2) {              // per-pixel tap partials [hf][pw][12] fp32
+        row_bytes = (size_t)band->pw * 12 * sizeof(float);
+        plane_bytes = 0;
+        nseg = 1;
+    } else {                          // activation frame [2][hf][pw][C] fp16
+        const int C = band->model->layers[(size_t)step].n_out;
+        row_bytes = (size_t)band->pw * C * 2;
+        plane_bytes = row_bytes * band->hf;
+        nseg = 2;
+    }
+    *n_segments = nseg;
+    *seg_bytes = row_bytes;
+    for (int s = 0; s < 2; s++) {
+        char *pl = base + plane_bytes * s;
+        const bool on = s < nseg;
+        send_up[s] = on && band->up ? pl + row_bytes * 1 : nullptr;                       // first owned row
+        recv_up[s] = on && band->up ? pl : nullptr;                                      // halo row above
+        send_down[s] = on && band->down ? pl + row_bytes * (size_t)(band->hf - 2) : nullptr;   // last owned row
+        recv_down[s] = on && band->down ? pl + row_bytes * (size_t)(band->hf - 1) : nullptr;   // halo row below
+    }
+    return W2X_OK;
+}
+
+int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (band->last_step != band->n - 2) return fail(W2X_ERR_ARG, "w2x_band_finish: steps 0..%d must have run", band->n - 2);
+    if (!d_out || out_stride_bytes % 4 || out_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_finish: bad output");
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const Layer &L = band->model->layers.back();
+    {
+        LayerTimer t(ctx, band->n - 1);
+        CU_CHECK(tc::launch_last_gather_xy(reinterpret_cast<const float *>(band->act[band->cur]), band->pw, band->hf,
+                                           static_cast<float>(L.b[0]), band->n, band->pt, band->pb, d_out,
+                                           (long)(out_stride_bytes / 4), ctx->stream));
+    }
+    note_kernel(ctx, band->n - 1, "last_gather");
+    ctx->launches++;
+    band->last_step = band->n - 1;
+    return W2X_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
 // C ABI
 // ================================================================================================
 extern "C" {

@@ -10,6 +10,9 @@ namespace w2x {
 // ---- kernels_fp32.cu --------------------------------------------------------------------------
 cudaError_t launch_pad_replicate(const float *in, int w, int h, long in_stride_floats, int pad, int rows_above,
                                  int rows_below, float *out, cudaStream_t s);
+// general form: horizontal pad pad_x, vertical pads pad_top / pad_bottom (row-band sessions)
+cudaError_t launch_pad_replicate_xy(const float *in, int w, int h, long in_stride_floats, int pad_x, int pad_top,
+                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s);
 cudaError_t launch_crop(const float *in, int w, int h, int pad, float *out, long out_stride_floats, cudaStream_t s);
 cudaError_t launch_copy2d(const float *in, long in_stride_floats, float *out, long out_stride_floats, int w, int h,
                           cudaStream_t s);
@@ -44,6 +47,9 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, c
 // neighbourhood of partials, adds the bias, applies the leaky-ReLU and writes the cropped fp32 plane.
 cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias, int crop, float *dst,
                                long dst_stride_floats, cudaStream_t s);
+// general form: crop_x columns left/right, crop_top / crop_bottom rows
+cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bias, int crop_x, int crop_top,
+                                  int crop_bottom, float *dst, long dst_stride_floats, cudaStream_t s);
 inline size_t partial_bytes(int Wp, int Hp) { return (size_t)Hp * Wp * 12 * sizeof(float); }
 constexpr int PROF_WORDS = 16;      // per-CTA profile record (see kernels_tc.cu PROF_*)
 constexpr int PROF_MAX_CTAS = 256;

@@ -19,14 +19,14 @@ namespace w2x {
 // rows_above/rows_below > 0 mean real neighbour rows exist there (row-band mode): the source
 // pointer addresses band row 0 and may be read at rows [-rows_above, h + rows_below).
 __global__ void pad_replicate_kernel(const float *__restrict__ in, int w, int h, long in_stride,
-                                     int pad, int rows_above, int rows_below,
+                                     int pad_x, int pad_top, int pad_bottom, int rows_above, int rows_below,
                                      float *__restrict__ out) {
-    const int W = w + 2 * pad, H = h + 2 * pad;
+    const int W = w + 2 * pad_x, H = h + pad_top + pad_bottom;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
-    int sx = min(max(x - pad, 0), w - 1);
-    int sy = min(max(y - pad, -rows_above), h - 1 + rows_below);
+    int sx = min(max(x - pad_x, 0), w - 1);
+    int sy = min(max(y - pad_top, -rows_above), h - 1 + rows_below);
     out[(long)y * W + x] = in[(long)sy * in_stride + sx];
 }
 
@@ -145,9 +145,14 @@ static inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.
 
 cudaError_t launch_pad_replicate(const float *in, int w, int h, long in_stride_floats, int pad,
                                  int rows_above, int rows_below, float *out, cudaStream_t s) {
+    return launch_pad_replicate_xy(in, w, h, in_stride_floats, pad, pad, pad, rows_above, rows_below, out, s);
+}
+
+cudaError_t launch_pad_replicate_xy(const float *in, int w, int h, long in_stride_floats, int pad_x, int pad_top,
+                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s) {
     dim3 b(32, 8);
-    pad_replicate_kernel<<<grid2d(w + 2 * pad, h + 2 * pad, b), b, 0, s>>>(in, w, h, in_stride_floats, pad,
-                                                                         rows_above, rows_below, out);
+    pad_replicate_kernel<<<grid2d(w + 2 * pad_x, h + pad_top + pad_bottom, b), b, 0, s>>>(
+        in, w, h, in_stride_floats, pad_x, pad_top, pad_bottom, rows_above, rows_below, out);
     return cudaGetLastError();
 }
 

@@ -678,10 +678,10 @@ last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__
 // Second half of the fused last layer: out(y,x) = leaky(bias + sum_t P[(y+ky-1, x+kx-1)][t]), taps in
 // row-major order, for the interior [crop, ph-crop) x [crop, pw-crop).
 __global__ void __launch_bounds__(256)
-last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias, int crop, float *__restrict__ dst,
-                   long dst_stride) {
-    const int x = crop + blockIdx.x * 32 + (threadIdx.x & 31), y = crop + blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= pw - crop || y >= ph - crop) return;
+last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias, int crop_x, int crop_top,
+                   int crop_bottom, float *__restrict__ dst, long dst_stride) {
+    const int x = crop_x + blockIdx.x * 32 + (threadIdx.x & 31), y = crop_top + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw - crop_x || y >= ph - crop_bottom) return;
     float acc = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 3; ky++)
@@ -689,7 +689,7 @@ last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias
         for (int kx = 0; kx < 3; kx++)
             acc += __ldg(partial + ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * 12 + ky * 3 + kx);
     const float r = acc + bias;
-    dst[(long)(y - crop) * dst_stride + (x - crop)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
+    dst[(long)(y - crop_top) * dst_stride + (x - crop_x)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
 }
 
 __global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out) {
@@ -821,11 +821,16 @@ cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *
 
 cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias, int crop, float *dst,
                                long dst_stride_floats, cudaStream_t s) {
-    const int ow = pw - 2 * crop, oh = ph - 2 * crop;
-    if (ow < 1 || oh < 1 || crop < 1) return cudaErrorInvalidValue;
+    return launch_last_gather_xy(partial, pw, ph, bias, crop, crop, crop, dst, dst_stride_floats, s);
+}
+
+cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bias, int crop_x, int crop_top,
+                                  int crop_bottom, float *dst, long dst_stride_floats, cudaStream_t s) {
+    const int ow = pw - 2 * crop_x, oh = ph - crop_top - crop_bottom;
+    if (ow < 1 || oh < 1 || crop_x < 1 || crop_top < 1 || crop_bottom < 1) return cudaErrorInvalidValue;
     dim3 grid((ow + 31) / 32, (oh + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
-    last_gather_kernel<<<grid, 256, 0, s>>>(partial, pw, ph, bias, crop, dst, dst_stride_floats);
+    last_gather_kernel<<<grid, 256, 0, s>>>(partial, pw, ph, bias, crop_x, crop_top, crop_bottom, dst, dst_stride_floats);
     return cudaGetLastError();
 }
 
