@@ -257,6 +257,18 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
+    if args.check and world > 1:
+        got = d_out.clone()
+        exchange_halos()
+        ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(got, d_out))
+        flags = [None] * world
+        dist.all_gather_object(flags, same)
+        if rank == 0:
+            print(f"[check] per-rank bit-equality of halo={args.halo} vs one-shot input-halo band mode: {flags}", file=sys.stderr, flush=True)
+        if not all(flags):
+            raise SystemExit("multi-GPU check failed")
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, _, launches, layers, clocks = timed(step_device, args.steps, with_layers=True, sampler=sampler)
     for _ in range(min(args.warmup, 2)):
@@ -325,7 +337,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--halo", default="input", choices=["input", "per-layer"],
+    ap.add_argument("--check", action="store_true", help="multi-GPU: verify the per-layer result against the one-shot band mode, bit for bit")
+    ap.add_argument("--halo", default="per-layer", choices=["input", "per-layer"],
                     help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
