@@ -1,0 +1,189 @@
+// imageio.hpp -- cv::imread(path, IMREAD_COLOR) / cv::imwrite(path, image) for the drop-in CLI (src/main.cpp:74,190)
+// without OpenCV: 8-bit PNG (zlib) and binary PPM/PGM.  Pixels come back as 3-channel B,G,R bytes like imread does.
+#ifndef W2X_IMAGEIO_HPP_
+#define W2X_IMAGEIO_HPP_
+
+#include <zlib.h>
+
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+namespace w2xio {
+
+struct Image8 {
+    int width = 0, height = 0;
+    std::vector<uint8_t> bgr;   // [h][w][3]
+    bool empty() const { return bgr.empty(); }
+};
+
+namespace detail {
+inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+inline void put32(std::vector<uint8_t> &v, uint32_t x) { v.push_back(x >> 24); v.push_back(x >> 16); v.push_back(x >> 8); v.push_back(x); }
+inline int paeth(int a, int b, int c) {
+    int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+inline bool read_png(const std::vector<uint8_t> &f, Image8 &out, std::string &err) {
+    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+    if (f.size() < 8 || std::memcmp(f.data(), sig, 8)) { err = "not a PNG file"; return false; }
+    size_t pos = 8;
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    while (pos + 12 <= f.size()) {
+        uint32_t len = be32(&f[pos]);
+        const uint8_t *type = &f[pos + 4], *data = &f[pos + 8];
+        if (pos + 12 + len > f.size()) { err = "truncated PNG chunk"; return false; }
+        if (!std::memcmp(type, "IHDR", 4)) {
+            w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
+        } else if (!std::memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
+        else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!std::memcmp(type, "IEND", 4)) break;
+        pos += 12 + len;
+    }
+    if (!w || !h) { err = "PNG without IHDR"; return false; }
+    if (interlace) { err = "interlaced PNG is not supported"; return false; }
+    if (depth != 8 && depth != 16) { err = "only 8/16-bit PNG is supported"; return false; }
+    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch || (ctype == 3 && depth != 8)) { err = "unsupported PNG colour type"; return false; }
+    const size_t bpp = (size_t)ch * depth / 8, stride = bpp * w;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf rawlen = (uLongf)raw.size();
+    if (uncompress(raw.data(), &rawlen, idat.data(), (uLong)idat.size()) != Z_OK || rawlen != raw.size()) { err = "PNG inflate failed"; return false; }
+    std::vector<uint8_t> img(stride * h);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint8_t *src = &raw[(stride + 1) * y];
+        uint8_t *cur = &img[stride * y];
+        const uint8_t *prev = y ? &img[stride * (y - 1)] : nullptr;
+        int ft = src[0];
+        for (size_t i = 0; i < stride; i++) {
+            int a = i >= bpp ? cur[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= bpp) ? prev[i - bpp] : 0;
+            int x = src[i + 1];
+            switch (ft) {
+                case 0: break;
+                case 1: x += a; break;
+                case 2: x += b; break;
+                case 3: x += (a + b) / 2; break;
+                case 4: x += paeth(a, b, c); break;
+                default: err = "bad PNG filter"; return false;
+            }
+            cur[i] = (uint8_t)x;
+        }
+    }
+    out.width = (int)w; out.height = (int)h;
+    out.bgr.resize((size_t)w * h * 3);
+    const size_t step = depth / 8;   // 16-bit: keep the high byte (imread IMREAD_COLOR converts to 8 bit)
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const uint8_t *p = &img[i * bpp];
+        uint8_t r, g, b;
+        if (ctype == 0 || ctype == 4) r = g = b = p[0];
+        else if (ctype == 3) {
+            size_t k = (size_t)p[0] * 3;
+            if (k + 2 < plte.size()) { r = plte[k]; g = plte[k + 1]; b = plte[k + 2]; }
+            else { r = g = b = 0; }
+        } else { r = p[0]; g = p[step]; b = p[2 * step]; }
+        out.bgr[i * 3] = b; out.bgr[i * 3 + 1] = g; out.bgr[i * 3 + 2] = r;
+    }
+    return true;
+}
+
+inline bool read_pnm(const std::vector<uint8_t> &f, Image8 &out, std::string &err) {
+    size_t pos = 2;
+    auto next_int = [&](int &v) {
+        while (pos < f.size()) {
+            if (f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') pos++; }
+            else if (std::isspace(f[pos])) pos++;
+            else break;
+        }
+        v = 0;
+        bool any = false;
+        while (pos < f.size() && std::isdigit(f[pos])) { v = v * 10 + (f[pos++] - '0'); any = true; }
+        return any;
+    };
+    int w, h, mx;
+    if (!next_int(w) || !next_int(h) || !next_int(mx) || mx != 255) { err = "unsupported PNM header"; return false; }
+    pos++;
+    const int ch = f[1] == '6' ? 3 : 1;
+    if (pos + (size_t)w * h * ch > f.size()) { err = "truncated PNM"; return false; }
+    out.width = w; out.height = h;
+    out.bgr.resize((size_t)w * h * 3);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        const uint8_t *p = &f[pos + i * ch];
+        uint8_t r = p[0], g = ch == 3 ? p[1] : p[0], b = ch == 3 ? p[2] : p[0];
+        out.bgr[i * 3] = b; out.bgr[i * 3 + 1] = g; out.bgr[i * 3 + 2] = r;
+    }
+    return true;
+}
+}  // namespace detail
+
+// cv::imread(path, cv::IMREAD_COLOR): empty image on failure (the reference does not check, src/main.cpp:74)
+inline Image8 imread(const std::string &path, std::string *err_out = nullptr) {
+    Image8 img;
+    std::string err;
+    std::ifstream in(path, std::ios::binary);
+    if (!in) { err = "cannot open " + path; }
+    else {
+        std::vector<uint8_t> f((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        if (f.size() > 2 && f[0] == 'P' && (f[1] == '6' || f[1] == '5')) detail::read_pnm(f, img, err);
+        else detail::read_png(f, img, err);
+        if (!err.empty()) img = Image8();
+    }
+    if (err_out) *err_out = err;
+    return img;
+}
+
+// cv::imwrite(path, image): format by extension (.png, .ppm)
+inline bool imwrite(const std::string &path, const uint8_t *bgr, int w, int h) {
+    std::string ext = path.size() >= 4 ? path.substr(path.size() - 4) : "";
+    for (auto &c : ext) c = (char)std::tolower(c);
+    std::ofstream out(path, std::ios::binary);
+    if (!out) return false;
+    if (ext == ".ppm") {
+        out << "P6\n" << w << " " << h << "\n255\n";
+        std::vector<uint8_t> row((size_t)w * 3);
+        for (int y = 0; y < h; y++) {
+            for (int x = 0; x < w; x++) { const uint8_t *p = bgr + ((size_t)y * w + x) * 3; row[x * 3] = p[2]; row[x * 3 + 1] = p[1]; row[x * 3 + 2] = p[0]; }
+            out.write(reinterpret_cast<const char *>(row.data()), (std::streamsize)row.size());
+        }
+        return (bool)out;
+    }
+    // PNG, 8-bit RGB, filter type 0
+    std::vector<uint8_t> raw((size_t)(w * 3 + 1) * h);
+    for (int y = 0; y < h; y++) {
+        uint8_t *r = &raw[(size_t)(w * 3 + 1) * y];
+        r[0] = 0;
+        for (int x = 0; x < w; x++) { const uint8_t *p = bgr + ((size_t)y * w + x) * 3; r[1 + x * 3] = p[2]; r[2 + x * 3] = p[1]; r[3 + x * 3] = p[0]; }
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> comp(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 3) != Z_OK) return false;
+    comp.resize(clen);
+    auto chunk = [&](const char *type, const std::vector<uint8_t> &data) {
+        std::vector<uint8_t> c;
+        detail::put32(c, (uint32_t)data.size());
+        c.insert(c.end(), type, type + 4);
+        c.insert(c.end(), data.begin(), data.end());
+        uint32_t crc = (uint32_t)crc32(0L, c.data() + 4, (uInt)(c.size() - 4));
+        detail::put32(c, crc);
+        out.write(reinterpret_cast<const char *>(c.data()), (std::streamsize)c.size());
+    };
+    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+    out.write(reinterpret_cast<const char *>(sig), 8);
+    std::vector<uint8_t> ihdr;
+    detail::put32(ihdr, (uint32_t)w); detail::put32(ihdr, (uint32_t)h);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
+    chunk("IHDR", ihdr);
+    chunk("IDAT", comp);
+    chunk("IEND", {});
+    return (bool)out;
+}
+
+}  // namespace w2xio
+#endif
