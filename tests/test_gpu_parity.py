@@ -273,6 +273,46 @@ def test_fused_and_separate_last_layer_agree(ctxs, models, oracle_mod, oracle_mo
     assert np.abs(fused - sep).max() <= 5e-6
 
 
+@pytest.mark.parametrize("widths", [(32, 64, 128, 32), (128, 64, 32, 64), (64, 128, 32, 128), (128, 128, 64), (32,), (64, 32, 32)])
+def test_random_models_cover_every_tcgen05_shape(w2x, ctxs, oracle_mod, ncpu, widths):
+    """Every (Cin, Cout) instantiation of the tcgen05 layer kernel, stacked and unstacked, with the last layer folded
+    into a 32-, 64- and 128-wide epilogue: random weights, both engines against the CPU oracle."""
+    dims = [(1, widths[0])] + [(widths[i], widths[i + 1]) for i in range(len(widths) - 1)] + [(widths[-1], 1)]
+    om = oracle_mod.OracleModel.random(dims, seed=sum(widths))
+    m = w2x.Model.from_arrays(om.weights, om.biases)
+    x = oracle_mod.seeded_plane(83, 59, 5, "uniform")
+    ref = om.convert(x, n_job=ncpu)
+    scale = max(1.0, float(np.abs(ref).max()))
+    for engine, _, tol in ENGINES:
+        y = ctxs[engine].convert_plane(m, x)
+        assert y.shape == ref.shape
+        assert np.abs(y - ref).max() <= tol * scale, (engine, widths)
+    # the separate-last-layer path too
+    ctx = ctxs["tc"]
+    try:
+        ctx.debug_set_fuse_last(False)
+        y = ctx.convert_plane(m, x)
+    finally:
+        ctx.debug_set_fuse_last(True)
+    assert np.abs(y - ref).max() <= TC_TOL * scale
+
+
+def test_unsupported_shapes_fall_back_to_the_fp32_engine_or_fail_loudly(w2x, ctxs, oracle_mod, ncpu):
+    """A model the tensor-core engine cannot take (48-wide layer): AUTO picks the fp32 CUDA engine, TC refuses."""
+    om = oracle_mod.OracleModel.random([(1, 48), (48, 1)], seed=3)
+    m = w2x.Model.from_arrays(om.weights, om.biases)
+    x = oracle_mod.seeded_plane(40, 30, 2, "uniform")
+    ref = om.convert(x, n_job=ncpu)
+    auto = w2x.Context(0)
+    try:
+        assert np.abs(auto.convert_plane(m, x) - ref).max() <= FP32_TOL
+    finally:
+        auto.close()
+    with pytest.raises(w2x.W2xError) as ei:
+        ctxs["tc"].convert_plane(m, x)
+    assert ei.value.status == 7
+
+
 def test_launch_counter_and_timing(ctxs, models, oracle_mod):
     ctx = ctxs["tc"]
     x = oracle_mod.seeded_plane(64, 64, 1, "uniform")
