@@ -144,6 +144,21 @@ def test_scratch_limit_bands_are_bit_identical(ctxs, models, oracle_mod, engine,
     assert np.array_equal(whole, banded)
 
 
+@pytest.mark.parametrize("engine,eng_id,tol", ENGINES)
+def test_host_copy_pipeline_bands_are_bit_identical(ctxs, models, oracle_mod, engine, eng_id, tol):
+    """w2x_convert_plane overlaps H2D / layers / D2H over row bands for big planes; any band count gives the same bits."""
+    x = oracle_mod.seeded_plane(120, 260, 14, "uniform")
+    ctx = ctxs[engine]
+    try:
+        ctx.debug_set_host_bands(1)
+        single = ctx.convert_plane(models["noise1"], x)
+        for nb in (2, 3, 8):
+            ctx.debug_set_host_bands(nb)
+            assert np.array_equal(ctx.convert_plane(models["noise1"], x), single), nb
+    finally:
+        ctx.debug_set_host_bands(0)
+
+
 def test_engines_agree_with_each_other(ctxs, models, oracle_mod):
     x = oracle_mod.seeded_plane(300, 200, 31, "smooth")
     a = ctxs["fp32"].convert_plane(models["noise2"], x)
@@ -273,7 +288,7 @@ def test_fused_and_separate_last_layer_agree(ctxs, models, oracle_mod, oracle_mo
     assert np.abs(fused - sep).max() <= 5e-6
 
 
-@pytest.mark.parametrize("widths", [(32, 64, 128, 32), (128, 64, 32, 64), (64, 128, 32, 128), (128, 128, 64), (32,), (64, 32, 32)])
+@pytest.mark.parametrize("widths", [(32, 64, 128, 32), (128, 64, 32, 64), (64, 128, 32, 128), (128, 128, 64), (32, 32), (64, 32, 32)])
 def test_random_models_cover_every_tcgen05_shape(w2x, ctxs, oracle_mod, ncpu, widths):
     """Every (Cin, Cout) instantiation of the tcgen05 layer kernel, stacked and unstacked, with the last layer folded
     into a 32-, 64- and 128-wide epilogue: random weights, both engines against the CPU oracle."""

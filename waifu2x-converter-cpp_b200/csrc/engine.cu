@@ -67,6 +67,9 @@ struct w2x_ctx {
     float *io_buf[2] = {nullptr, nullptr};   // device staging for the host-buffer entry points
     size_t io_bytes[2] = {0, 0};
     bool tc_ready = false;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies of w2x_convert_plane overlap the compute stream
+    cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
+    int host_bands = 0;                                   // 0 = automatic (up to 4 bands of >= 512 rows), 1 = no pipelining
     unsigned long long *prof_buf = nullptr;   // [16 layers][PROF_MAX_CTAS][PROF_WORDS], debug profile
 };
 
@@ -572,6 +575,12 @@ int w2x_ctx_create(int device, w2x_ctx **out_ctx) {
     DeviceGuard g(device);
     CU_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    CU_CHECK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        CU_CHECK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+    }
     *out_ctx = ctx.release();
     return W2X_OK;
 }
@@ -594,6 +603,12 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
     cudaFree(ctx->prof_buf);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.e0); cudaEventDestroy(s.e1); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 8; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -673,6 +688,13 @@ W2X_API int w2x_debug_tc_profile_read(w2x_ctx *ctx, int layer, unsigned long lon
     return W2X_OK;
 }
 
+// Probe switch (not part of the stable ABI): number of host-copy pipeline bands of w2x_convert_plane (0 auto, 1 off).
+W2X_API int w2x_debug_set_host_bands(w2x_ctx *ctx, int bands) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->host_bands = bands < 0 ? 0 : bands;
+    return W2X_OK;
+}
+
 // Probe switch (not part of the stable ABI): 1 = fold the last layer into the preceding tcgen05 layer (default), 0 = separate kernel.
 W2X_API int w2x_debug_set_fuse_last(w2x_ctx *ctx, int on) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
@@ -719,13 +741,45 @@ int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int
         int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], bytes);
         if (rc) return rc;
     }
-    CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0], (size_t)width * 4, in, in_stride_bytes, (size_t)width * 4, (size_t)height,
-                               cudaMemcpyHostToDevice, ctx->stream));
-    int rc = convert_device(ctx, model, ctx->io_buf[0], width, height, (size_t)width * 4, 0, 0, ctx->io_buf[1],
-                            (size_t)width * 4, block_splitting);
-    if (rc) return rc;
-    CU_CHECK(cudaMemcpy2DAsync(out, out_stride_bytes, ctx->io_buf[1], (size_t)width * 4, (size_t)width * 4, (size_t)height,
-                               cudaMemcpyDeviceToHost, ctx->stream));
+    // Large planes are cut into row bands so that the upload of band i+1 and the download of band i-1 overlap the
+    // layers of band i (copy engines + compute run concurrently); each band re-reads n real rows of context from its
+    // neighbours, which keeps the result bit-identical to the single-pass path.
+    const int n_model = model ? (int)model->layers.size() : 0;
+    int nb = ctx->host_bands > 0 ? ctx->host_bands : std::min(4, height / 512);
+    const bool literal_walk = block_splitting && ctx->walk == W2X_WALK_BLOCKS && w2x_requires_splitting(width, height);
+    if (nb > 8) nb = 8;
+    if (nb < 2 || literal_walk || ctx->log || !model || height / nb < 2 * n_model) {   // (a log sink wants the reference's exact line sequence)
+        CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0], (size_t)width * 4, in, in_stride_bytes, (size_t)width * 4, (size_t)height,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        int rc = convert_device(ctx, model, ctx->io_buf[0], width, height, (size_t)width * 4, 0, 0, ctx->io_buf[1],
+                                (size_t)width * 4, block_splitting);
+        if (rc) return rc;
+        CU_CHECK(cudaMemcpy2DAsync(out, out_stride_bytes, ctx->io_buf[1], (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        CU_CHECK(cudaStreamSynchronize(ctx->stream));
+        return W2X_OK;
+    }
+    std::vector<int> r0((size_t)nb + 1);
+    for (int i = 0; i <= nb; i++) r0[(size_t)i] = (int)((long)height * i / nb);
+    for (int i = 0; i < nb; i++) {
+        const int y = r0[(size_t)i], rows = r0[(size_t)i + 1] - y;
+        CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0] + (size_t)y * width, (size_t)width * 4, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes,
+                                   in_stride_bytes, (size_t)width * 4, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU_CHECK(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+    }
+    for (int i = 0; i < nb; i++) {
+        const int y = r0[(size_t)i], rows = r0[(size_t)i + 1] - y;
+        CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[std::min(i + 1, nb - 1)], 0));   // needs the first rows of the next band
+        const int above = i > 0 ? n_model : 0, below = i + 1 < nb ? n_model : 0;
+        int rc = convert_device(ctx, model, ctx->io_buf[0] + (size_t)y * width, width, rows, (size_t)width * 4, above, below,
+                                ctx->io_buf[1] + (size_t)y * width, (size_t)width * 4, 0);
+        if (rc) return rc;
+        CU_CHECK(cudaEventRecord(ctx->ev_done[i], ctx->stream));
+        CU_CHECK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[i], 0));
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, ctx->io_buf[1] + (size_t)y * width,
+                                   (size_t)width * 4, (size_t)width * 4, (size_t)rows, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CU_CHECK(cudaStreamSynchronize(ctx->copy_out));
     CU_CHECK(cudaStreamSynchronize(ctx->stream));
     return W2X_OK;
 }

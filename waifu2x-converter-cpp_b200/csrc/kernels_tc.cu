@@ -584,7 +584,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
 // First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
 // writes the NHWC hi/lo frame the tcgen05 layers consume.  One thread per pixel.
 template <int COUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const float *__restrict__ wgt,
                    const float *__restrict__ bias, __half *__restrict__ out) {
     __shared__ float s_w[COUT * 9];
@@ -605,8 +605,8 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
     const size_t plane_elems = (size_t)ph * pw * COUT;
     __half *dst_hi = out + ((size_t)y * pw + x) * COUT;
     __half *dst_lo = dst_hi + plane_elems;
-#pragma unroll
-    for (int c8 = 0; c8 < COUT / 8; c8++) {
+#pragma unroll 1
+    for (int c8 = 0; c8 < COUT / 8; c8++) {   // not unrolled: keeps the kernel at <= 64 registers, 4 blocks/SM (HBM-write-bound)
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
