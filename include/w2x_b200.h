@@ -101,6 +101,15 @@ W2X_API int w2x_ctx_create(int device, w2x_ctx **out_ctx);
 W2X_API void w2x_ctx_destroy(w2x_ctx *ctx);
 W2X_API int w2x_ctx_set_engine(w2x_ctx *ctx, int engine);
 W2X_API int w2x_ctx_get_engine(const w2x_ctx *ctx);
+/* Arithmetic of the tcgen05 engine (both keep fp32 accumulators and meet the 1e-4 gate of BASELINE.json):
+ *   W2X_PRECISION_F16X3     x*w = xh*wh + xl*wh + xh*wl, three fp16 tensor-core products (default;
+ *                           measured <= 8e-6 max-abs against the reference CPU path on white noise)
+ *   W2X_PRECISION_F16_F8X2  the two correction products run on e4m3 copies of the operands at twice the
+ *                           tensor rate (2.0 instead of 3.0 pass-equivalents; ~2-3e-5 max-abs on white noise) */
+#define W2X_PRECISION_F16X3 0
+#define W2X_PRECISION_F16_F8X2 1
+W2X_API int w2x_ctx_set_precision(w2x_ctx *ctx, int precision);
+W2X_API int w2x_ctx_get_precision(const w2x_ctx *ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = the ctx's own stream. */
 W2X_API int w2x_ctx_set_stream(w2x_ctx *ctx, void *cuda_stream);
 /* Block until everything queued by this context has finished. */
@@ -173,9 +182,9 @@ W2X_API int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int
 W2X_API void w2x_band_destroy(w2x_band *band);
 W2X_API int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes);
 W2X_API int w2x_band_step(w2x_band *band, int step);
-/* Segments to exchange after `step` was queued: n_segments (<= 2) contiguous device ranges of
+/* Segments to exchange after `step` was queued: n_segments (<= 4) contiguous device ranges of
  * seg_bytes each per direction; send_* hold this rank's boundary row, recv_* its halo row.
- * Pointers for a missing neighbour are NULL.  Arrays must have room for 2 entries. */
+ * Pointers for a missing neighbour are NULL.  Arrays must have room for 4 entries. */
 W2X_API int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up,
                           void **send_down, void **recv_down, size_t *seg_bytes);
 W2X_API int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes);

@@ -5,6 +5,8 @@ the CPU oracle and the committed golden vectors.  Floating-point path: tolerance
   FP32_TOL   5e-6  fp32 CUDA-core engine: same association as the reference, FMA contraction only
   TC_TOL     2e-5  tcgen05 engine: 3-pass fp16 split, fp32 TMEM accumulation (CPU emulation of the
                    scheme measures 7e-7, tests/test_numerics_model.py; the rest is accumulation order)
+  F8_TOL     6e-5  tcgen05 engine, W2X_PRECISION_F16_F8X2: fp16 main product + two e4m3 correction
+                   products (CPU emulation: 2.1e-5 on white noise, tests/test_numerics_model.py)
 """
 import json
 import os
@@ -19,12 +21,14 @@ pytestmark = pytest.mark.gpu
 GOLD_TOL = 1e-4
 FP32_TOL = 5e-6
 TC_TOL = 2e-5
-ENGINES = [("fp32", 1, FP32_TOL), ("tc", 2, TC_TOL)]
+F8_TOL = 6e-5
+ENGINES = [("fp32", 1, FP32_TOL), ("tc", 2, TC_TOL), ("tc8", 2, F8_TOL)]
 
 
 @pytest.fixture(scope="module")
 def ctxs(w2x):
     c = {name: w2x.Context(0, engine=eng) for name, eng, _ in ENGINES}
+    c["tc8"].set_precision(w2x.PRECISION_F16_F8X2)
     yield c
     for v in c.values():
         v.close()
@@ -75,7 +79,7 @@ def test_per_layer_filter_against_reference_golden(ctxs, models, engine, eng_id,
     z = np.load(golden_path("layers_32x24.npz"))
     m = models["scale2.0x"]
     for li in range(7):
-        if engine == "tc" and li in (0, 6):
+        if engine.startswith("tc") and li in (0, 6):
             continue          # 1->32 and 128->1 have no MMA form; covered by the whole-path tests
         out = ctxs[engine].filter_layer(m, li, z[f"in{li}"])
         # these single-layer probes feed uniform noise into every plane, so outputs reach |5..7|:
@@ -164,6 +168,7 @@ def test_engines_agree_with_each_other(ctxs, models, oracle_mod):
     a = ctxs["fp32"].convert_plane(models["noise2"], x)
     b = ctxs["tc"].convert_plane(models["noise2"], x)
     assert np.abs(a - b).max() <= TC_TOL
+    assert np.abs(a - ctxs["tc8"].convert_plane(models["noise2"], x)).max() <= F8_TOL
 
 
 def test_cfg5_tile_512_noise2(ctxs, models, oracle_mod, oracle_models, ncpu):

@@ -33,3 +33,37 @@ def test_single_pass_fp16_would_fail_the_gate(oracle_mod, oracle_models, ncpu):
         a = T.leaky(v)
     err = np.abs(a[0, 0, n:-n, n:-n].numpy() - ref).max()
     assert err > 1e-4
+
+
+def test_fp16_plus_two_e4m3_corrections_is_inside_the_gate(oracle_mod, oracle_models, ncpu):
+    """W2X_PRECISION_F16_F8X2: xh*wh in fp16, xl*wh and xh*wl on e4m3 copies (scale exponents F8_A = 10, F8_C = 1).
+    Emulated with torch.float8_e4m3fn: ~2e-5 on white noise, 4x inside the 1e-4 gate."""
+    import torch
+    import torch.nn.functional as F
+    A, Cc = 10, 1
+
+    def e4m3(t):
+        return t.to(torch.float8_e4m3fn).to(torch.float64)
+
+    worst = 0.0
+    for name in ("scale2.0x", "noise1"):
+        om = oracle_models[name]
+        x = oracle_mod.seeded_plane(96, 80, 4, "uniform")
+        ref = om.convert(x, n_job=ncpu)
+        n = len(om)
+        act = torch.from_numpy(np.pad(x, n, mode="edge"))[None, None]
+        act = T.leaky(F.conv2d(F.pad(act, (1, 1, 1, 1), mode="replicate"), torch.from_numpy(om.weights[0])) +
+                      torch.from_numpy(om.biases[0].astype(np.float32))[None, :, None, None])
+        for li in range(1, n - 1):
+            ws = T.wscale_of(om.weights[li])
+            w = torch.from_numpy(om.weights[li]) * ws
+            wh = w.half().float()
+            xs = act * 16.0
+            xh = xs.half().float()
+            acc = (F.conv2d(xh.double(), wh.double(), padding=1) +
+                   F.conv2d(e4m3((xs - xh) * 2.0 ** A), e4m3(wh * 2.0 ** -A), padding=1) +
+                   F.conv2d(e4m3(xh * 2.0 ** -Cc), e4m3((w - wh) * 2.0 ** Cc), padding=1))
+            act = T.leaky(acc.float() * np.float32(1 / (ws * 16.0)) + torch.from_numpy(om.biases[li].astype(np.float32))[None, :, None, None])
+        out = T.leaky(F.conv2d(act, torch.from_numpy(om.weights[-1]), padding=1) + np.float32(om.biases[-1][0]))[0, 0, n:-n, n:-n].numpy()
+        worst = max(worst, float(np.abs(out - ref).max()))
+    assert worst <= 4e-5, worst

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libw2x_b200.so")
 
 ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
+PRECISION_F16X3, PRECISION_F16_F8X2 = 0, 1
 WALK_FUSED, WALK_BLOCKS = 0, 1
 
 STATUS = {0: "W2X_OK", 1: "W2X_ERR_ARG", 2: "W2X_ERR_IO", 3: "W2X_ERR_PARSE", 4: "W2X_ERR_MODEL",
@@ -27,6 +28,7 @@ ABI_SYMBOLS = (
     "w2x_model_layer_count", "w2x_model_layer_dims", "w2x_model_layer_params", "w2x_set_jobs", "w2x_get_jobs",
     "w2x_set_block_size", "w2x_set_block_size_exp2_square", "w2x_get_block_size", "w2x_requires_splitting",
     "w2x_block_table", "w2x_ctx_create", "w2x_ctx_destroy", "w2x_ctx_set_engine", "w2x_ctx_get_engine",
+    "w2x_ctx_set_precision", "w2x_ctx_get_precision",
     "w2x_ctx_set_stream", "w2x_ctx_synchronize", "w2x_ctx_set_log", "w2x_ctx_set_block_walk",
     "w2x_ctx_set_scratch_limit", "w2x_convert_plane", "w2x_convert_plane_device", "w2x_filter_layer",
     "w2x_filter_layer_device", "w2x_convert_band_device", "w2x_ctx_launch_count", "w2x_ctx_set_timing",
@@ -82,6 +84,8 @@ def lib():
     L.w2x_ctx_destroy.restype = None
     L.w2x_ctx_set_engine.argtypes = [vp, ci]
     L.w2x_ctx_get_engine.argtypes = [vp]
+    L.w2x_ctx_set_precision.argtypes = [vp, ci]
+    L.w2x_ctx_get_precision.argtypes = [vp]
     L.w2x_ctx_set_stream.argtypes = [vp, vp]
     L.w2x_ctx_synchronize.argtypes = [vp]
     L.w2x_ctx_set_log.argtypes = [vp, LOG_FN, vp]
@@ -107,6 +111,7 @@ def lib():
     L.w2x_debug_set_mma_mode.argtypes = [vp, ci]
     L.w2x_debug_set_host_bands.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
+    L.w2x_debug_tc_pack8.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(cs)]
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
     L.w2x_debug_tc_profile_read.argtypes = [vp, ci, C.POINTER(C.c_uint64), C.POINTER(ci)]
     L.w2x_debug_tc_pack.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint16)), C.POINTER(cs), C.POINTER(ci), C.POINTER(ci),
@@ -210,6 +215,13 @@ class Model:
         return np.ctypeslib.as_array(dp, shape=(n.value,)).copy(), nch.value, kbl.value, ws.value
 
 
+    def debug_tc_pack8(self, layer):
+        """uint8 image [chunk][tap][kblock][wh fp16 n_out*64 B | wh8 n_out*32 B | wl8 n_out*32 B] of the f8 flavour."""
+        dp, n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        _check(lib().w2x_debug_tc_pack8(self._h, layer, C.byref(dp), C.byref(n)))
+        return None if n.value == 0 else np.ctypeslib.as_array(dp, shape=(n.value,)).copy()
+
+
 # ---- Context ------------------------------------------------------------------------------------
 class Context:
     def __init__(self, device=0, engine=ENGINE_AUTO):
@@ -228,6 +240,8 @@ class Context:
     __del__ = close
 
     def set_engine(self, engine): _check(lib().w2x_ctx_set_engine(self._h, engine))
+    def set_precision(self, precision): _check(lib().w2x_ctx_set_precision(self._h, precision))
+    def get_precision(self): return lib().w2x_ctx_get_precision(self._h)
     def set_stream(self, stream_ptr): _check(lib().w2x_ctx_set_stream(self._h, C.c_void_p(stream_ptr)))
     def synchronize(self): _check(lib().w2x_ctx_synchronize(self._h))
     def set_block_walk(self, mode): _check(lib().w2x_ctx_set_block_walk(self._h, mode))
@@ -340,6 +354,6 @@ class Band:
     def halo(self, k):
         """-> list of (send_up, recv_up, send_down, recv_down, nbytes) device-pointer tuples (None = no neighbour)."""
         n, nb = C.c_int(), C.c_size_t()
-        su, ru, sd, rd = ((C.c_void_p * 2)() for _ in range(4))
+        su, ru, sd, rd = ((C.c_void_p * 4)() for _ in range(4))
         _check(lib().w2x_band_halo(self._h, k, C.byref(n), su, ru, sd, rd, C.byref(nb)))
         return [(su[i], ru[i], sd[i], rd[i], nb.value) for i in range(n.value)]

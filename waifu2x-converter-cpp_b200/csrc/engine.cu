@@ -32,6 +32,7 @@ struct DevModel {                       // device-resident copy of one model
     std::vector<float *> w;             // per layer [Cout][Cin][9] fp32
     std::vector<float *> b;             // per layer [Cout] fp32  ((float)bias, src/modelHandler.cpp:147)
     std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
+    std::vector<uint8_t *> pack8;       // same for the "f8" flavour (fp16 main product + e4m3 corrections)
     std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
     float *last_w_t = nullptr;          // last layer's weights transposed to [9][Cin] (fused last layer)
 };
@@ -48,6 +49,7 @@ struct w2x_ctx {
     int walk = W2X_WALK_FUSED;
     int desc_mode = 0;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
+    int precision = W2X_PRECISION_F16X3;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     size_t scratch_limit = (size_t)16 << 30;
@@ -120,6 +122,7 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
     dm.w.assign(n, nullptr);
     dm.b.assign(n, nullptr);
     dm.pack.assign(n, nullptr);
+    dm.pack8.assign(n, nullptr);
     dm.out_scale.assign(n, 1.f);
     for (size_t i = 0; i < n; i++) {
         const Layer &L = m->layers[i];
@@ -135,6 +138,8 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
             CU_CHECK(cudaMalloc(&dm.pack[i], P.bytes.size() * 2));
             CU_CHECK(cudaMemcpyAsync(dm.pack[i], P.bytes.data(), P.bytes.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
             dm.out_scale[i] = 1.0f / (P.wscale * tc::ACT_SCALE);
+            CU_CHECK(cudaMalloc(&dm.pack8[i], P.bytes8.size()));
+            CU_CHECK(cudaMemcpyAsync(dm.pack8[i], P.bytes8.data(), P.bytes8.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
     }
     if (m->tc_eligible) {
@@ -246,6 +251,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         return W2X_OK;
     }
     // ---- tcgen05 engine ----
+    const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
     int rc = ensure_tc(ctx);
     if (rc) return rc;
     const size_t need = tc::act_bytes(maxc, pw, ph);
@@ -258,7 +264,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         const Layer &L = m->layers[0];
         logf(ctx, "Iteration #%d...", 1);
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, dm->w[0], dm->b[0], L.n_out, cur, ctx->stream));
+        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, dm->w[0], dm->b[0], L.n_out, cur, ctx->stream, f8));
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
@@ -266,18 +272,20 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
     for (int li = 1; li + 1 < n; li++) {
         const Layer &L = m->layers[(size_t)li];
         logf(ctx, "Iteration #%d...", li + 1);
-        CUtensorMap map;
-        int e = tc::make_act_tensor_map(&map, cur, L.n_in, pw, ph);
+        CUtensorMap map, map8;
+        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, cur, L.n_in, pw, ph) : tc::make_act_tensor_map(&map, cur, L.n_in, pw, ph);
         if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, li);
         const bool fused_here = fuse && li == n - 2;
         {
             LayerTimer t(ctx, li);
-            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)li], dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph,
-                                         dm->out_scale[(size_t)li], ctx->desc_mode, ctx->num_sms, ctx->stream,
+            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)li] : (const void *)dm->pack[(size_t)li],
+                                         dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
+                                         ctx->num_sms, ctx->stream,
                                          ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
-                                         fused_here ? dm->last_w_t : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr));
+                                         fused_here ? dm->last_w_t : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
+                                         f8 ? &map8 : nullptr));
         }
-        note_kernel(ctx, li, fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
+        note_kernel(ctx, li, f8 ? (fused_here ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
         ctx->launches++;
         std::swap(cur, nxt);
     }
@@ -291,7 +299,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
             note_kernel(ctx, n - 1, "last_gather");
         } else {
             CU_CHECK(tc::launch_last(cur, L.n_in, pw, ph, dm->w[(size_t)n - 1], static_cast<float>(L.b[0]), n, dst,
-                                     dst_stride, ctx->stream));
+                                     dst_stride, ctx->stream, f8));
             note_kernel(ctx, n - 1, "last_Nx1");
         }
         ctx->launches++;
@@ -468,22 +476,24 @@ int w2x_band_step(w2x_band *band, int step) {
     const w2x_model *m = band->model;
     DevModel *dm = band->dm;
     const Layer &L = m->layers[(size_t)step];
+    const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
     if (step == 0) {
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, dm->w[0], dm->b[0], L.n_out, band->act[0], ctx->stream));
+        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, dm->w[0], dm->b[0], L.n_out, band->act[0], ctx->stream, f8));
         band->cur = 0;
         note_kernel(ctx, 0, "first_1xN");
     } else {
         __half *in = band->act[band->cur], *out = band->act[band->cur ^ 1];
-        CUtensorMap map;
-        int e = tc::make_act_tensor_map(&map, in, L.n_in, band->pw, band->hf);
+        CUtensorMap map, map8;
+        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, in, L.n_in, band->pw, band->hf) : tc::make_act_tensor_map(&map, in, L.n_in, band->pw, band->hf);
         if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, step);
         const bool fused = step == band->n - 2;
         {
             LayerTimer t(ctx, step);
-            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)step], dm->b[(size_t)step], out, L.n_in, L.n_out, band->pw, band->hf,
-                                         dm->out_scale[(size_t)step], 0, ctx->num_sms, ctx->stream, nullptr,
-                                         fused ? dm->last_w_t : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr));
+            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)step] : (const void *)dm->pack[(size_t)step],
+                                         dm->b[(size_t)step], out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
+                                         ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t : nullptr,
+                                         fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr));
         }
         note_kernel(ctx, step, fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
         band->cur ^= 1;
@@ -500,27 +510,40 @@ int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, voi
         return fail(W2X_ERR_ARG, "w2x_band_halo: call it for the step that was queued last");
     const int n = band->n;
     char *base = reinterpret_cast<char *>(band->act[band->cur]);
-    size_t row_bytes, plane_bytes;
+    // every segment: `bytes` at  base + plane_off + row * pitch + in_row
+    struct Seg { size_t plane_off, pitch, in_row; } seg[4];
+    size_t bytes;
     int nseg;
     if (step == n - 2) {              // per-pixel tap partials [hf][pw][12] fp32
-        row_bytes = (size_t)band->pw * 12 * sizeof(float);
-        plane_bytes = 0;
+        bytes = (size_t)band->pw * 12 * sizeof(float);
+        seg[0] = {0, bytes, 0};
         nseg = 1;
-    } else {                          // activation frame [2][hf][pw][C] fp16
-        const int C = band->model->layers[(size_t)step].n_out;
-        row_bytes = (size_t)band->pw * C * 2;
-        plane_bytes = row_bytes * band->hf;
-        nseg = 2;
+    } else {
+        const size_t C = (size_t)band->model->layers[(size_t)step].n_out, px = (size_t)band->pw * C, fr = px * band->hf;
+        if (band->ctx->precision == W2X_PRECISION_F16_F8X2) {   // frame [xh fp16][xh8][xl8]: four segments of pw*C bytes
+            bytes = px;
+            seg[0] = {0, 2 * px, 0};
+            seg[1] = {0, 2 * px, px};
+            seg[2] = {2 * fr, px, 0};
+            seg[3] = {3 * fr, px, 0};
+            nseg = 4;
+        } else {                                                 // frame [hi fp16][lo fp16]: two segments of pw*C*2 bytes
+            bytes = 2 * px;
+            seg[0] = {0, 2 * px, 0};
+            seg[1] = {2 * fr, 2 * px, 0};
+            nseg = 2;
+        }
     }
     *n_segments = nseg;
-    *seg_bytes = row_bytes;
-    for (int s = 0; s < 2; s++) {
-        char *pl = base + plane_bytes * s;
+    *seg_bytes = bytes;
+    for (int s = 0; s < 4; s++) {
         const bool on = s < nseg;
-        send_up[s] = on && band->up ? pl + row_bytes * 1 : nullptr;                       // first owned row
-        recv_up[s] = on && band->up ? pl : nullptr;                                      // halo row above
-        send_down[s] = on && band->down ? pl + row_bytes * (size_t)(band->hf - 2) : nullptr;   // last owned row
-        recv_down[s] = on && band->down ? pl + row_bytes * (size_t)(band->hf - 1) : nullptr;   // halo row below
+        char *pl = on ? base + seg[s].plane_off + seg[s].in_row : nullptr;
+        const size_t pitch = on ? seg[s].pitch : 0;
+        send_up[s] = on && band->up ? pl + pitch * 1 : nullptr;                                 // first owned row
+        recv_up[s] = on && band->up ? pl : nullptr;                                            // halo row above
+        send_down[s] = on && band->down ? pl + pitch * (size_t)(band->hf - 2) : nullptr;         // last owned row
+        recv_down[s] = on && band->down ? pl + pitch * (size_t)(band->hf - 1) : nullptr;         // halo row below
     }
     return W2X_OK;
 }
@@ -593,6 +616,7 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
         for (auto p : kv.second.w) cudaFree(p);
         for (auto p : kv.second.b) cudaFree(p);
         for (auto p : kv.second.pack) cudaFree(p);
+        for (auto p : kv.second.pack8) cudaFree(p);
         cudaFree(kv.second.last_w_t);
     }
     for (int i = 0; i < 2; i++) {
@@ -620,6 +644,14 @@ int w2x_ctx_set_engine(w2x_ctx *ctx, int engine) {
     return W2X_OK;
 }
 int w2x_ctx_get_engine(const w2x_ctx *ctx) { return ctx ? ctx->engine : -1; }
+
+int w2x_ctx_set_precision(w2x_ctx *ctx, int precision) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (precision != W2X_PRECISION_F16X3 && precision != W2X_PRECISION_F16_F8X2) return fail(W2X_ERR_ARG, "unknown precision mode %d", precision);
+    ctx->precision = precision;
+    return W2X_OK;
+}
+int w2x_ctx_get_precision(const w2x_ctx *ctx) { return ctx ? ctx->precision : -1; }
 
 int w2x_ctx_set_stream(w2x_ctx *ctx, void *cuda_stream) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
@@ -808,17 +840,19 @@ int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, con
         rc = ensure(&ctx->buf[1], &ctx->buf_bytes[1], tc::act_bytes(L.n_out, pw, ph));
         if (rc) return rc;
         __half *fin = static_cast<__half *>(ctx->buf[0]), *fout = static_cast<__half *>(ctx->buf[1]);
-        CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream));
-        CUtensorMap map;
-        int e = tc::make_act_tensor_map(&map, fin, L.n_in, pw, ph);
+        const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
+        CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream, f8));
+        CUtensorMap map, map8;
+        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, fin, L.n_in, pw, ph) : tc::make_act_tensor_map(&map, fin, L.n_in, pw, ph);
         if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", e);
         {
             LayerTimer t(ctx, layer);
-            CU_CHECK(tc::launch_tc_layer(&map, dm->pack[(size_t)layer], dm->b[(size_t)layer], fout, L.n_in, L.n_out, pw, ph,
-                                         dm->out_scale[(size_t)layer], ctx->desc_mode, ctx->num_sms, ctx->stream));
+            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)layer] : (const void *)dm->pack[(size_t)layer],
+                                         dm->b[(size_t)layer], fout, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)layer], f8,
+                                         ctx->num_sms, ctx->stream, nullptr, nullptr, nullptr, f8 ? &map8 : nullptr));
         }
-        CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream));
-        note_kernel(ctx, layer, "tcgen05_f16x3");
+        CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream, f8));
+        note_kernel(ctx, layer, f8 ? "tcgen05_f16+f8x2" : "tcgen05_f16x3");
         ctx->launches += 3;
         return W2X_OK;
     }

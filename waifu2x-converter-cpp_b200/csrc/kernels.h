@@ -36,12 +36,14 @@ cudaError_t init_kernels();
 // First layer (Cin = 1): fp32 plane (ROI with stride) -> NHWC hi/lo frame of the same size (pw x ph),
 // same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
-                         const float *bias, int cout, __half *out, cudaStream_t s);
+                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0);
 // tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
-cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out,
-                            int cin, int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms,
+// f8 = 0: "f16x3" frames [hi][lo] + wpack = TcPack::bytes; f8 = 1: frames [xh][xh8][xl8], wpack = TcPack::bytes8 and
+// tmap_in8 describing the two e4m3 planes (see make_act_tensor_maps_f8).
+cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out,
+                            int cin, int cout, int pw, int ph, float out_scale, int f8, int num_sms,
                             cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
-                            float *partial = nullptr);
+                            float *partial = nullptr, const CUtensorMap *tmap_in8 = nullptr);
 // Fused last layer: launch_tc_layer(..., last_w = [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
 // tcgen05 layer emit per-pixel tap partials instead of activations; launch_last_gather sums the 3x3
 // neighbourhood of partials, adds the bias, applies the leaky-ReLU and writes the cropped fp32 plane.
@@ -56,14 +58,15 @@ constexpr int PROF_MAX_CTAS = 256;
 // Last layer (Cout = 1): NHWC hi/lo frame -> fp32 plane, interior only: out(y,x) for
 // y in [crop, ph-crop), x in [crop, pw-crop) is written to dst[(y-crop)*stride + (x-crop)].
 cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt /*[C][9]*/, float bias,
-                        int crop, float *dst, long dst_stride_floats, cudaStream_t s);
+                        int crop, float *dst, long dst_stride_floats, cudaStream_t s, int f8 = 0);
 // planar fp32 [C][h][w] -> NHWC hi/lo frame (h+2) x (w+2), replicate ring of 1 (for w2x_filter_layer)
-cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s);
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8 = 0);
 // NHWC hi/lo frame (h+2) x (w+2) -> planar fp32 [C][h][w] (interior)
-cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s);
+cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s, int f8 = 0);
 
 // Host: build the 4-D TMA descriptor {C, Wp, Hp, 2} with box {kc, HALO, HALO, 1}.
 int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp);
+int make_act_tensor_maps_f8(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp);
 }  // namespace tc
 
 }  // namespace w2x

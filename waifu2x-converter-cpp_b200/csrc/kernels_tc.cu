@@ -15,17 +15,19 @@
 // grows by one pixel per layer and is cropped at the end -- the same argument that makes the
 // reference's per-layer BORDER_REPLICATE harmless.
 //
-// Per CTA (persistent, 1 per SM, 7 warps):
-//   warp 0  A producer   one TMA box {KC ch, 18, 18} per (tile-set, channel chunk, hi|lo): the
-//                        16x16 output region plus a 1-pixel ring, staged ONCE and addressed nine
-//                        times (the 3x3 taps are UMMA-descriptor start-address offsets into it)
-//   warp 1  MMA issuer   single thread, tcgen05.mma cta_group::1, M=128 (8 wide x 16 tall pixels),
-//                        N=Cout, K=16 per instruction; two M-tiles per weight pass
-//   warp 2  B producer   pre-swizzled weight tiles streamed with cp.async.bulk; owns TMEM alloc
-//   warps 3-6 epilogue   tcgen05.ld -> scale, +bias, leaky-ReLU -> re-split to fp16 hi/lo ->
-//                        vectorised NHWC stores; overlaps the next tile-set (TMEM double buffer)
+// Per CTA (persistent, 1 per SM, 12 warps):
+//   warp 0      A producer   one TMA box {KC ch, 18, 18} per (tile-set, channel chunk, hi|lo): the
+//                            16x16 output region plus a 1-pixel ring, staged ONCE and addressed nine
+//                            times (the 3x3 taps are UMMA-descriptor start-address offsets into it)
+//   warps 1, 7  MMA issuers  one per M-tile (8 wide x 16 tall pixels): tcgen05.mma cta_group::1, M=128,
+//                            N=Cout (N=2*Cout with [wh;wl] stacked when Cout<=64), K=16 per instruction
+//   warp 2      B producer   pre-swizzled 32-channel weight stages streamed with cp.async.bulk; owns TMEM
+//   warps 3-6, 8-11 epilogue one set per M-tile: tcgen05.ld -> scale, +bias, leaky-ReLU -> either re-split to
+//                            fp16 hi/lo + transposed, coalesced NHWC stores, or (FUSE) the last layer's nine
+//                            tap partials; overlaps the next tile-set (TMEM double buffer)
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -132,6 +134,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
                      : "memory");                                                                              \
     }
 W2X_UMMA_VARIANT(umma_f16, "tcgen05.mma.cta_group::1.kind::f16")
+W2X_UMMA_VARIANT(umma_f8, "tcgen05.mma.cta_group::1.kind::f8f6f4")   // e4m3 x e4m3 -> f32, K = 32 per instruction, twice the f16 rate
 // operand-collector hints (SASS: UTCHMMA gdesc.A_KEEP / .A_REUSE): keep the A operand in the tensor core's
 // collector for the next MMA that uses the same activation slice
 W2X_UMMA_VARIANT(umma_f16_a_fill, "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill")
@@ -206,7 +209,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 // Per-layer configuration
 // ================================================================================================
-template <int CIN, int COUT, bool FUSE = false>
+// F8 = false: three kind::f16 products xh*wh + xl*wh + xh*wl ("f16x3").
+// F8 = true : xh*wh in kind::f16, the two correction products in kind::f8f6f4 on e4m3 copies
+//             xl8*wh8 + xh8*wl8 (K = 32 per MMA at twice the rate: 2.0 instead of 3.0 pass-equivalents).
+//             Activation frames then hold [xh fp16][xh8][xl8] planes (same 4 bytes per element).
+constexpr int F8_A = 10, F8_C = 1;   // xl8 = e4m3((x16 - xh) * 2^F8_A), xh8 = e4m3(xh * 2^-F8_C); must match w2x_internal.h
+
+template <int CIN, int COUT, bool FUSE = false, bool F8 = false>
 struct Cfg {
     // ---- A operand (activations): one TMA box per (tile-set, 64-channel chunk, hi|lo) ----
     static constexpr int KC = CIN < 64 ? CIN : 64;      // channels per activation chunk
@@ -215,7 +224,12 @@ struct Cfg {
     static constexpr uint32_t A_LAYOUT = ROWB == 128 ? 2u : 4u;                // SWIZZLE_128B : SWIZZLE_64B
     static constexpr int A_PLANE = HALO * HALO * ROWB;                       // bytes one TMA box delivers
     static constexpr int A_PLANE_PAD = (A_PLANE + 1023) / 1024 * 1024;
-    static constexpr int A_SLOT = 2 * A_PLANE_PAD;                           // hi + lo
+    static constexpr int ROWB8 = KC;                                         // e4m3 planes: one byte per channel
+    static constexpr uint32_t A8_LAYOUT = ROWB8 == 64 ? 4u : 6u;               // SWIZZLE_64B : SWIZZLE_32B
+    static constexpr int A8_PLANE = HALO * HALO * ROWB8;
+    static constexpr int A8_PLANE_PAD = (A8_PLANE + 1023) / 1024 * 1024;
+    static constexpr int A_SLOT = F8 ? A_PLANE_PAD + 2 * A8_PLANE_PAD : 2 * A_PLANE_PAD;   // xh + (xh8, xl8)  |  hi + lo
+    static constexpr int A_TX = F8 ? A_PLANE + 2 * A8_PLANE : 2 * A_PLANE;   // bytes the TMA loads of one slot deliver
     static constexpr int A_SLOTS = 2;
     // ---- B operand (weights): stages of 32 input channels (two K=16 steps), SWIZZLE_64B rows of 64 B ----
     static constexpr int KB = 32;
@@ -224,9 +238,10 @@ struct Cfg {
     static constexpr uint32_t B_LAYOUT = 4u;
     // Cout <= 64: hi and lo weights form ONE stage of 2*Cout rows, so xh*[wh;wl] is a single N = 2*Cout MMA
     // (accumulators D1 | D2 side by side, summed in the epilogue) -- two MMAs per K step instead of three.
-    static constexpr bool STACK = COUT <= 64;
+    static constexpr bool STACK = COUT <= 64 && !F8;
     static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
     static constexpr int B_STAGE = STACK ? 2 * B_BLOCK : B_BLOCK;
+    // F8: per 32-channel block one stage of wh (fp16, Cout x 64 B) and one of [wh8 | wl8] (e4m3, Cout x 32 B each)
     static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * (STACK ? 1 : 2);
     // ---- accumulators ----
     static constexpr int TILE_COLS = STACK ? 2 * COUT : COUT;                // TMEM columns per M-tile
@@ -282,10 +297,10 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // ================================================================================================
 // The layer kernel
 // ================================================================================================
-template <int CIN, int COUT, bool FUSE>
+template <int CIN, int COUT, bool FUSE, bool F8>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p) {
-    using C = Cfg<CIN, COUT, FUSE>;
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8, const TcParams p) {
+    using C = Cfg<CIN, COUT, FUSE, F8>;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: swizzle patterns repeat every 1024 B (SWIZZLE_128B) / 512 B (SWIZZLE_64B)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -327,7 +342,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 0 && lane == 0) prefetch_tmap(&tmap_in);
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_in);
+        if constexpr (F8) prefetch_tmap(&tmap_in8);
+    }
     if (warp == 2) {
         tmem_alloc(tmem_slot, C::TMEM_COLS);
         tmem_relinquish();
@@ -348,10 +366,15 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
                     const uint32_t slot = it & 1u, round = it >> 1;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
-                    mbar_arrive_expect_tx(a_full(slot), 2u * C::A_PLANE);
+                    mbar_arrive_expect_tx(a_full(slot), (uint32_t)C::A_TX);
                     const uint32_t dst = a_base + slot * C::A_SLOT;
                     tma_load_4d(dst, &tmap_in, a_full(slot), c * C::KC, x0, y0, 0);
-                    tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in, a_full(slot), c * C::KC, x0, y0, 1);
+                    if constexpr (F8) {
+                        tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in8, a_full(slot), c * C::KC, x0, y0, 0);                     // xh8
+                        tma_load_4d(dst + C::A_PLANE_PAD + C::A8_PLANE_PAD, &tmap_in8, a_full(slot), c * C::KC, x0, y0, 1);   // xl8
+                    } else {
+                        tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in, a_full(slot), c * C::KC, x0, y0, 1);
+                    }
                 }
             }
             if (prof_on) prof[PROF_APROD_WAIT] += w_a;
@@ -384,6 +407,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
         constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::A_LAYOUT) >> 32);
         constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::B_LAYOUT) >> 32);
         constexpr uint32_t LO_FIXED = 1u << 16;                      // LBO field = 1
+        // e4m3 operands (F8): activation planes with ROWB8-byte rows, weight blocks with 32-byte rows (SWIZZLE_32B)
+        constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(HALO * C::ROWB8, C::A8_LAYOUT) >> 32);
+        constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
         auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
         uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
         uint32_t b_ready = 0;                         // result of the early probe of b_full(stage)
@@ -414,7 +440,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                 // descriptor low words (address >> 4) of this issuer's window into the hi / lo activation planes
                 const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
                 const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
+                // F8: windows into the xh8 / xl8 planes of this slot
+                const uint32_t a8h0 = ((((a_base + slot * C::A_SLOT + C::A_PLANE_PAD) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB8 >> 4);
+                const uint32_t a8l0 = a8h0 + (C::A8_PLANE_PAD >> 4);
                 uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
+                uint32_t tap_off8 = 0;                // ((ky*HALO + kx) * ROWB8) >> 4
                 for (int t = 0; t < 9; t++) {
                     const uint32_t first = (c | t) != 0 ? 1u : 0u;
 #pragma unroll
@@ -422,7 +452,18 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                         const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;   // 32 channels = 64 B = 4 units
                         const uint32_t acc0 = kb ? 1u : first;
                         uint32_t b0;
-                        if constexpr (C::STACK) {
+                        if constexpr (F8) {
+                            // ---- stage 1: wh (fp16): the main product xh*wh, two K=16 steps ----
+                            acquire_b(b0);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            release_b();
+                            // ---- stage 2: [wh8 | wl8] (e4m3): corrections xl8*wh8 and xh8*wl8, one K=32 step each ----
+                            acquire_b(b0);
+                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u, leader);
+                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 32u >> 4)), idesc_c, 1u, leader);
+                            release_b();
+                        } else if constexpr (C::STACK) {
                             // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
                             acquire_b(b0);
                             umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_2c, acc0, leader);
@@ -447,6 +488,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                     }
                     // next tap: kx+1, or the next halo row
                     tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
+                    tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
                 }
                 umma_commit_if(a_empty(slot), leader);   // the staged boxes may be overwritten once these MMAs retire
             }
@@ -505,7 +547,46 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
                     const float v = fmaf(act[i], p.out_scale, s_bias[cb * 32 + i]);
                     act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
                 }
-                if constexpr (!FUSE) {
+                if constexpr (!FUSE && F8) {
+                    // planes: xh = fp16(x16) | xh8 = e4m3(xh * 2^-F8_C) | xl8 = e4m3((x16 - xh) * 2^F8_A)
+                    uint32_t hi[16], b8[16];       // b8[0..7] = xh8 (32 bytes), b8[8..15] = xl8 (32 bytes)
+                    constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+                        __half2 h = __floats2half2_rn(v0, v1);
+                        float2 hf = __half22float2(h);
+                        hi[i] = *reinterpret_cast<uint32_t *>(&h);
+                        const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+                        const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                        if (i & 1) { b8[i >> 1] |= h8 << 16; b8[8 + (i >> 1)] |= l8 << 16; }
+                        else { b8[i >> 1] = h8; b8[8 + (i >> 1)] = l8; }
+                    }
+                    const size_t pix_elems = (size_t)p.Hp * p.Wp * COUT;
+                    uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
+#pragma unroll
+                    for (int grp = 0; grp < 2; grp++) {       // grp 0: the fp16 plane (64 B per pixel), grp 1: both e4m3 planes (32 + 32 B)
+                        const uint32_t *src = grp ? b8 : hi;
+#pragma unroll
+                        for (int v = 0; v < 4; v++)
+                            sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+                            const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+                            const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+                            if (gy < p.Hp && gx < p.Wp) {
+                                const size_t pix = (size_t)gy * p.Wp + gx;
+                                uint8_t *dst = grp == 0 ? base + (pix * COUT + cb * 32) * 2 + ch * 16
+                                                        : base + (size_t)(2 + (ch >> 1)) * pix_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
+                                *reinterpret_cast<uint4 *>(dst) = val;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                } else if constexpr (!FUSE) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
@@ -583,7 +664,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const TcParams p)
 // ================================================================================================
 // First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
 // writes the NHWC hi/lo frame the tcgen05 layers consume.  One thread per pixel.
-template <int COUT>
+template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
 first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const float *__restrict__ wgt,
                    const float *__restrict__ bias, __half *__restrict__ out) {
@@ -622,18 +703,33 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             }
             __half2 h = __floats2half2_rn(a[0], a[1]);
             float2 hf = __half22float2(h);
-            __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
             hi[i] = *reinterpret_cast<uint32_t *>(&h);
-            lo[i] = *reinterpret_cast<uint32_t *>(&l);
+            if constexpr (F8) {
+                constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+                const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
+                else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+            } else {
+                __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
+                lo[i] = *reinterpret_cast<uint32_t *>(&l);
+            }
         }
         reinterpret_cast<uint4 *>(dst_hi)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        reinterpret_cast<uint4 *>(dst_lo)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if constexpr (F8) {
+            uint8_t *b = reinterpret_cast<uint8_t *>(out);
+            const size_t pix = (size_t)y * pw + x;
+            *reinterpret_cast<uint2 *>(b + 2 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[0], lo[1]);
+            *reinterpret_cast<uint2 *>(b + 3 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[2], lo[3]);
+        } else {
+            reinterpret_cast<uint4 *>(dst_lo)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
 // Last layer: nOutputPlanes = 1.  fp32 arithmetic in the reference's association: per input plane a
 // 9-tap sum, planes added in ascending order, then bias and leaky-ReLU.  One thread per pixel.
-template <int CIN>
+template <int CIN, bool F8>
 __global__ void __launch_bounds__(256)
 last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__restrict__ wgt, float bias, int crop,
                   float *__restrict__ dst, long dst_stride) {
@@ -654,14 +750,25 @@ last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__
 #pragma unroll
             for (int kx = 0; kx < 3; kx++) {
                 // frame reads outside [0,pw)x[0,ph) cannot happen: crop >= 1 keeps the 3x3 window inside
-                const __half *ph_ = in + ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * CIN + c8 * 8;
+                const size_t pixo = ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * CIN + c8 * 8;
+                const __half *ph_ = in + pixo;
                 uint4 uh = __ldg(reinterpret_cast<const uint4 *>(ph_));
-                uint4 ul = __ldg(reinterpret_cast<const uint4 *>(ph_ + plane_elems));
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&uh);
+                uint4 ul = make_uint4(0, 0, 0, 0);
+                uint2 ul8 = make_uint2(0, 0);
+                if constexpr (F8) ul8 = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + 3 * plane_elems + pixo));
+                else ul = __ldg(reinterpret_cast<const uint4 *>(ph_ + plane_elems));
                 const __half2 *l2 = reinterpret_cast<const __half2 *>(&ul);
+                const __nv_fp8x2_storage_t *l8 = reinterpret_cast<const __nv_fp8x2_storage_t *>(&ul8);
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    float2 hf = __half22float2(h2[i]), lf = __half22float2(l2[i]);
+                    float2 hf = __half22float2(h2[i]), lf;
+                    if constexpr (F8) {
+                        __half2_raw r = __nv_cvt_fp8x2_to_halfraw2(l8[i], __NV_E4M3);
+                        lf = __half22float2(*reinterpret_cast<__half2 *>(&r));
+                        lf.x *= 1.0f / (float)(1 << F8_A);
+                        lf.y *= 1.0f / (float)(1 << F8_A);
+                    } else lf = __half22float2(l2[i]);
                     float a0 = (hf.x + lf.x) * inv, a1 = (hf.y + lf.y) * inv;
                     const int tap = ky * 3 + kx;
                     t[2 * i] = fmaf(s_w[(c8 * 8 + 2 * i) * 9 + tap], a0, t[2 * i]);
@@ -692,7 +799,7 @@ last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias
     dst[(long)(y - crop_top) * dst_stride + (x - crop_x)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
 }
 
-__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out) {
+__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8) {
     const int pw = w + 2, ph = h + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)pw * ph * C;
@@ -703,12 +810,18 @@ __global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w
     int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1);
     float a = in[((long)c * h + sy) * w + sx] * ACT_SCALE;
     __half hh = __float2half_rn(a);
-    __half ll = __float2half_rn(a - __half2float(hh));
     out[idx] = hh;
-    out[idx + total] = ll;
+    if (f8) {
+        uint8_t *b = reinterpret_cast<uint8_t *>(out);
+        const float hf = __half2float(hh);
+        b[2 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
+        b[3 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
+    } else {
+        out[idx + total] = __float2half_rn(a - __half2float(hh));
+    }
 }
 
-__global__ void nhwc_to_planar_kernel(const __half *__restrict__ in, int C, int w, int h, float *__restrict__ out) {
+__global__ void nhwc_to_planar_kernel(const __half *__restrict__ in, int C, int w, int h, float *__restrict__ out, int f8) {
     const int pw = w + 2, ph = h + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)w * h * C;
@@ -718,7 +831,12 @@ __global__ void nhwc_to_planar_kernel(const __half *__restrict__ in, int C, int 
     int y = (int)(r % h), c = (int)(r / h);
     long src = ((long)(y + 1) * pw + (x + 1)) * C + c;
     long plane = (long)pw * ph * C;
-    out[idx] = (__half2float(in[src]) + __half2float(in[src + plane])) * (1.0f / ACT_SCALE);
+    float lo;
+    if (f8) {
+        __half_raw r = __nv_cvt_fp8_to_halfraw(reinterpret_cast<const uint8_t *>(in)[3 * plane + src], __NV_E4M3);
+        lo = __half2float(*reinterpret_cast<__half *>(&r)) * (1.0f / (float)(1 << F8_A));
+    } else lo = __half2float(in[src + plane]);
+    out[idx] = (__half2float(in[src]) + lo) * (1.0f / ACT_SCALE);
 }
 
 // ================================================================================================
@@ -729,13 +847,18 @@ bool layer_supported(int cin, int cout) {
     return ok(cin) && ok(cout);
 }
 
+template <int CIN, int COUT, bool FUSE, bool F8>
+static cudaError_t set_attr1() {
+    return cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT, FUSE, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES);
+}
 template <int CIN, int COUT>
 static cudaError_t set_attr() {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg<CIN, COUT, false>::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc_conv3x3_kernel<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<CIN, COUT, true>::SMEM_BYTES);
+    cudaError_t e;
+    if ((e = set_attr1<CIN, COUT, false, false>()) != cudaSuccess) return e;
+    if ((e = set_attr1<CIN, COUT, true, false>()) != cudaSuccess) return e;
+    if ((e = set_attr1<CIN, COUT, false, true>()) != cudaSuccess) return e;
+    return set_attr1<CIN, COUT, true, true>();
 }
 
 #define W2X_TC_SHAPES(X) \
@@ -743,7 +866,7 @@ static cudaError_t set_attr() {
 
 size_t layer_smem_bytes(int cin, int cout) {
 #define X(ci, co) \
-    if (cin == ci && cout == co) return Cfg<ci, co, true>::SMEM_BYTES;
+    if (cin == ci && cout == co) return Cfg<ci, co, true, false>::SMEM_BYTES;
     W2X_TC_SHAPES(X)
 #undef X
     return 0;
@@ -758,21 +881,24 @@ cudaError_t init_kernels() {
     return cudaSuccess;
 }
 
-template <int CIN, int COUT>
-static cudaError_t launch_one(const CUtensorMap *tmap, const TcParams &p, int num_sms, cudaStream_t s) {
-    int grid = p.n_tilesets < num_sms ? p.n_tilesets : num_sms;
-    if (p.partial)
-        tc_conv3x3_kernel<CIN, COUT, true><<<grid, NUM_THREADS, Cfg<CIN, COUT, true>::SMEM_BYTES, s>>>(*tmap, p);
-    else
-        tc_conv3x3_kernel<CIN, COUT, false><<<grid, NUM_THREADS, Cfg<CIN, COUT, false>::SMEM_BYTES, s>>>(*tmap, p);
+template <int CIN, int COUT, bool FUSE, bool F8>
+static cudaError_t launch_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int grid, cudaStream_t s) {
+    tc_conv3x3_kernel<CIN, COUT, FUSE, F8><<<grid, NUM_THREADS, Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, const float *bias, __half *out, int cin,
-                            int cout, int pw, int ph, float out_scale, int desc_mode, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial) {
+template <int CIN, int COUT>
+static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+    int grid = p.n_tilesets < num_sms ? p.n_tilesets : num_sms;
+    if (f8) return p.partial ? launch_k<CIN, COUT, true, true>(tmap, tmap8, p, grid, s) : launch_k<CIN, COUT, false, true>(tmap, tmap8, p, grid, s);
+    return p.partial ? launch_k<CIN, COUT, true, false>(tmap, tmap8, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, tmap8, p, grid, s);
+}
+
+cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out, int cin,
+                            int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
+                            unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8) {
     TcParams p;
-    p.wpack = wpack;
+    p.wpack = reinterpret_cast<const uint16_t *>(wpack);
     p.bias = bias;
     p.out = out;
     p.Wp = pw;
@@ -780,42 +906,52 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const uint16_t *wpack, c
     p.tiles_x = (pw + REGION - 1) / REGION;
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale;
-    p.mma_mode = desc_mode;
+    p.mma_mode = 0;
     p.prof = prof;
     p.last_w = last_w;
     p.partial = partial;
+    if (f8 && !tmap_in8) return cudaErrorInvalidValue;
+    const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
 #define X(ci, co) \
-    if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, p, num_sms, s);
+    if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, t8, p, num_sms, f8 != 0, s);
     W2X_TC_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s) {
+                         int cout, __half *out, cudaStream_t s, int f8) {
     dim3 grid((pw + 31) / 32, (ph + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+#define W2X_FIRST(C)                                                                                         \
+    case C:                                                                                                  \
+        if (f8) first_layer_kernel<C, true><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out);  \
+        else first_layer_kernel<C, false><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out);    \
+        break;
     switch (cout) {
-        case 32: first_layer_kernel<32><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out); break;
-        case 64: first_layer_kernel<64><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out); break;
-        case 128: first_layer_kernel<128><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out); break;
+        W2X_FIRST(32) W2X_FIRST(64) W2X_FIRST(128)
         default: return cudaErrorInvalidValue;
     }
+#undef W2X_FIRST
     return cudaGetLastError();
 }
 
 cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt, float bias, int crop, float *dst,
-                        long dst_stride_floats, cudaStream_t s) {
+                        long dst_stride_floats, cudaStream_t s, int f8) {
     const int ow = pw - 2 * crop, oh = ph - 2 * crop;
     if (ow < 1 || oh < 1 || crop < 1) return cudaErrorInvalidValue;
     dim3 grid((ow + 31) / 32, (oh + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+#define W2X_LAST(C)                                                                                              \
+    case C:                                                                                                          \
+        if (f8) last_layer_kernel<C, true><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats);    \
+        else last_layer_kernel<C, false><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats);      \
+        break;
     switch (cin) {
-        case 32: last_layer_kernel<32><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats); break;
-        case 64: last_layer_kernel<64><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats); break;
-        case 128: last_layer_kernel<128><<<grid, 256, 0, s>>>(in, pw, ph, wgt, bias, crop, dst, dst_stride_floats); break;
+        W2X_LAST(32) W2X_LAST(64) W2X_LAST(128)
         default: return cudaErrorInvalidValue;
     }
+#undef W2X_LAST
     return cudaGetLastError();
 }
 
@@ -834,15 +970,15 @@ cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bi
     return cudaGetLastError();
 }
 
-cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s) {
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8) {
     long total = (long)(w + 2) * (h + 2) * C;
-    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out);
+    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8);
     return cudaGetLastError();
 }
 
-cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s) {
+cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s, int f8) {
     long total = (long)w * h * C;
-    nhwc_to_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out);
+    nhwc_to_planar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8);
     return cudaGetLastError();
 }
 
@@ -875,6 +1011,34 @@ int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int H
                      CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// F8 frames: [xh fp16 [Hp][Wp][C]] [xh8 [Hp][Wp][C]] [xl8 [Hp][Wp][C]]  (bytes 2 + 1 + 1 per element)
+int make_act_tensor_maps_f8(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -1;
+    const int kc = C < 64 ? C : 64;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 1};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
+        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return (int)r;
+    }
+    {
+        const char *b8 = reinterpret_cast<const char *>(base) + (size_t)2 * Hp * Wp * C;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
+        cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
+        cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
+        CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(b8), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return (int)r;
+    }
+    return 0;
 }
 
 }  // namespace tc

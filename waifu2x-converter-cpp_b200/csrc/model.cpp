@@ -80,6 +80,27 @@ float f16_to_f32(uint16_t h) {
     return f;
 }
 
+uint8_t f32_to_e4m3_rn(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint8_t sign = (uint8_t)((x >> 24) & 0x80u);
+    float a = std::fabs(f);
+    if (!(a == a)) return (uint8_t)(sign | 0x7f);       // NaN
+    if (a >= 448.0f) return (uint8_t)(sign | 0x7e);     // satfinite
+    if (a < 0.015625f) {                                // below the smallest normal 2^-6: subnormals, unit 2^-9
+        int q = (int)std::nearbyint((double)a * 512.0); // FE_TONEAREST: ties to even; q == 8 encodes the first normal
+        return (uint8_t)(sign | (uint8_t)q);
+    }
+    int e;
+    float m = std::frexp(a, &e);                        // a = m * 2^e, m in [0.5, 1)
+    e -= 1;                                             // a = (2m) * 2^e, 2m in [1, 2)
+    int q = (int)std::nearbyint(((double)m * 2.0 - 1.0) * 8.0);
+    if (q == 8) { q = 0; e += 1; }
+    int enc = ((e + 7) << 3) | q;
+    if (enc > 0x7e) enc = 0x7e;
+    return (uint8_t)(sign | (uint8_t)enc);
+}
+
 // ---- a small JSON reader ----------------------------------------------------------------------
 namespace {
 
@@ -337,6 +358,33 @@ static void pack_tc_layer(const Layer &L, TcPack &P) {
             }
 }
 
+// The "f8" operand image of the same layer (see TcPack::bytes8).
+static inline size_t swizzle32(size_t logical) { return logical ^ (((logical >> 7) & 1) << 4); }
+
+static void pack_tc_layer_f8(const Layer &L, TcPack &P) {
+    const int kc_a = L.n_in < 64 ? L.n_in : 64;
+    const size_t blk16 = (size_t)L.n_out * 64, blk8 = (size_t)L.n_out * 32, stage = blk16 + 2 * blk8;
+    P.bytes8.assign((size_t)P.n_chunk * 9 * P.kblocks * stage, 0);
+    const float up = std::ldexp(1.0f, F8_C), down = std::ldexp(1.0f, -F8_A);
+    for (int c = 0; c < P.n_chunk; c++)
+        for (int t = 0; t < 9; t++)
+            for (int kb = 0; kb < P.kblocks; kb++) {
+                uint8_t *base = P.bytes8.data() + (((size_t)c * 9 + t) * P.kblocks + kb) * stage;
+                uint16_t *wh16 = reinterpret_cast<uint16_t *>(base);
+                uint8_t *wh8 = base + blk16, *wl8 = wh8 + blk8;
+                for (int n = 0; n < L.n_out; n++)
+                    for (int k = 0; k < 32; k++) {
+                        int ci = c * kc_a + kb * 32 + k;
+                        float w = L.w[((size_t)n * L.n_in + ci) * 9 + t] * P.wscale;
+                        uint16_t h = f32_to_f16_rn(w);
+                        float hf = f16_to_f32(h);
+                        wh16[swizzled_offset((size_t)n * 64 + 2 * (size_t)k, 64) / 2] = h;
+                        wh8[swizzle32((size_t)n * 32 + (size_t)k)] = f32_to_e4m3_rn(hf * down);
+                        wl8[swizzle32((size_t)n * 32 + (size_t)k)] = f32_to_e4m3_rn((w - hf) * up);
+                    }
+            }
+}
+
 int finalize_model(w2x_model *m) {
     if (m->layers.empty()) return fail(W2X_ERR_MODEL, "Error : model has no layers");
     for (size_t i = 0; i < m->layers.size(); i++) {
@@ -357,7 +405,10 @@ int finalize_model(w2x_model *m) {
     m->tc.assign(n, TcPack());
     for (size_t i = 0; i < n; i++) {
         const Layer &L = m->layers[i];
-        if (okc(L.n_in) && okc(L.n_out)) pack_tc_layer(L, m->tc[i]);
+        if (okc(L.n_in) && okc(L.n_out)) {
+            pack_tc_layer(L, m->tc[i]);
+            pack_tc_layer_f8(L, m->tc[i]);
+        }
     }
     m->uid = g_uid.fetch_add(1);
     return W2X_OK;
@@ -441,6 +492,14 @@ W2X_API int w2x_debug_tc_pack(const w2x_model *model, int layer, const uint16_t 
     if (n_chunk) *n_chunk = P.n_chunk;
     if (wscale) *wscale = P.wscale;
     if (kblocks) *kblocks = P.kblocks;
+    return W2X_OK;
+}
+
+W2X_API int w2x_debug_tc_pack8(const w2x_model *model, int layer, const uint8_t **data, size_t *n_bytes) {
+    if (!model || layer < 0 || layer >= (int)model->tc.size())
+        return w2x::fail(W2X_ERR_ARG, "w2x_debug_tc_pack8: bad model or layer index");
+    if (data) *data = model->tc[(size_t)layer].bytes8.data();
+    if (n_bytes) *n_bytes = model->tc[(size_t)layer].bytes8.size();
     return W2X_OK;
 }
 

@@ -30,7 +30,15 @@ struct TcPack {
     int kc = 0, n_chunk = 0, kblocks = 0, row_bytes = 0;
     float wscale = 1.0f;          // power of two
     std::vector<uint16_t> bytes;  // fp16 bit patterns
+    // "f8" flavour (fp16 main product + two e4m3 correction products): per (chunk, tap, 32-channel block)
+    //   [wh fp16: n_out rows x 64 B, SWIZZLE_64B][wh8 = e4m3(wh * 2^-F8_A): n_out rows x 32 B, SWIZZLE_32B]
+    //   [wl8 = e4m3((w*wscale - wh) * 2^F8_C): n_out rows x 32 B, SWIZZLE_32B]
+    std::vector<uint8_t> bytes8;
 };
+// Scale exponents of the e4m3 correction operands: activations store xl8 = e4m3((x16 - xh) * 2^F8_A) and
+// xh8 = e4m3(xh * 2^-F8_C); the weight side carries the inverse so both correction products land on the
+// main product's scale (x16 * w * wscale).  Chosen by CPU emulation (tests/test_numerics_model.py).
+constexpr int F8_A = 10, F8_C = 1;
 
 }  // namespace w2x
 
@@ -47,6 +55,7 @@ int parse_model_json(const char *path, w2x_model **out);
 int finalize_model(w2x_model *m);   // validation + tcgen05 packing
 uint16_t f32_to_f16_rn(float f);    // round-to-nearest-even, subnormals kept
 float f16_to_f32(uint16_t h);
+uint8_t f32_to_e4m3_rn(float f);    // OCP e4m3 (max 448, no inf), round-to-nearest-even, saturating (cvt.rn.satfinite.e4m3x2.f32)
 
 // geometry.cpp
 struct Config { int n_job = 4, block_w = 512, block_h = 512; };
