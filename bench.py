@@ -171,6 +171,8 @@ def run_ours(args):
     model = w2x.Model.from_arrays(om.weights, om.biases)
     engine = {"auto": w2x.ENGINE_AUTO, "tc": w2x.ENGINE_TC, "fp32": w2x.ENGINE_FP32}[args.engine]
     ctx = w2x.Context(local, engine=engine)
+    ctx.set_precision(w2x.PRECISION_F16_F8X2 if args.precision == "f8" else w2x.PRECISION_F16X3)
+    passes = 2.0 if args.precision == "f8" else 3.0
     stream = torch.cuda.Stream()            # a real (non-default) stream: handle 0 would mean "the context's own stream"
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
@@ -297,10 +299,11 @@ def run_ours(args):
             roof = {"kernel": f"{name_k} (layer L{k}, {LAYER_MACS[k] // 9} MAC/tap/px)", "bound": "tensor" if tensor else "fp32-cuda-core",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if peak else None,
                     "peak_source": f"{peaks['source']}: cuBLAS bf16 sustained (kernel timed inside a long step); fp16 and bf16 share the rate",
-                    "mma_passes": MMA_PASSES if tensor else None,
-                    "frac_of_attainable": (ach * MMA_PASSES / peak) if peak else None,
-                    "note": "achieved = ALGORITHMIC flops (one multiply-add per weight per output pixel); the fp32-faithful 2-term fp16 split "
-                            "issues 3 MMA passes, so the attainable ceiling is peak/3",
+                    "mma_passes": passes if tensor else None,
+                    "frac_of_attainable": (ach * passes / peak) if peak else None,
+                    "note": "achieved = ALGORITHMIC flops (one multiply-add per weight per output pixel); the fp32-faithful operand split issues "
+                            "3 fp16 MMA passes (f16x3) or 1 fp16 + 2 double-rate e4m3 passes (f8: 2.0 pass-equivalents), so the attainable "
+                            "ceiling is peak/passes",
                     "launch_ms": ms_k / n_k, "launches": n_k, "traffic": traffic,
                     "all_layers_ms": [round(l[0] / max(l[1], 1), 4) for l in layers],
                     "whole_pass_algorithmic_tflops": FLOP_PER_PIXEL * pix_total / (ms_step * 1e-3) / 1e12 / world}
@@ -312,7 +315,8 @@ def run_ours(args):
                    "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} (reference default -j 4)"}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.engine != "fp32" else "f32",
+                "dtype": ("f32" if args.engine == "fp32" else "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.precision == "f16x3"
+                          else "f16 + 2x e4m3 correction products, f32 accumulate (fp32-faithful to ~3e-5)"),
                 "data": "synthetic",
                 "config": {"workload": f"{W}x{H} fp32 Y plane per GPU, scale2.0x_model.json weights (7x conv3x3 + bias + leaky-ReLU 0.1), "
                                        f"block_splitting=on; plane {W}x{H * world} in {world} row band(s)",
@@ -337,6 +341,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f8"],
+                    help="tcgen05 arithmetic: three fp16 products (default) or fp16 + two e4m3 correction products")
     ap.add_argument("--check", action="store_true", help="multi-GPU: verify the per-layer result against the one-shot band mode, bit for bit")
     ap.add_argument("--halo", default="per-layer", choices=["input", "per-layer"],
                     help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")

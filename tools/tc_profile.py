@@ -20,14 +20,14 @@ om = oracle.OracleModel.golden("scale2.0x")
 m = w2x.Model.from_arrays(om.weights, om.biases)
 ctx = w2x.Context(0, engine=w2x.ENGINE_TC)
 x = oracle.seeded_plane(size, size, 1, "uniform")
-mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-ctx.debug_set_mma_mode(mode)
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0 = f16x3, 1 = f16 + 2 x e4m3 corrections
+ctx.set_precision(mode)
 ctx.convert_plane(m, x)
 ctx.convert_plane(m, x)
 ctx.set_timing(True)
 ctx.convert_plane(m, x)
 clean = ctx.layer_times()
-print(f"size {size}x{size} mma_mode {mode}; per-layer ms without counters:", [round(t[0], 3) for t in clean], "sum", round(sum(t[0] for t in clean), 3))
+print(f"size {size}x{size} precision {mode}; per-layer ms without counters:", [round(t[0], 3) for t in clean], "sum", round(sum(t[0] for t in clean), 3))
 ctx.debug_tc_profile_enable(True)
 ctx.convert_plane(m, x)
 times = ctx.layer_times()
