@@ -240,9 +240,11 @@ struct Cfg {
     // (accumulators D1 | D2 side by side, summed in the epilogue) -- two MMAs per K step instead of three.
     static constexpr bool STACK = COUT <= 64 && !F8;
     static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
-    static constexpr int B_STAGE = STACK ? 2 * B_BLOCK : B_BLOCK;
-    // F8: per 32-channel block one stage of wh (fp16, Cout x 64 B) and one of [wh8 | wl8] (e4m3, Cout x 32 B each)
-    static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * (STACK ? 1 : 2);
+    // F8: per 32-channel block one stage of wh (fp16, Cout x 64 B) and one of [wh8 | wl8] (e4m3, Cout x 32 B each);
+    // for Cout <= 64 the two are merged into one stage (fewer barrier round trips on layers that are not tensor-bound).
+    static constexpr bool MERGE = F8 && COUT <= 64;
+    static constexpr int B_STAGE = (STACK || MERGE) ? 2 * B_BLOCK : B_BLOCK;
+    static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * ((STACK || MERGE) ? 1 : 2);
     // ---- accumulators ----
     static constexpr int TILE_COLS = STACK ? 2 * COUT : COUT;                // TMEM columns per M-tile
     static constexpr int ACC_COLS = 4 * TILE_COLS;                           // 2 sets x 2 M-tiles
@@ -452,7 +454,15 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                         const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;   // 32 channels = 64 B = 4 units
                         const uint32_t acc0 = kb ? 1u : first;
                         uint32_t b0;
-                        if constexpr (F8) {
+                        if constexpr (C::MERGE) {
+                            // one stage = [wh fp16 | wh8 | wl8]: main product (two K=16 steps) + both e4m3 corrections (K=32 each)
+                            acquire_b(b0);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u, leader);
+                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u, leader);
+                            release_b();
+                        } else if constexpr (F8) {
                             // ---- stage 1: wh (fp16): the main product xh*wh, two K=16 steps ----
                             acquire_b(b0);
                             umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
