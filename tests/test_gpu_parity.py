@@ -163,6 +163,30 @@ def test_host_copy_pipeline_bands_are_bit_identical(ctxs, models, oracle_mod, en
         ctx.debug_set_host_bands(0)
 
 
+@pytest.mark.parametrize("engine", ["tc", "tc8"])
+def test_cta_pair_kernels_are_bit_identical_to_single_cta(ctxs, models, oracle_mod, engine):
+    """cta_group::2 (M = 256 across two SMs, weight rows split between the CTAs) issues the same K sequence per pixel,
+    so it must reproduce the single-CTA kernels bit for bit -- including an odd tile-set count (phantom region)."""
+    ctx = ctxs[engine]
+    for (w, h, seed) in ((200, 120, 3), (90, 75, 4), (16, 16, 5), (333, 41, 6)):
+        x = oracle_mod.seeded_plane(w, h, seed, "uniform")
+        single = ctx.convert_plane(models["scale2.0x"], x)
+        try:
+            ctx.debug_set_pair(True)
+            paired = ctx.convert_plane(models["scale2.0x"], x)
+            ctx.debug_set_fuse_last(False)
+            paired_sep = ctx.convert_plane(models["scale2.0x"], x)
+        finally:
+            ctx.debug_set_pair(False)
+            ctx.debug_set_fuse_last(True)
+        assert np.array_equal(single, paired), (w, h)
+        ctx.debug_set_fuse_last(False)
+        try:
+            assert np.array_equal(ctx.convert_plane(models["scale2.0x"], x), paired_sep), (w, h)
+        finally:
+            ctx.debug_set_fuse_last(True)
+
+
 def test_engines_agree_with_each_other(ctxs, models, oracle_mod):
     x = oracle_mod.seeded_plane(300, 200, 31, "smooth")
     a = ctxs["fp32"].convert_plane(models["noise2"], x)

@@ -110,6 +110,7 @@ def lib():
     L.w2x_band_finish.argtypes = [vp, vp, cs]
     L.w2x_debug_set_mma_mode.argtypes = [vp, ci]
     L.w2x_debug_set_host_bands.argtypes = [vp, ci]
+    L.w2x_debug_set_pair.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
     L.w2x_debug_tc_pack8.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(cs)]
     L.w2x_debug_tc_profile_enable.argtypes = [vp, ci]
@@ -249,6 +250,7 @@ class Context:
     def set_timing(self, on): _check(lib().w2x_ctx_set_timing(self._h, int(on)))
     def debug_set_mma_mode(self, mode): _check(lib().w2x_debug_set_mma_mode(self._h, mode))
 
+    def debug_set_pair(self, on): _check(lib().w2x_debug_set_pair(self._h, int(on)))
     def debug_set_host_bands(self, n): _check(lib().w2x_debug_set_host_bands(self._h, n))
     def debug_set_fuse_last(self, on): _check(lib().w2x_debug_set_fuse_last(self._h, int(on)))
     def debug_tc_profile_enable(self, on=True): _check(lib().w2x_debug_tc_profile_enable(self._h, int(on)))

@@ -50,6 +50,7 @@ struct w2x_ctx {
     int desc_mode = 0;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
     int precision = W2X_PRECISION_F16X3;
+    int pair = 0;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     size_t scratch_limit = (size_t)16 << 30;
@@ -283,7 +284,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
                                          ctx->num_sms, ctx->stream,
                                          ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
                                          fused_here ? dm->last_w_t : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
-                                         f8 ? &map8 : nullptr));
+                                         f8 ? &map8 : nullptr, ctx->pair));
         }
         note_kernel(ctx, li, f8 ? (fused_here ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
         ctx->launches++;
@@ -717,6 +718,13 @@ W2X_API int w2x_debug_tc_profile_read(w2x_ctx *ctx, int layer, unsigned long lon
         for (int w = 0; w < tc::PROF_WORDS; w++) out[w] += h[(size_t)c * tc::PROF_WORDS + w];
     }
     if (n_ctas) *n_ctas = n;
+    return W2X_OK;
+}
+
+// Probe switch (not part of the stable ABI): 1 = CTA-pair (cta_group::2) kernels for the 128-wide layers.
+W2X_API int w2x_debug_set_pair(w2x_ctx *ctx, int on) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->pair = on != 0;
     return W2X_OK;
 }
 

@@ -296,6 +296,90 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
     }
 }
 
+// Epilogue store of 32 activated output channels of ONE pixel per thread (lane = pixel inside this warp's 4x8 pixel
+// block of M-tile j): conversion to the frame's planes and transposed, coalesced stores through the warp's 2 KB
+// staging tile `stg` (XOR-swizzled 16-byte units, conflict-free both ways): every store instruction then writes
+// 8 pixels x 64 B instead of 32 lanes x 16 B at a Cout*2-byte stride.
+template <int COUT, bool F8>
+__device__ __forceinline__ void epilogue_store32(const float (&act)[32], const TcParams &p, uint32_t stg, int lane, int q, int j,
+                                                 int tx, int ty, int cb) {
+    const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
+    if constexpr (F8) {
+        // planes: xh = fp16(x16) | xh8 = e4m3(xh * 2^-F8_C) | xl8 = e4m3((x16 - xh) * 2^F8_A)
+        uint32_t hi[16], b8[16];       // b8[0..7] = xh8 (32 bytes), b8[8..15] = xl8 (32 bytes)
+        constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+            __half2 h = __floats2half2_rn(v0, v1);
+            float2 hf = __half22float2(h);
+            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+            const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+            if (i & 1) { b8[i >> 1] |= h8 << 16; b8[8 + (i >> 1)] |= l8 << 16; }
+            else { b8[i >> 1] = h8; b8[8 + (i >> 1)] = l8; }
+        }
+        const size_t pix_elems = (size_t)p.Hp * p.Wp * COUT;
+        uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
+#pragma unroll
+        for (int grp = 0; grp < 2; grp++) {       // grp 0: the fp16 plane (64 B per pixel), grp 1: both e4m3 planes (32 + 32 B)
+            const uint32_t *src = grp ? b8 : hi;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+                if (gy < p.Hp && gx < p.Wp) {
+                    const size_t pix = (size_t)gy * p.Wp + gx;
+                    uint8_t *dst = grp == 0 ? base + (pix * COUT + cb * 32) * 2 + ch * 16
+                                            : base + (size_t)(2 + (ch >> 1)) * pix_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
+                    *reinterpret_cast<uint4 *>(dst) = val;
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+            __half2 h = __floats2half2_rn(v0, v1);
+            float2 hf = __half22float2(h);
+            __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+            lo[i] = *reinterpret_cast<uint32_t *>(&l);
+        }
+        // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
+        // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
+        // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
+#pragma unroll
+        for (int plane = 0; plane < 2; plane++) {
+            const uint32_t *src = plane ? lo : hi;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+                if (gy < p.Hp && gx < p.Wp) {
+                    __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
+                    *reinterpret_cast<uint4 *>(dst) = val;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // ================================================================================================
 // The layer kernel
 // ================================================================================================
@@ -557,79 +641,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     const float v = fmaf(act[i], p.out_scale, s_bias[cb * 32 + i]);
                     act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
                 }
-                if constexpr (!FUSE && F8) {
-                    // planes: xh = fp16(x16) | xh8 = e4m3(xh * 2^-F8_C) | xl8 = e4m3((x16 - xh) * 2^F8_A)
-                    uint32_t hi[16], b8[16];       // b8[0..7] = xh8 (32 bytes), b8[8..15] = xl8 (32 bytes)
-                    constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
-                        __half2 h = __floats2half2_rn(v0, v1);
-                        float2 hf = __half22float2(h);
-                        hi[i] = *reinterpret_cast<uint32_t *>(&h);
-                        const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
-                        const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
-                        if (i & 1) { b8[i >> 1] |= h8 << 16; b8[8 + (i >> 1)] |= l8 << 16; }
-                        else { b8[i >> 1] = h8; b8[8 + (i >> 1)] = l8; }
-                    }
-                    const size_t pix_elems = (size_t)p.Hp * p.Wp * COUT;
-                    uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
-#pragma unroll
-                    for (int grp = 0; grp < 2; grp++) {       // grp 0: the fp16 plane (64 B per pixel), grp 1: both e4m3 planes (32 + 32 B)
-                        const uint32_t *src = grp ? b8 : hi;
-#pragma unroll
-                        for (int v = 0; v < 4; v++)
-                            sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-                            const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-                            const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-                            if (gy < p.Hp && gx < p.Wp) {
-                                const size_t pix = (size_t)gy * p.Wp + gx;
-                                uint8_t *dst = grp == 0 ? base + (pix * COUT + cb * 32) * 2 + ch * 16
-                                                        : base + (size_t)(2 + (ch >> 1)) * pix_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
-                                *reinterpret_cast<uint4 *>(dst) = val;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                } else if constexpr (!FUSE) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
-                        __half2 h = __floats2half2_rn(v0, v1);
-                        float2 hf = __half22float2(h);
-                        __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                        hi[i] = *reinterpret_cast<uint32_t *>(&h);
-                        lo[i] = *reinterpret_cast<uint32_t *>(&l);
-                    }
-                    // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
-                    // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
-                    // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
-#pragma unroll
-                    for (int plane = 0; plane < 2; plane++) {
-                        const uint32_t *src = plane ? lo : hi;
-#pragma unroll
-                        for (int v = 0; v < 4; v++)
-                            sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-                            const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-                            const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-                            if (gy < p.Hp && gx < p.Wp) {
-                                __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
-                                *reinterpret_cast<uint4 *>(dst) = val;
-                            }
-                        }
-                        __syncwarp();
-                    }
+                if constexpr (!FUSE) {
+                    epilogue_store32<COUT, F8>(act, p, stg, lane, (int)q, j, tx, ty, cb);
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll
@@ -667,6 +680,340 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ================================================================================================
+// The CTA-pair variant (cta_group::2) for Cout = 128
+// ================================================================================================
+// Two CTAs of a cluster (the two SMs of a TPC) each stage THEIR 16x16 region like the single-CTA kernel, but every
+// tcgen05.mma is M = 256: rows 0-127 come from CTA 0's shared memory, rows 128-255 from CTA 1's, and the N = 128
+// weight rows are split -- each CTA loads and holds only 64 of them.  One thread pair in the leader CTA drives both
+// SMs' tensor cores.  Per CTA this halves the weight bytes pulled from L2 and the B-operand bytes read from shared
+// memory per MMA (the single-CTA N = 128 MMAs sit at the 128 B/clk shared-memory operand limit).
+//   * all TMA loads of both CTAs signal the LEADER's mbarriers (cp.async.bulk.tensor ... .cta_group::2),
+//   * tcgen05.commit ... .multicast::cluster releases stages / slots / accumulators in both CTAs,
+//   * both CTAs' epilogue warps arrive (remotely) on the leader's accumulator-empty barriers.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+#define W2X_UMMA2_VARIANT(NAME, OPCODE)                                                                       \
+    __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,      \
+                                         uint32_t accum, uint32_t issue) {                                     \
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q " OPCODE      \
+                     " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),                                                \
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(issue)                                \
+                     : "memory");                                                                              \
+    }
+W2X_UMMA2_VARIANT(umma2_f16, "tcgen05.mma.cta_group::2.kind::f16")
+W2X_UMMA2_VARIANT(umma2_f8, "tcgen05.mma.cta_group::2.kind::f8f6f4")
+#undef W2X_UMMA2_VARIANT
+__device__ __forceinline__ void umma2_commit_if(uint32_t bar, uint32_t issue) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
+        "r"(issue), "h"((uint16_t)3)
+        : "memory");
+}
+
+template <int CIN, int COUT, bool FUSE, bool F8>
+struct PairCfg : Cfg<CIN, COUT, FUSE, F8> {
+    using Base = Cfg<CIN, COUT, FUSE, F8>;
+    static_assert(COUT == 128, "the CTA-pair kernel is built for the 128-wide layers");
+    static constexpr int B_HALF = Base::B_BLOCK / 2;                     // bytes of one weight stage held by ONE CTA (64 of the 128 rows)
+    static constexpr int NBP_FIT = (Base::SMEM_MAX - 1024 - Base::BAR_BYTES - Base::W6_BYTES - Base::STG_BYTES - Base::A_SLOTS * Base::A_SLOT) / B_HALF;
+    static constexpr int NBP = NBP_FIT > 12 ? 12 : NBP_FIT;
+    static constexpr int SMEM_BYTES = 1024 + Base::A_SLOTS * Base::A_SLOT + NBP * B_HALF + Base::BAR_BYTES + Base::W6_BYTES + Base::STG_BYTES;
+    static_assert((8 + 2 * NBP) * 8 + 4 <= 512, "barrier area overflow");
+    static_assert(B_HALF % 2048 == 0, "weight halves are moved as 2 KB TMA boxes");
+};
+
+template <int CIN, int COUT, bool FUSE, bool F8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
+                       const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+    using C = PairCfg<CIN, COUT, FUSE, F8>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + C::A_SLOTS * C::A_SLOT;
+    const uint32_t bar_base = b_base + C::NBP * C::B_HALF;
+    auto a_full = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+    auto a_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 + i); };
+    auto acc_full = [&](int i) { return bar_base + 8u * (uint32_t)(4 + i); };
+    auto acc_empty = [&](int i) { return bar_base + 8u * (uint32_t)(6 + i); };
+    auto b_full = [&](int i) { return bar_base + 8u * (uint32_t)(8 + i); };
+    auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(8 + C::NBP + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NBP);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
+    const float *s_w6 = reinterpret_cast<const float *>(smem_raw + (bar_base + C::BAR_BYTES - smem_u32(smem_raw)));
+    if constexpr (FUSE) {
+        float *w6 = const_cast<float *>(s_w6);
+        for (int i = threadIdx.x; i < 9 * COUT; i += NUM_THREADS) w6[i] = p.last_w[i];
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool is_leader = rank == 0;
+    const int n_pairs_cl = (int)(gridDim.x >> 1), pair_id = (int)(blockIdx.x >> 1);
+    const int n_pair_sets = (p.n_tilesets + 1) / 2;          // tile-sets are taken two at a time: (2q, 2q+1) -> (CTA 0, CTA 1)
+    const int tiles_y = (p.Hp + REGION - 1) / REGION;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(a_full(i), 1);        // leader's: its A producer's arrive.expect_tx covers the bytes of BOTH CTAs
+            mbar_init(a_empty(i), 2);       // one multicast tcgen05.commit per issuer
+            mbar_init(acc_full(i), 2);
+            mbar_init(acc_empty(i), 16);    // leader's: 8 local + 8 remote epilogue warps
+        }
+        for (int i = 0; i < C::NBP; i++) {
+            mbar_init(b_full(i), 1);
+            mbar_init(b_empty(i), 2);
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_in);
+        prefetch_tmap(&tmap_w);
+        if constexpr (F8) prefetch_tmap(&tmap_in8);
+    }
+    cluster_sync_all();                     // both CTAs' barriers exist before anything can signal them
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    // this CTA's tile-set of pair-set q (a phantom region below the frame when the count is odd: loads zero-fill, stores are masked)
+    auto region_of = [&](int q, int &tx, int &ty) {
+        const int ts = 2 * q + (int)rank;
+        if (ts < p.n_tilesets) { ty = ts / p.tiles_x; tx = ts - ty * p.tiles_x; }
+        else { ty = tiles_y; tx = 0; }
+    };
+
+    if (warp == 0) {
+        // ===================== A producer (both CTAs): boxes land locally, completion is counted on the LEADER's barrier ====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
+                int tx, ty;
+                region_of(q, tx, ty);
+                const int x0 = tx * REGION - 1, y0 = ty * REGION - 1;
+                for (int c = 0; c < C::NCHUNK; c++, it++) {
+                    const uint32_t slot = it & 1u, round = it >> 1;
+                    mbar_wait(a_empty(slot), (round & 1u) ^ 1u);
+                    if (is_leader) mbar_arrive_expect_tx(a_full(slot), 2u * (uint32_t)C::A_TX);
+                    const uint32_t bar = mapa_rank(a_full(slot), 0);
+                    const uint32_t dst = a_base + slot * C::A_SLOT;
+                    tma_load_4d_2cta(dst, &tmap_in, bar, c * C::KC, x0, y0, 0);
+                    if constexpr (F8) {
+                        tma_load_4d_2cta(dst + C::A_PLANE_PAD, &tmap_in8, bar, c * C::KC, x0, y0, 0);
+                        tma_load_4d_2cta(dst + C::A_PLANE_PAD + C::A8_PLANE_PAD, &tmap_in8, bar, c * C::KC, x0, y0, 1);
+                    } else {
+                        tma_load_4d_2cta(dst + C::A_PLANE_PAD, &tmap_in, bar, c * C::KC, x0, y0, 1);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== B producer (both CTAs): this CTA's 64 rows of every weight stage ========================
+        // tmap_w views the packed stream as rows of 64 bytes, box = 32 rows (2 KB).  A 128-row fp16 block is 8 KB
+        // (this CTA's half: 4 KB at +rank*4 KB); an e4m3 stage is [wh8 4 KB | wl8 4 KB] (halves: 2 KB at +rank*2 KB each).
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            constexpr int N_BLK = C::STAGES_PER_TILESET;
+            for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
+                for (int blk = 0; blk < N_BLK; blk++) {
+                    mbar_wait(b_empty(stage), phase ^ 1u);
+                    if (is_leader) mbar_arrive_expect_tx(b_full(stage), 2u * (uint32_t)C::B_HALF);
+                    const uint32_t bar = mapa_rank(b_full(stage), 0);
+                    const uint32_t dst = b_base + stage * C::B_HALF;
+                    const int row0 = blk * (C::B_BLOCK / 64);                 // first 64-byte row of this block in the stream
+                    const bool e4m3_stage = F8 && (blk & 1);
+                    if (e4m3_stage) {
+                        tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 32);               // wh8 rows 64*rank ..
+                        tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + 64 + (int)rank * 32);  // wl8 rows 64*rank ..
+                    } else {
+                        tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 64);
+                        tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + (int)rank * 64 + 32);
+                    }
+                    if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 7) {
+        // ===================== MMA issuers: LEADER CTA only, M = 256 across the pair ====================================
+        if (is_leader) {
+            const uint32_t leader = lane == 0 ? 1u : 0u;
+            const uint32_t jt = warp == 1 ? 0u : 1u;
+            constexpr uint32_t idesc_c = make_idesc(256, COUT);
+            constexpr uint32_t A_SBO = HALO * C::ROWB;
+            constexpr uint32_t B_SBO = 8 * C::B_ROWB;
+            constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::A_LAYOUT) >> 32);
+            constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::B_LAYOUT) >> 32);
+            constexpr uint32_t LO_FIXED = 1u << 16;
+            constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(HALO * C::ROWB8, C::A8_LAYOUT) >> 32);
+            constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
+            auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
+            uint32_t a_it = 0, stage = 0, phase = 0, n = 0, b_ready = 0;
+            auto acquire_b = [&](uint32_t &b0_out) {
+                if (!b_ready) mbar_wait(b_full(stage), phase);
+                tc_fence_after();
+                b0_out = (((b_base + stage * C::B_HALF) >> 4) & 0x3FFFu) | LO_FIXED;
+                uint32_t ns = stage + 1, np = phase;
+                if (ns == (uint32_t)C::NBP) { ns = 0; np ^= 1u; }
+                b_ready = mbar_test(b_full(ns), np);
+            };
+            auto release_b = [&]() {
+                umma2_commit_if(b_empty(stage), leader);
+                if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
+            };
+            for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
+                const uint32_t set = n & 1u;
+                mbar_wait(acc_empty(set), ((n >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t dj = tmem_base + (set * 2u + jt) * C::TILE_COLS;
+                for (int c = 0; c < C::NCHUNK; c++, a_it++) {
+                    const uint32_t slot = a_it & 1u;
+                    mbar_wait(a_full(slot), (a_it >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
+                    const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
+                    const uint32_t a8h0 = ((((a_base + slot * C::A_SLOT + C::A_PLANE_PAD) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB8 >> 4);
+                    const uint32_t a8l0 = a8h0 + (C::A8_PLANE_PAD >> 4);
+                    uint32_t tap_off = 0, tap_off8 = 0;
+                    for (int t = 0; t < 9; t++) {
+                        const uint32_t first = (c | t) != 0 ? 1u : 0u;
+#pragma unroll
+                        for (int kb = 0; kb < C::KBLOCKS; kb++) {
+                            const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;
+                            const uint32_t acc0 = kb ? 1u : first;
+                            uint32_t b0;
+                            if constexpr (F8) {
+                                acquire_b(b0);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                                release_b();
+                                acquire_b(b0);
+                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u, leader);
+                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (2048u >> 4)), idesc_c, 1u, leader);
+                                release_b();
+                            } else {
+                                acquire_b(b0);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                                release_b();
+                                acquire_b(b0);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                                release_b();
+                            }
+                        }
+                        tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
+                        tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
+                    }
+                    umma2_commit_if(a_empty(slot), leader);
+                }
+                umma2_commit_if(acc_full(set), leader);
+            }
+        }
+    } else {
+        // ===================== epilogue (both CTAs), same math as the single-CTA kernel ===================================
+        const uint32_t q4 = (uint32_t)warp & 3u;
+        const int j = warp >= 8 ? 1 : 0;
+        const uint32_t row = q4 * 32u + (uint32_t)lane;
+        const int oy = (int)(row >> 3), ox = (int)(row & 7u);
+        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q4) * 2048u;
+        uint32_t n = 0;
+        for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
+            const uint32_t set = n & 1u;
+            int tx, ty;
+            region_of(q, tx, ty);
+            mbar_wait(acc_full(set), (n >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + ((q4 * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
+            const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
+            const bool inside = fy < p.Hp && fx < p.Wp;
+            float pt[9];
+#pragma unroll
+            for (int t = 0; t < 9; t++) pt[t] = 0.f;
+#pragma unroll
+            for (int cb = 0; cb < COUT / 32; cb++) {
+                float act[32];
+                {
+                    uint32_t r[32];
+                    tmem_ld32(tcol + (uint32_t)cb * 32u, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const float v = fmaf(__uint_as_float(r[i]), p.out_scale, s_bias[cb * 32 + i]);
+                        act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
+                    }
+                }
+                if constexpr (FUSE) {
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+#pragma unroll
+                        for (int t = 0; t < 9; t++) {
+                            const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
+                            pt[t] = fmaf(act[4 * g + 0], w.x, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 1], w.y, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 2], w.z, pt[t]);
+                            pt[t] = fmaf(act[4 * g + 3], w.w, pt[t]);
+                        }
+                    }
+                } else {
+                    epilogue_store32<COUT, F8>(act, p, stg, lane, (int)q4, j, tx, ty, cb);
+                }
+            }
+            if constexpr (FUSE) {
+                if (inside) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)fy * p.Wp + fx) * 12);
+                    dst[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
+                    dst[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
+                    dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty(set), 0));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                     // nobody may free TMEM / exit while the peer can still signal or read
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
 }
 
 // ================================================================================================
@@ -882,8 +1229,22 @@ size_t layer_smem_bytes(int cin, int cout) {
     return 0;
 }
 
+template <int CIN, bool FUSE, bool F8>
+static cudaError_t set_attr_pair() {
+    return cudaFuncSetAttribute(tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES);
+}
+#define W2X_PAIR_CINS(X) X(32) X(64) X(128)
+
 cudaError_t init_kernels() {
     cudaError_t e;
+#define X(ci)                                                            \
+    if ((e = set_attr_pair<ci, false, false>()) != cudaSuccess) return e; \
+    if ((e = set_attr_pair<ci, true, false>()) != cudaSuccess) return e;  \
+    if ((e = set_attr_pair<ci, false, true>()) != cudaSuccess) return e;  \
+    if ((e = set_attr_pair<ci, true, true>()) != cudaSuccess) return e;
+    W2X_PAIR_CINS(X)
+#undef X
 #define X(ci, co) \
     if ((e = set_attr<ci, co>()) != cudaSuccess) return e;
     W2X_TC_SHAPES(X)
@@ -904,9 +1265,30 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8,
     return p.partial ? launch_k<CIN, COUT, true, false>(tmap, tmap8, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, tmap8, p, grid, s);
 }
 
+static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
+
+template <int CIN, bool FUSE, bool F8>
+static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const TcParams &p, int grid,
+                                 cudaStream_t s) {
+    tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8><<<grid, NUM_THREADS, PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, *tmapw, p);
+    return cudaGetLastError();
+}
+
+template <int CIN>
+static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+    using C0 = Cfg<CIN, 128, false, false>;
+    const size_t bytes = (size_t)C0::NCHUNK * 9 * C0::KBLOCKS * 2 * C0::B_BLOCK;   // both flavours stream the same number of bytes per tile-set
+    CUtensorMap tmapw;
+    if (make_weight_stream_map(&tmapw, p.wpack, bytes)) return cudaErrorInvalidValue;
+    const int n_pair_sets = (p.n_tilesets + 1) / 2;
+    int grid = 2 * (n_pair_sets < num_sms / 2 ? n_pair_sets : num_sms / 2);
+    if (f8) return p.partial ? launch_pair_k<CIN, true, true>(tmap, tmap8, &tmapw, p, grid, s) : launch_pair_k<CIN, false, true>(tmap, tmap8, &tmapw, p, grid, s);
+    return p.partial ? launch_pair_k<CIN, true, false>(tmap, tmap8, &tmapw, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, tmap8, &tmapw, p, grid, s);
+}
+
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8) {
+                            unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8, int pair) {
     TcParams p;
     p.wpack = reinterpret_cast<const uint16_t *>(wpack);
     p.bias = bias;
@@ -922,6 +1304,12 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     p.partial = partial;
     if (f8 && !tmap_in8) return cudaErrorInvalidValue;
     const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
+    if (pair && cout == 128 && num_sms >= 2) {
+#define X(ci) \
+    if (cin == ci) return launch_pair<ci>(tmap_in, t8, p, num_sms, f8 != 0, s);
+        W2X_PAIR_CINS(X)
+#undef X
+    }
 #define X(ci, co) \
     if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, t8, p, num_sms, f8 != 0, s);
     W2X_TC_SHAPES(X)
@@ -1007,6 +1395,20 @@ static PFN_encodeTiled get_encode() {
             fn = reinterpret_cast<PFN_encodeTiled>(p);
     }
     return fn;
+}
+
+// The packed weight stream as rows of 64 bytes, box = 32 rows (2 KB), no swizzle: the CTA-pair kernel's B loads.
+static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc || bytes % 2048) return -1;
+    cuuint64_t dims[2] = {64, (cuuint64_t)(bytes / 64)};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
 int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp) {
