@@ -779,6 +779,8 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool prof_on = p.prof != nullptr;
+    unsigned long long *prof = prof_on ? p.prof + (size_t)blockIdx.x * PROF_N : nullptr;
     const uint32_t rank = cluster_ctarank();
     const bool is_leader = rank == 0;
     const int n_pairs_cl = (int)(gridDim.x >> 1), pair_id = (int)(blockIdx.x >> 1);
@@ -824,13 +826,14 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         // ===================== A producer (both CTAs): boxes land locally, completion is counted on the LEADER's barrier ====
         if (lane == 0) {
             uint32_t it = 0;
+            unsigned long long w_a = 0;
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
                 int tx, ty;
                 region_of(q, tx, ty);
                 const int x0 = tx * REGION - 1, y0 = ty * REGION - 1;
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
                     const uint32_t slot = it & 1u, round = it >> 1;
-                    mbar_wait(a_empty(slot), (round & 1u) ^ 1u);
+                    mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
                     if (is_leader) mbar_arrive_expect_tx(a_full(slot), 2u * (uint32_t)C::A_TX);
                     const uint32_t bar = mapa_rank(a_full(slot), 0);
                     const uint32_t dst = a_base + slot * C::A_SLOT;
@@ -843,6 +846,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     }
                 }
             }
+            if (prof_on) prof[PROF_APROD_WAIT] += w_a;
         }
     } else if (warp == 2) {
         // ===================== B producer (both CTAs): this CTA's 64 rows of every weight stage ========================
@@ -850,10 +854,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         // (this CTA's half: 4 KB at +rank*4 KB); an e4m3 stage is [wh8 4 KB | wl8 4 KB] (halves: 2 KB at +rank*2 KB each).
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            unsigned long long w_b = 0;
             constexpr int N_BLK = C::STAGES_PER_TILESET;
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
                 for (int blk = 0; blk < N_BLK; blk++) {
-                    mbar_wait(b_empty(stage), phase ^ 1u);
+                    mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
                     if (is_leader) mbar_arrive_expect_tx(b_full(stage), 2u * (uint32_t)C::B_HALF);
                     const uint32_t bar = mapa_rank(b_full(stage), 0);
                     const uint32_t dst = b_base + stage * C::B_HALF;
@@ -869,6 +874,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
                 }
             }
+            if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1 || warp == 7) {
         // ===================== MMA issuers: LEADER CTA only, M = 256 across the pair ====================================
@@ -885,8 +891,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
             auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
             uint32_t a_it = 0, stage = 0, phase = 0, n = 0, b_ready = 0;
+            unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+            const long long t_begin = clock64();
             auto acquire_b = [&](uint32_t &b0_out) {
-                if (!b_ready) mbar_wait(b_full(stage), phase);
+                if (!b_ready) mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
                 tc_fence_after();
                 b0_out = (((b_base + stage * C::B_HALF) >> 4) & 0x3FFFu) | LO_FIXED;
                 uint32_t ns = stage + 1, np = phase;
@@ -899,12 +907,12 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             };
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
                 const uint32_t set = n & 1u;
-                mbar_wait(acc_empty(set), ((n >> 1) & 1u) ^ 1u);
+                mbar_wait_prof(acc_empty(set), ((n >> 1) & 1u) ^ 1u, prof_on, w_acc);
                 tc_fence_after();
                 const uint32_t dj = tmem_base + (set * 2u + jt) * C::TILE_COLS;
                 for (int c = 0; c < C::NCHUNK; c++, a_it++) {
                     const uint32_t slot = a_it & 1u;
-                    mbar_wait(a_full(slot), (a_it >> 1) & 1u);
+                    mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                     tc_fence_after();
                     const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
                     const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
@@ -947,6 +955,13 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                 }
                 umma2_commit_if(acc_full(set), leader);
             }
+            if (prof_on && leader && jt == 0) {
+                prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
+                prof[PROF_MMA_WAIT_ACC] += w_acc;
+                prof[PROF_MMA_WAIT_A] += w_af;
+                prof[PROF_MMA_WAIT_B] += w_bf;
+                prof[PROF_TILESETS] += n;
+            }
         }
     } else {
         // ===================== epilogue (both CTAs), same math as the single-CTA kernel ===================================
@@ -956,11 +971,13 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
         const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q4) * 2048u;
         uint32_t n = 0;
+        unsigned long long w_e = 0, work_e = 0;
         for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
             const uint32_t set = n & 1u;
             int tx, ty;
             region_of(q, tx, ty);
-            mbar_wait(acc_full(set), (n >> 1) & 1u);
+            mbar_wait_prof(acc_full(set), (n >> 1) & 1u, prof_on, w_e);
+            const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q4 * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
             const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
@@ -1008,6 +1025,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty(set), 0));
+            if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
+        }
+        if (prof_on && warp == 3 && lane == 0) {
+            prof[PROF_EPI_WAIT] += w_e;
+            prof[PROF_EPI_WORK] += work_e;
         }
     }
 
