@@ -341,8 +341,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f8"],
-                    help="tcgen05 arithmetic: three fp16 products (default) or fp16 + two e4m3 correction products")
+    ap.add_argument("--precision", default="f8", choices=["f16x3", "f8"],
+                    help="tcgen05 arithmetic: fp16 + two e4m3 correction products (the library default) or three fp16 products")
     ap.add_argument("--check", action="store_true", help="multi-GPU: verify the per-layer result against the one-shot band mode, bit for bit")
     ap.add_argument("--halo", default="per-layer", choices=["input", "per-layer"],
                     help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")

@@ -102,10 +102,12 @@ W2X_API void w2x_ctx_destroy(w2x_ctx *ctx);
 W2X_API int w2x_ctx_set_engine(w2x_ctx *ctx, int engine);
 W2X_API int w2x_ctx_get_engine(const w2x_ctx *ctx);
 /* Arithmetic of the tcgen05 engine (both keep fp32 accumulators and meet the 1e-4 gate of BASELINE.json):
- *   W2X_PRECISION_F16X3     x*w = xh*wh + xl*wh + xh*wl, three fp16 tensor-core products (default;
- *                           measured <= 8e-6 max-abs against the reference CPU path on white noise)
- *   W2X_PRECISION_F16_F8X2  the two correction products run on e4m3 copies of the operands at twice the
- *                           tensor rate (2.0 instead of 3.0 pass-equivalents; ~2-3e-5 max-abs on white noise) */
+ *   W2X_PRECISION_F16X3     x*w = xh*wh + xl*wh + xh*wl, three fp16 tensor-core products
+ *                           (measured <= 8e-6 max-abs against the reference CPU path on white noise)
+ *   W2X_PRECISION_F16_F8X2  (default) the two correction products run on e4m3 copies of the operands at twice
+ *                           the tensor rate: 2.0 instead of 3.0 pass-equivalents; measured <= 2.9e-5 max-abs on
+ *                           white noise, <= 7e-6 on a smooth image (profiles/r01_parity_report.txt)
+ * The environment variable W2X_PRECISION=f16x3|f8 sets the initial value of new contexts. */
 #define W2X_PRECISION_F16X3 0
 #define W2X_PRECISION_F16_F8X2 1
 W2X_API int w2x_ctx_set_precision(w2x_ctx *ctx, int precision);

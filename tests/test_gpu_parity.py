@@ -28,6 +28,7 @@ ENGINES = [("fp32", 1, FP32_TOL), ("tc", 2, TC_TOL), ("tc8", 2, F8_TOL)]
 @pytest.fixture(scope="module")
 def ctxs(w2x):
     c = {name: w2x.Context(0, engine=eng) for name, eng, _ in ENGINES}
+    c["tc"].set_precision(w2x.PRECISION_F16X3)
     c["tc8"].set_precision(w2x.PRECISION_F16_F8X2)
     yield c
     for v in c.values():
@@ -349,6 +350,7 @@ def test_unsupported_shapes_fall_back_to_the_fp32_engine_or_fail_loudly(w2x, ctx
     ref = om.convert(x, n_job=ncpu)
     auto = w2x.Context(0)
     try:
+        assert auto.get_precision() == w2x.PRECISION_F16_F8X2          # the library default
         assert np.abs(auto.convert_plane(m, x) - ref).max() <= FP32_TOL
     finally:
         auto.close()
@@ -369,4 +371,5 @@ def test_launch_counter_and_timing(ctxs, models, oracle_mod):
         ctx.set_timing(False)
     assert ctx.launch_count() - n0 == 8                        # pad + 7 layer kernels
     assert [t[2] for t in times] == ["first_1xN"] + ["tcgen05_f16x3"] * 4 + ["tcgen05_f16x3+last", "last_gather"]
+    assert ctxs["tc8"].get_precision() == 1
     assert all(t[0] > 0 and t[1] == 1 for t in times)

@@ -38,4 +38,4 @@ def test_cpp_convert_with_models_on_gpu(exe, json_models, oracle_mod, oracle_mod
     assert "number of input planes mismatch" in p.stderr
     y = np.fromfile(fout, np.float32).reshape(45, 70)
     ref = oracle_models["noise1"].convert(x, n_job=ncpu)
-    assert np.abs(y - ref).max() <= 2e-5
+    assert np.abs(y - ref).max() <= 6e-5   # library default precision: fp16 + 2 x e4m3 corrections

@@ -13,7 +13,7 @@ passes = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 engine = {"tc": w2x.ENGINE_TC, "fp32": w2x.ENGINE_FP32}[sys.argv[3] if len(sys.argv) > 3 else "tc"]
 om = oracle.OracleModel.golden("scale2.0x")
 m = w2x.Model.from_arrays(om.weights, om.biases)
-ctx = w2x.Context(0, engine=engine)
+ctx = w2x.Context(0, engine=engine)      # precision: library default, or W2X_PRECISION=f16x3
 x = oracle.seeded_plane(size, size, 1, "uniform")
 for _ in range(passes):
     y = ctx.convert_plane(m, x)

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -49,7 +50,7 @@ struct w2x_ctx {
     int walk = W2X_WALK_FUSED;
     int desc_mode = 0;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
-    int precision = W2X_PRECISION_F16X3;
+    int precision = W2X_PRECISION_F16_F8X2;   // default; W2X_PRECISION=f16x3 in the environment or w2x_ctx_set_precision() selects the 3 x fp16 scheme
     int pair = 0;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -599,6 +600,10 @@ int w2x_ctx_create(int device, w2x_ctx **out_ctx) {
     DeviceGuard g(device);
     CU_CHECK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    if (const char *pe = std::getenv("W2X_PRECISION")) {
+        if (!std::strcmp(pe, "f16x3")) ctx->precision = W2X_PRECISION_F16X3;
+        else if (!std::strcmp(pe, "f16+f8x2") || !std::strcmp(pe, "f8")) ctx->precision = W2X_PRECISION_F16_F8X2;
+    }
     CU_CHECK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
     CU_CHECK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
     for (int i = 0; i < 8; i++) {
