@@ -108,7 +108,6 @@ def lib():
     L.w2x_band_step.argtypes = [vp, ci]
     L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
     L.w2x_band_finish.argtypes = [vp, vp, cs]
-    L.w2x_debug_set_mma_mode.argtypes = [vp, ci]
     L.w2x_debug_set_host_bands.argtypes = [vp, ci]
     L.w2x_debug_set_pair.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
@@ -248,7 +247,6 @@ class Context:
     def set_block_walk(self, mode): _check(lib().w2x_ctx_set_block_walk(self._h, mode))
     def set_scratch_limit(self, nbytes): _check(lib().w2x_ctx_set_scratch_limit(self._h, nbytes))
     def set_timing(self, on): _check(lib().w2x_ctx_set_timing(self._h, int(on)))
-    def debug_set_mma_mode(self, mode): _check(lib().w2x_debug_set_mma_mode(self._h, mode))
 
     def debug_set_pair(self, on): _check(lib().w2x_debug_set_pair(self._h, int(on)))
     def debug_set_host_bands(self, n): _check(lib().w2x_debug_set_host_bands(self._h, n))

@@ -48,7 +48,6 @@ struct w2x_ctx {
     int cc_major = 0, cc_minor = 0;
     int engine = W2X_ENGINE_AUTO;
     int walk = W2X_WALK_FUSED;
-    int desc_mode = 0;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
     int precision = W2X_PRECISION_F16_F8X2;   // default; W2X_PRECISION=f16x3 in the environment or w2x_ctx_set_precision() selects the 3 x fp16 scheme
     int pair = 0;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2)
@@ -744,14 +743,6 @@ W2X_API int w2x_debug_set_host_bands(w2x_ctx *ctx, int bands) {
 W2X_API int w2x_debug_set_fuse_last(w2x_ctx *ctx, int on) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
     ctx->fuse_last = on != 0;
-    return W2X_OK;
-}
-
-// Probe switch (not part of the stable ABI): MMA issue variant of the tcgen05 engine
-// (0 plain, 1 A-collector reuse, 2 weight-stationary .ws with B-collector reuse).
-W2X_API int w2x_debug_set_mma_mode(w2x_ctx *ctx, int mode) {
-    if (check_ctx(ctx)) return W2X_ERR_ARG;
-    ctx->desc_mode = mode;
     return W2X_OK;
 }
 

@@ -135,10 +135,6 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
     }
 W2X_UMMA_VARIANT(umma_f16, "tcgen05.mma.cta_group::1.kind::f16")
 W2X_UMMA_VARIANT(umma_f8, "tcgen05.mma.cta_group::1.kind::f8f6f4")   // e4m3 x e4m3 -> f32, K = 32 per instruction, twice the f16 rate
-// operand-collector hints (SASS: UTCHMMA gdesc.A_KEEP / .A_REUSE): keep the A operand in the tensor core's
-// collector for the next MMA that uses the same activation slice
-W2X_UMMA_VARIANT(umma_f16_a_fill, "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill")
-W2X_UMMA_VARIANT(umma_f16_a_last, "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse")
 #undef W2X_UMMA_VARIANT
 __device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t issue) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue) : "memory");
@@ -274,7 +270,6 @@ struct TcParams {
     int Wp, Hp;
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / (wscale * ACT_SCALE)
-    int mma_mode;            // reserved probe switch (unused)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
@@ -1320,7 +1315,6 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     p.tiles_x = (pw + REGION - 1) / REGION;
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale;
-    p.mma_mode = 0;
     p.prof = prof;
     p.last_w = last_w;
     p.partial = partial;
