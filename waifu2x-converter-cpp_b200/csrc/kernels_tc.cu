@@ -1037,22 +1037,18 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
 // First layer (Cin = 1), last layer (Cout = 1), layout converters -- CUDA-core, HBM-bound
 // ================================================================================================
 // First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
-// writes the NHWC frame the tcgen05 layers consume.
+// writes the NHWC hi/lo frame the tcgen05 layers consume.  One thread per pixel.
 template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
 first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const float *__restrict__ wgt,
                    const float *__restrict__ bias, __half *__restrict__ out) {
-    // thread = (pixel, group of 8 output planes); consecutive threads cover the groups of one pixel, then the next
-    // pixel of the row: a warp's stores are 32 x 16 B (xh) / 32 x 8 B (e4m3 planes) of CONTIGUOUS memory.
-    constexpr int G = COUT / 8, PX = 256 / G;          // groups per pixel, pixels per block
     __shared__ float s_w[COUT * 9];
     __shared__ float s_b[COUT];
     for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) s_w[i] = wgt[i];
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = bias[i];
     __syncthreads();
-    const int c8 = threadIdx.x % G;
-    const int x = blockIdx.x * PX + threadIdx.x / G, y = blockIdx.y;
-    if (x >= pw) return;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw || y >= ph) return;
     float v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ky++)
@@ -1062,41 +1058,46 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
         }
     const size_t plane_elems = (size_t)ph * pw * COUT;
-    const size_t pix = (size_t)y * pw + x;
-    uint32_t hi[4], lo[4];
+    __half *dst_hi = out + ((size_t)y * pw + x) * COUT;
+    __half *dst_lo = dst_hi + plane_elems;
+#pragma unroll 1
+    for (int c8 = 0; c8 < COUT / 8; c8++) {   // not unrolled: keeps the kernel at <= 64 registers, 4 blocks/SM (HBM-write-bound)
+        uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float a[2];
+        for (int i = 0; i < 4; i++) {
+            float a[2];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const float *w = s_w + (c8 * 8 + 2 * i + e) * 9;
-            float t = w[0] * v[0];
+            for (int e = 0; e < 2; e++) {
+                const float *w = s_w + (c8 * 8 + 2 * i + e) * 9;
+                float t = w[0] * v[0];
 #pragma unroll
-            for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
-            float r = (0.f + t) + s_b[c8 * 8 + 2 * i + e];
-            a[e] = (fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f)) * ACT_SCALE;
+                for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
+                float r = (0.f + t) + s_b[c8 * 8 + 2 * i + e];
+                a[e] = (fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f)) * ACT_SCALE;
+            }
+            __half2 h = __floats2half2_rn(a[0], a[1]);
+            float2 hf = __half22float2(h);
+            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+            if constexpr (F8) {
+                constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+                const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+                const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
+                else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+            } else {
+                __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
+                lo[i] = *reinterpret_cast<uint32_t *>(&l);
+            }
         }
-        __half2 h = __floats2half2_rn(a[0], a[1]);
-        float2 hf = __half22float2(h);
-        hi[i] = *reinterpret_cast<uint32_t *>(&h);
+        reinterpret_cast<uint4 *>(dst_hi)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         if constexpr (F8) {
-            constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
-            const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
-            const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
-            if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
-            else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+            uint8_t *b = reinterpret_cast<uint8_t *>(out);
+            const size_t pix = (size_t)y * pw + x;
+            *reinterpret_cast<uint2 *>(b + 2 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[0], lo[1]);
+            *reinterpret_cast<uint2 *>(b + 3 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[2], lo[3]);
         } else {
-            __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
-            lo[i] = *reinterpret_cast<uint32_t *>(&l);
+            reinterpret_cast<uint4 *>(dst_lo)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-    }
-    reinterpret_cast<uint4 *>(out + pix * COUT)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if constexpr (F8) {
-        uint8_t *b = reinterpret_cast<uint8_t *>(out);
-        *reinterpret_cast<uint2 *>(b + 2 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[0], lo[1]);
-        *reinterpret_cast<uint2 *>(b + 3 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[2], lo[3]);
-    } else {
-        reinterpret_cast<uint4 *>(out + plane_elems + pix * COUT)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -1334,8 +1335,7 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
 
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
                          int cout, __half *out, cudaStream_t s, int f8) {
-    const int px_per_block = 256 / (cout / 8);
-    dim3 grid((pw + px_per_block - 1) / px_per_block, ph);
+    dim3 grid((pw + 31) / 32, (ph + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
 #define W2X_FIRST(C)                                                                                         \
     case C:                                                                                                  \
