@@ -35,7 +35,7 @@ struct DevModel {                       // device-resident copy of one model
     std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
     std::vector<uint8_t *> pack8;       // same for the "f8" flavour (fp16 main product + e4m3 corrections)
     std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
-    float *last_w_t = nullptr;          // last layer's weights transposed to [9][Cin] (fused last layer)
+    std::vector<float> last_w_t;        // HOST: last layer's weights transposed to [9][Cin] (fused last layer, passed as kernel parameters)
 };
 
 struct TimedSpan { int layer; cudaEvent_t e0, e1; };
@@ -145,11 +145,9 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
     }
     if (m->tc_eligible) {
         const Layer &L = m->layers.back();                // n_out == 1: w is [1][Cin][9]
-        std::vector<float> wt((size_t)9 * L.n_in);
+        dm.last_w_t.assign((size_t)9 * L.n_in, 0.f);
         for (int c = 0; c < L.n_in; c++)
-            for (int t = 0; t < 9; t++) wt[(size_t)t * L.n_in + c] = L.w[(size_t)c * 9 + t];
-        CU_CHECK(cudaMalloc(&dm.last_w_t, wt.size() * sizeof(float)));
-        CU_CHECK(cudaMemcpy(dm.last_w_t, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice));
+            for (int t = 0; t < 9; t++) dm.last_w_t[(size_t)t * L.n_in + c] = L.w[(size_t)c * 9 + t];
     }
     CU_CHECK(cudaStreamSynchronize(ctx->stream));
     auto res = ctx->models.emplace(m->uid, std::move(dm));
@@ -269,7 +267,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
-    const bool fuse = ctx->fuse_last && n >= 3 && dm->last_w_t != nullptr;
+    const bool fuse = ctx->fuse_last && n >= 3 && !dm->last_w_t.empty();
     for (int li = 1; li + 1 < n; li++) {
         const Layer &L = m->layers[(size_t)li];
         logf(ctx, "Iteration #%d...", li + 1);
@@ -283,7 +281,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
                                          dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
                                          ctx->num_sms, ctx->stream,
                                          ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
-                                         fused_here ? dm->last_w_t : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
+                                         fused_here ? dm->last_w_t.data() : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
                                          f8 ? &map8 : nullptr, ctx->pair));
         }
         note_kernel(ctx, li, f8 ? (fused_here ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
@@ -493,7 +491,7 @@ int w2x_band_step(w2x_band *band, int step) {
             LayerTimer t(ctx, step);
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)step] : (const void *)dm->pack[(size_t)step],
                                          dm->b[(size_t)step], out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
-                                         ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t : nullptr,
+                                         ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t.data() : nullptr,
                                          fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr));
         }
         note_kernel(ctx, step, fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
@@ -622,7 +620,6 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
         for (auto p : kv.second.b) cudaFree(p);
         for (auto p : kv.second.pack) cudaFree(p);
         for (auto p : kv.second.pack8) cudaFree(p);
-        cudaFree(kv.second.last_w_t);
     }
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->buf[i]);

@@ -44,7 +44,7 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
                             int cin, int cout, int pw, int ph, float out_scale, int f8, int num_sms,
                             cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
                             float *partial = nullptr, const CUtensorMap *tmap_in8 = nullptr, int pair = 0);
-// Fused last layer: launch_tc_layer(..., last_w = [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
+// Fused last layer: launch_tc_layer(..., last_w = HOST pointer to [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
 // tcgen05 layer emit per-pixel tap partials instead of activations; launch_last_gather sums the 3x3
 // neighbourhood of partials, adds the bias, applies the leaky-ReLU and writes the cropped fp32 plane.
 cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias, int crop, float *dst,

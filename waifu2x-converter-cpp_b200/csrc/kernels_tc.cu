@@ -236,9 +236,9 @@ struct Cfg {
     // (accumulators D1 | D2 side by side, summed in the epilogue) -- two MMAs per K step instead of three.
     static constexpr bool STACK = COUT <= 64 && !F8;
     static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
-    // F8: per 32-channel block one stage of wh (fp16, Cout x 64 B) and one of [wh8 | wl8] (e4m3, Cout x 32 B each);
-    // for Cout <= 64 the two are merged into one stage (fewer barrier round trips on layers that are not tensor-bound).
-    static constexpr bool MERGE = F8 && COUT <= 64;
+    // F8: per 32-channel block ONE stage [wh fp16 (Cout x 64 B) | wh8 | wl8 (e4m3, Cout x 32 B each)]: four MMAs per
+    // issuer per barrier round trip.
+    static constexpr bool MERGE = F8 && (COUT <= 64 || FUSE);   // (a 128-wide layer with store staging has room for only two 16 KB stages)
     static constexpr int B_STAGE = (STACK || MERGE) ? 2 * B_BLOCK : B_BLOCK;
     static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * ((STACK || MERGE) ? 1 : 2);
     // ---- accumulators ----
@@ -247,7 +247,7 @@ struct Cfg {
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
     // ---- shared memory map: [A slots][B stages][barriers + bias (1 KB)][last-layer weights][store staging] ----
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int W6_BYTES = FUSE ? 9 * COUT * 4 : 0;                 // fused last layer: its [tap][c] fp32 weights
+    static constexpr int W6_BYTES = 0;                                       // (the fused last layer's weights travel as kernel parameters)
     static constexpr int STG_BYTES = FUSE ? 0 : 8 * 2048;                    // epilogue store staging, 2 KB per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
@@ -273,8 +273,10 @@ struct TcParams {
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
-    const float *last_w;        // [9][COUT]  (tap-major)
-    float *partial;
+    float *partial;             // nullptr = not fused
+    float last_w[9 * 128];      // [9][COUT] tap-major, by value: the epilogue's FFMAs read them straight from the constant
+                                // bank (kernel parameters), which keeps 288 broadcast LDS.128 per pixel off the shared-memory
+                                // pipe the tensor core's operand fetches saturate
 };
 
 // per-CTA profile record (cycles, accumulated over launches)
@@ -399,11 +401,6 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));   // COUT floats
     for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
-    const float *s_w6 = reinterpret_cast<const float *>(smem_raw + (bar_base + C::BAR_BYTES - smem_u32(smem_raw)));   // [9][COUT]
-    if constexpr (FUSE) {
-        float *w6 = const_cast<float *>(s_w6);
-        for (int i = threadIdx.x; i < 9 * COUT; i += NUM_THREADS) w6[i] = p.last_w[i];
-    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
@@ -644,11 +641,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     for (int g = 0; g < 8; g++) {
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
-                            const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
-                            pt[t] = fmaf(act[4 * g + 0], w.x, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 1], w.y, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 2], w.z, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 3], w.w, pt[t]);
+                            const float *w = p.last_w + t * COUT + cb * 32 + 4 * g;   // compile-time offsets into the parameter bank
+                            pt[t] = fmaf(act[4 * g + 0], w[0], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 1], w[1], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 2], w[2], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 3], w[3], pt[t]);
                         }
                     }
                 }
@@ -739,7 +736,8 @@ template <int CIN, int COUT, bool FUSE, bool F8>
 struct PairCfg : Cfg<CIN, COUT, FUSE, F8> {
     using Base = Cfg<CIN, COUT, FUSE, F8>;
     static_assert(COUT == 128, "the CTA-pair kernel is built for the 128-wide layers");
-    static constexpr int B_HALF = Base::B_BLOCK / 2;                     // bytes of one weight stage held by ONE CTA (64 of the 128 rows)
+    static constexpr int B_HALF = Base::B_BLOCK;                         // bytes of one weight stage held by ONE CTA: its 64 rows of BOTH blocks
+                                                                         // of a 32-channel step ([hi | lo] or [wh | wh8 | wl8])
     static constexpr int NBP_FIT = (Base::SMEM_MAX - 1024 - Base::BAR_BYTES - Base::W6_BYTES - Base::STG_BYTES - Base::A_SLOTS * Base::A_SLOT) / B_HALF;
     static constexpr int NBP = NBP_FIT > 12 ? 12 : NBP_FIT;
     static constexpr int SMEM_BYTES = 1024 + Base::A_SLOTS * Base::A_SLOT + NBP * B_HALF + Base::BAR_BYTES + Base::W6_BYTES + Base::STG_BYTES;
@@ -767,11 +765,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
     for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
-    const float *s_w6 = reinterpret_cast<const float *>(smem_raw + (bar_base + C::BAR_BYTES - smem_u32(smem_raw)));
-    if constexpr (FUSE) {
-        float *w6 = const_cast<float *>(s_w6);
-        for (int i = threadIdx.x; i < 9 * COUT; i += NUM_THREADS) w6[i] = p.last_w[i];
-    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
@@ -850,21 +843,23 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             unsigned long long w_b = 0;
-            constexpr int N_BLK = C::STAGES_PER_TILESET;
+            constexpr int N_STEPS = C::NCHUNK * 9 * C::KBLOCKS;                // one stage per (chunk, tap, 32-channel block)
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
-                for (int blk = 0; blk < N_BLK; blk++) {
+                for (int blk = 0; blk < N_STEPS; blk++) {
                     mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
                     if (is_leader) mbar_arrive_expect_tx(b_full(stage), 2u * (uint32_t)C::B_HALF);
                     const uint32_t bar = mapa_rank(b_full(stage), 0);
                     const uint32_t dst = b_base + stage * C::B_HALF;
-                    const int row0 = blk * (C::B_BLOCK / 64);                 // first 64-byte row of this block in the stream
-                    const bool e4m3_stage = F8 && (blk & 1);
-                    if (e4m3_stage) {
-                        tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 32);               // wh8 rows 64*rank ..
-                        tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + 64 + (int)rank * 32);  // wl8 rows 64*rank ..
-                    } else {
-                        tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 64);
-                        tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + (int)rank * 64 + 32);
+                    const int row0 = blk * (2 * C::B_BLOCK / 64);             // first 64-byte row of this step in the stream (256 rows per step)
+                    // first block (128 rows x 64 B, fp16): this CTA's rows 64*rank .. +64
+                    tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 64);
+                    tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + (int)rank * 64 + 32);
+                    if constexpr (F8) {   // [wh8 | wl8]: 128 rows x 32 B each = 64 stream rows each; this CTA's half = 32 stream rows
+                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 32);
+                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 192 + (int)rank * 32);
+                    } else {              // lo block (fp16)
+                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 64);
+                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 64 + 32);
                     }
                     if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
                 }
@@ -921,27 +916,21 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                             const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;
                             const uint32_t acc0 = kb ? 1u : first;
                             uint32_t b0;
+                            acquire_b(b0);                  // one stage per 32-channel step: this CTA's rows of both blocks
                             if constexpr (F8) {
-                                acquire_b(b0);
                                 umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
                                 umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                release_b();
-                                acquire_b(b0);
-                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u, leader);
-                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (2048u >> 4)), idesc_c, 1u, leader);
-                                release_b();
+                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u, leader);
+                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u, leader);
                             } else {
-                                acquire_b(b0);
                                 umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
                                 umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
                                 umma2_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
                                 umma2_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                release_b();
-                                acquire_b(b0);
-                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
-                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                release_b();
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0 + (4096u >> 4)), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + (4096u >> 4) + 2u), idesc_c, 1u, leader);
                             }
+                            release_b();
                         }
                         tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                         tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
@@ -998,11 +987,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     for (int g = 0; g < 8; g++) {
 #pragma unroll
                         for (int t = 0; t < 9; t++) {
-                            const float4 w = *reinterpret_cast<const float4 *>(s_w6 + t * COUT + cb * 32 + 4 * g);
-                            pt[t] = fmaf(act[4 * g + 0], w.x, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 1], w.y, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 2], w.z, pt[t]);
-                            pt[t] = fmaf(act[4 * g + 3], w.w, pt[t]);
+                            const float *w = p.last_w + t * COUT + cb * 32 + 4 * g;   // compile-time offsets into the parameter bank
+                            pt[t] = fmaf(act[4 * g + 0], w[0], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 1], w[1], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 2], w[2], pt[t]);
+                            pt[t] = fmaf(act[4 * g + 3], w[3], pt[t]);
                         }
                     }
                 } else {
@@ -1316,8 +1305,11 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale;
     p.prof = prof;
-    p.last_w = last_w;
     p.partial = partial;
+    if (partial) {
+        if (!last_w) return cudaErrorInvalidValue;
+        for (int i = 0; i < 9 * cout; i++) p.last_w[i] = last_w[i];      // HOST pointer: [9][cout]
+    }
     if (f8 && !tmap_in8) return cudaErrorInvalidValue;
     const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
     if (pair && cout == 128 && num_sms >= 2) {
