@@ -171,21 +171,19 @@ def test_cta_pair_kernels_are_bit_identical_to_single_cta(ctxs, models, oracle_m
     ctx = ctxs[engine]
     for (w, h, seed) in ((200, 120, 3), (90, 75, 4), (16, 16, 5), (333, 41, 6)):
         x = oracle_mod.seeded_plane(w, h, seed, "uniform")
-        single = ctx.convert_plane(models["scale2.0x"], x)
+        paired = ctx.convert_plane(models["scale2.0x"], x)              # the default: CTA pairs on the 128-wide layers
         try:
-            ctx.debug_set_pair(True)
-            paired = ctx.convert_plane(models["scale2.0x"], x)
             ctx.debug_set_fuse_last(False)
             paired_sep = ctx.convert_plane(models["scale2.0x"], x)
-        finally:
             ctx.debug_set_pair(False)
+            single_sep = ctx.convert_plane(models["scale2.0x"], x)
+            ctx.debug_set_fuse_last(True)
+            single = ctx.convert_plane(models["scale2.0x"], x)
+        finally:
+            ctx.debug_set_pair(True)
             ctx.debug_set_fuse_last(True)
         assert np.array_equal(single, paired), (w, h)
-        ctx.debug_set_fuse_last(False)
-        try:
-            assert np.array_equal(ctx.convert_plane(models["scale2.0x"], x), paired_sep), (w, h)
-        finally:
-            ctx.debug_set_fuse_last(True)
+        assert np.array_equal(single_sep, paired_sep), (w, h)
 
 
 def test_engines_agree_with_each_other(ctxs, models, oracle_mod):

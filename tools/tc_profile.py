@@ -22,7 +22,7 @@ ctx = w2x.Context(0, engine=w2x.ENGINE_TC)
 x = oracle.seeded_plane(size, size, 1, "uniform")
 mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0 = f16x3, 1 = f16 + 2 x e4m3 corrections
 ctx.set_precision(mode)
-ctx.debug_set_pair(len(sys.argv) > 3 and sys.argv[3] == "pair")
+ctx.debug_set_pair(not (len(sys.argv) > 3 and sys.argv[3] == "single"))
 ctx.convert_plane(m, x)
 ctx.convert_plane(m, x)
 ctx.set_timing(True)

@@ -32,6 +32,7 @@ namespace {
 struct DevModel {                       // device-resident copy of one model
     std::vector<float *> w;             // per layer [Cout][Cin][9] fp32
     std::vector<float *> b;             // per layer [Cout] fp32  ((float)bias, src/modelHandler.cpp:147)
+    std::vector<std::vector<float>> b_host;   // the same on the host (the tcgen05 kernels take them as kernel parameters)
     std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
     std::vector<uint8_t *> pack8;       // same for the "f8" flavour (fp16 main product + e4m3 corrections)
     std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
@@ -50,7 +51,7 @@ struct w2x_ctx {
     int walk = W2X_WALK_FUSED;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
     int precision = W2X_PRECISION_F16_F8X2;   // default; W2X_PRECISION=f16x3 in the environment or w2x_ctx_set_precision() selects the 3 x fp16 scheme
-    int pair = 0;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2)
+    int pair = 1;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2); w2x_debug_set_pair(0) = single-CTA kernels
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     size_t scratch_limit = (size_t)16 << 30;
@@ -131,6 +132,7 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
         CU_CHECK(cudaMemcpyAsync(dm.w[i], L.w.data(), L.w.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         std::vector<float> bf(L.b.size());
         for (size_t k = 0; k < bf.size(); k++) bf[k] = static_cast<float>(L.b[k]);
+        dm.b_host.push_back(bf);
         CU_CHECK(cudaMalloc(&dm.b[i], bf.size() * sizeof(float)));
         CU_CHECK(cudaMemcpyAsync(dm.b[i], bf.data(), bf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         CU_CHECK(cudaStreamSynchronize(ctx->stream));   // bf goes out of scope
@@ -278,7 +280,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         {
             LayerTimer t(ctx, li);
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)li] : (const void *)dm->pack[(size_t)li],
-                                         dm->b[(size_t)li], nxt, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
+                                         dm->b_host[(size_t)li].data(), nxt, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
                                          ctx->num_sms, ctx->stream,
                                          ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
                                          fused_here ? dm->last_w_t.data() : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
@@ -490,7 +492,7 @@ int w2x_band_step(w2x_band *band, int step) {
         {
             LayerTimer t(ctx, step);
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)step] : (const void *)dm->pack[(size_t)step],
-                                         dm->b[(size_t)step], out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
+                                         dm->b_host[(size_t)step].data(), out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
                                          ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t.data() : nullptr,
                                          fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr));
         }
@@ -849,7 +851,7 @@ int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, con
         {
             LayerTimer t(ctx, layer);
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)layer] : (const void *)dm->pack[(size_t)layer],
-                                         dm->b[(size_t)layer], fout, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)layer], f8,
+                                         dm->b_host[(size_t)layer].data(), fout, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)layer], f8,
                                          ctx->num_sms, ctx->stream, nullptr, nullptr, nullptr, f8 ? &map8 : nullptr));
         }
         CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream, f8));

@@ -38,6 +38,7 @@ cudaError_t init_kernels();
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
                          const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0);
 // tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
+// `bias` is a HOST pointer to the layer's (float)bias values (they travel as kernel parameters).
 // f8 = 0: "f16x3" frames [hi][lo] + wpack = TcPack::bytes; f8 = 1: frames [xh][xh8][xl8], wpack = TcPack::bytes8 and
 // tmap_in8 describing the two e4m3 planes (see make_act_tensor_maps_f8).
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out,

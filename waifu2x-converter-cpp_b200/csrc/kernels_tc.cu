@@ -265,7 +265,7 @@ constexpr int NUM_THREADS = 12 * 32;
 
 struct TcParams {
     const uint16_t *wpack;   // [chunk][tap][kblock][hi|lo][COUT rows x 64 B], pre-swizzled (see model.cpp)
-    const float *bias;       // [COUT] (float)bias
+    float bias[128];         // [COUT] (float)bias, by value (constant bank, see last_w)
     __half *out;             // [2][Hp][Wp][COUT]
     int Wp, Hp;
     int tiles_x, n_tilesets;
@@ -399,8 +399,6 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(8 + C::NB + i); };
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NB);   // 4 bytes: TMEM base address
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));   // COUT floats
-    for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
@@ -630,7 +628,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                    const float v = fmaf(act[i], p.out_scale, s_bias[cb * 32 + i]);
+                    const float v = fmaf(act[i], p.out_scale, p.bias[cb * 32 + i]);
                     act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
                 }
                 if constexpr (!FUSE) {
@@ -763,8 +761,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(8 + C::NBP + i); };
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NBP);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float *s_bias = reinterpret_cast<float *>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < COUT; i += NUM_THREADS) s_bias[i] = p.bias[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
@@ -978,7 +974,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        const float v = fmaf(__uint_as_float(r[i]), p.out_scale, s_bias[cb * 32 + i]);
+                        const float v = fmaf(__uint_as_float(r[i]), p.out_scale, p.bias[cb * 32 + i]);
                         act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
                     }
                 }
@@ -1297,7 +1293,7 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
                             unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8, int pair) {
     TcParams p;
     p.wpack = reinterpret_cast<const uint16_t *>(wpack);
-    p.bias = bias;
+    for (int i = 0; i < cout; i++) p.bias[i] = bias[i];      // HOST pointer
     p.out = out;
     p.Wp = pw;
     p.Hp = ph;
