@@ -205,6 +205,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 // Per-layer configuration
 // ================================================================================================
+// Epilogue store staging per warp: 2 KB (two shared-memory round trips per 32 channels) or, for the 128-wide layers whose
+// epilogue is the critical path once the MMAs are fast, 4 KB (one round trip).
+__host__ __device__ constexpr bool stage_wide(int cout) { return cout == 128; }
+
 // F8 = false: three kind::f16 products xh*wh + xl*wh + xh*wl ("f16x3").
 // F8 = true : xh*wh in kind::f16, the two correction products in kind::f8f6f4 on e4m3 copies
 //             xl8*wh8 + xh8*wl8 (K = 32 per MMA at twice the rate: 2.0 instead of 3.0 pass-equivalents).
@@ -248,7 +252,8 @@ struct Cfg {
     // ---- shared memory map: [A slots][B stages][barriers + bias (1 KB)][last-layer weights][store staging] ----
     static constexpr int BAR_BYTES = 1024;
     static constexpr int W6_BYTES = 0;                                       // (the fused last layer's weights travel as kernel parameters)
-    static constexpr int STG_BYTES = FUSE ? 0 : 8 * 2048;                    // epilogue store staging, 2 KB per epilogue warp
+    static constexpr int STG_WARP = stage_wide(COUT) ? 4096 : 2048;
+    static constexpr int STG_BYTES = FUSE ? 0 : 8 * STG_WARP;               // epilogue store staging per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
     static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
@@ -300,80 +305,70 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 template <int COUT, bool F8>
 __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const TcParams &p, uint32_t stg, int lane, int q, int j,
                                                  int tx, int ty, int cb) {
+    // Two 64-byte groups per pixel: g0 = the fp16 plane (hi / xh), g1 = the fp16 lo plane, or [xh8 32 B | xl8 32 B].
+    constexpr bool WIDE = stage_wide(COUT);            // 4 KB of staging per warp: both groups in ONE shared-memory round trip
     const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
-    if constexpr (F8) {
-        // planes: xh = fp16(x16) | xh8 = e4m3(xh * 2^-F8_C) | xl8 = e4m3((x16 - xh) * 2^F8_A)
-        uint32_t hi[16], b8[16];       // b8[0..7] = xh8 (32 bytes), b8[8..15] = xl8 (32 bytes)
-        constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+    uint32_t g0[16], g1[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
-            __half2 h = __floats2half2_rn(v0, v1);
-            float2 hf = __half22float2(h);
-            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+    for (int i = 0; i < 16; i++) {
+        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+        __half2 h = __floats2half2_rn(v0, v1);
+        float2 hf = __half22float2(h);
+        g0[i] = *reinterpret_cast<uint32_t *>(&h);
+        if constexpr (F8) {
+            // xh8 = e4m3(xh * 2^-F8_C) in g1[0..7], xl8 = e4m3((x16 - xh) * 2^F8_A) in g1[8..15]
+            constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
             const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
             const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
-            if (i & 1) { b8[i >> 1] |= h8 << 16; b8[8 + (i >> 1)] |= l8 << 16; }
-            else { b8[i >> 1] = h8; b8[8 + (i >> 1)] = l8; }
-        }
-        const size_t pix_elems = (size_t)p.Hp * p.Wp * COUT;
-        uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
-#pragma unroll
-        for (int grp = 0; grp < 2; grp++) {       // grp 0: the fp16 plane (64 B per pixel), grp 1: both e4m3 planes (32 + 32 B)
-            const uint32_t *src = grp ? b8 : hi;
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-                if (gy < p.Hp && gx < p.Wp) {
-                    const size_t pix = (size_t)gy * p.Wp + gx;
-                    uint8_t *dst = grp == 0 ? base + (pix * COUT + cb * 32) * 2 + ch * 16
-                                            : base + (size_t)(2 + (ch >> 1)) * pix_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
-                    *reinterpret_cast<uint4 *>(dst) = val;
-                }
-            }
-            __syncwarp();
-        }
-    } else {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
-            __half2 h = __floats2half2_rn(v0, v1);
-            float2 hf = __half22float2(h);
+            if (i & 1) { g1[i >> 1] |= h8 << 16; g1[8 + (i >> 1)] |= l8 << 16; }
+            else { g1[i >> 1] = h8; g1[8 + (i >> 1)] = l8; }
+        } else {
             __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-            hi[i] = *reinterpret_cast<uint32_t *>(&h);
-            lo[i] = *reinterpret_cast<uint32_t *>(&l);
+            g1[i] = *reinterpret_cast<uint32_t *>(&l);
         }
-        // Each thread holds 64 B (32 channels) of ONE pixel per plane; stored directly that is 32 lanes x 16 B
-        // at a Cout*2-byte stride.  Transpose through a 2 KB per-warp staging tile (XOR-swizzled 16-byte
-        // units, conflict-free both ways) so that every store instruction writes 8 pixels x 64 B.
+    }
+    uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
+    // Each thread holds 64 B per group of ONE pixel; stored directly that is 32 lanes x 16 B at a Cout*2-byte stride.
+    // Transpose through the warp's staging tile (2 KB per group, XOR-swizzled 16-byte units, conflict-free both ways)
+    // so that every store instruction writes 8 pixels x 64 B.
+    auto put = [&](const uint32_t *src, uint32_t tile) {
 #pragma unroll
-        for (int plane = 0; plane < 2; plane++) {
-            const uint32_t *src = plane ? lo : hi;
+        for (int v = 0; v < 4; v++)
+            sts128(tile + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
+                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
+    };
+    auto get = [&](int grp, uint32_t tile) {
 #pragma unroll
-            for (int v = 0; v < 4; v++)
-                sts128(stg + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                       make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-                const uint4 val = lds128(stg + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-                const int gy = ty * REGION + 4 * (int)q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-                if (gy < p.Hp && gx < p.Wp) {
-                    __half *dst = p.out + (plane ? plane_elems : 0) + ((size_t)gy * p.Wp + gx) * COUT + cb * 32 + ch * 8;
-                    *reinterpret_cast<uint4 *>(dst) = val;
-                }
+        for (int k = 0; k < 4; k++) {
+            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
+            const uint4 val = lds128(tile + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
+            const int gy = ty * REGION + 4 * q + k, gx = tx * REGION + 8 * j + (lane >> 2);
+            if (gy < p.Hp && gx < p.Wp) {
+                const size_t pix = (size_t)gy * p.Wp + gx;
+                uint8_t *dst;
+                if (grp == 0) dst = base + (pix * COUT + cb * 32) * 2 + ch * 16;
+                else if constexpr (F8) dst = base + (size_t)(2 + (ch >> 1)) * plane_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
+                else dst = base + (plane_elems + pix * COUT + cb * 32) * 2 + ch * 16;
+                *reinterpret_cast<uint4 *>(dst) = val;
             }
-            __syncwarp();
         }
+    };
+    if constexpr (WIDE) {
+        put(g0, stg);
+        put(g1, stg + 2048u);
+        __syncwarp();
+        get(0, stg);
+        get(1, stg + 2048u);
+        __syncwarp();
+    } else {
+        put(g0, stg);
+        __syncwarp();
+        get(0, stg);
+        __syncwarp();
+        put(g1, stg);
+        __syncwarp();
+        get(1, stg);
+        __syncwarp();
     }
 }
 
@@ -592,7 +587,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         const uint32_t row = q * 32u + (uint32_t)lane;   // GEMM row = pixel inside the 8x16 M-tile
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
         const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
-        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q) * 2048u;   // this warp's staging tile
+        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q) * (uint32_t)C::STG_WARP;   // this warp's staging tile
         uint32_t n = 0;
         unsigned long long w_e = 0, work_e = 0;
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
@@ -949,7 +944,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         const int j = warp >= 8 ? 1 : 0;
         const uint32_t row = q4 * 32u + (uint32_t)lane;
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
-        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q4) * 2048u;
+        const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q4) * (uint32_t)C::STG_WARP;
         uint32_t n = 0;
         unsigned long long w_e = 0, work_e = 0;
         for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
