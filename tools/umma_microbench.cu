@@ -35,8 +35,12 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 
 // ISSUERS threads (one per warp 0..ISSUERS-1) each issue `iters` MMAs; rows of A: 128 x 128 B (SWIZZLE_128B, 64 fp16),
 // B: N rows x 64 B (SWIZZLE_64B).  The K=16/32 slice is rotated through the row so consecutive MMAs read different bytes.
+// Halo mode (rowb > 0) replays the conv kernel's operand addressing: A is one 18x18-pixel box with rowb bytes per pixel
+// (swizzle span = rowb), an M=128 tile is 16 image rows of 8 pixels (SBO = 18*rowb), the nine taps are start-address
+// offsets (ky*18 + kx)*rowb, and a row holds `nslice` 32-byte K slices.  rowb = 0: dense 128-byte rows, aligned atoms.
 template <int CG, int N, int ISSUERS, bool F8>
-__global__ void __launch_bounds__(128, 1) bench_kernel(int iters, unsigned long long *out) {
+__global__ void __launch_bounds__(128, 1) bench_kernel(int iters, unsigned long long *out, uint32_t rowb, uint32_t nslice, uint32_t a_lay, uint32_t b_lay,
+                                                       uint32_t b_rowb) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = base, b_base = base + 4 * 16384, bar = b_base + 65536, slot = bar + 64;
@@ -66,16 +70,21 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int iters, unsigned long 
     const uint32_t tmem = *slot_ptr;
     long long t0 = 0, t1 = 0;
     if (warp < ISSUERS && lane == 0 && rank == 0) {
-        constexpr uint32_t A_HI = (uint32_t)(desc_const(1024, 2) >> 32);    // SWIZZLE_128B, dense 8-row groups
-        constexpr uint32_t B_HI = (uint32_t)(desc_const(512, 4) >> 32);     // SWIZZLE_64B
-        const uint32_t a0 = (((a_base + warp * 16384) >> 4) & 0x3FFF) | (1u << 16);
+        const uint32_t A_HI = (uint32_t)(desc_const(rowb ? 18u * rowb : (a_lay == 2 ? 1024u : a_lay == 4 ? 512u : 256u), a_lay) >> 32);
+        const uint32_t B_HI = (uint32_t)(desc_const(8u * b_rowb, b_lay) >> 32);
+        const uint32_t a0 = (((a_base + (rowb ? (uint32_t)warp * 8u * rowb : (uint32_t)warp * 16384u)) >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t b0 = ((b_base >> 4) & 0x3FFF) | (1u << 16);
         const uint32_t d = tmem + (uint32_t)warp * 256u;                    // private accumulator columns
-        const uint32_t id = idesc(CG == 2 ? 256 : 128, N);
+        const uint32_t id = idesc(CG == 2 ? 256 : 128, N) | (F8 ? 0u : 0u);
+        uint32_t tap = 0, sl = 0;
         t0 = clock64();
         for (int i = 0; i < iters; i++) {
-            const uint32_t k = (uint32_t)(i & 1) * 2u;
-            mma<CG, F8>(d, ((uint64_t)A_HI << 32) | (a0 + k), ((uint64_t)B_HI << 32) | (b0 + k), id);
+            const uint32_t off = rowb ? ((tap / 3u) * 18u + (tap % 3u)) * rowb : 0u;
+            mma<CG, F8>(d, ((uint64_t)A_HI << 32) | (a0 + ((off + sl * 32u) >> 4)), ((uint64_t)B_HI << 32) | (b0 + ((sl * 32u) % b_rowb >> 4)), id);
+            if (++sl == nslice) {
+                sl = 0;
+                if (++tap == 9u) tap = 0;
+            }
         }
         if constexpr (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
         else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(int iters, unsigned long 
 }
 
 template <int CG, int N, int ISSUERS, bool F8>
-static void run(const char *name, int grid) {
+static void run(const char *name, int grid, uint32_t rowb = 0, uint32_t nslice = 2, uint32_t a_lay = 2, uint32_t b_lay = 4, uint32_t b_rowb = 64) {
     const int smem = 1024 + 4 * 16384 + 65536 + 256, iters = 4096;
     cudaFuncSetAttribute(bench_kernel<CG, N, ISSUERS, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     unsigned long long *d, h[2] = {0, 0};
@@ -111,7 +120,7 @@ static void run(const char *name, int grid) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     for (int rep = 0; rep < 2; rep++) {
-        cudaError_t e = cudaLaunchKernelEx(&cfg, bench_kernel<CG, N, ISSUERS, F8>, iters, d);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, bench_kernel<CG, N, ISSUERS, F8>, iters, d, rowb, nslice, a_lay, b_lay, b_rowb);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             std::printf("%-44s  ERROR %s\n", name, cudaGetErrorString(e));
@@ -144,5 +153,20 @@ int main() {
         run<2, 256, 2, false>("cta_group::2 M256 N256 f16  2 issuers", grid);
         run<2, 128, 2, true>("cta_group::2 M256 N128 e4m3 2 issuers", grid);
     }
+    // the conv kernel's operand addressing (one halo box, taps = start offsets), 2 issuers, full grid
+    std::printf("halo-box operand addressing (A = 18x18 px box, SBO = 18*rowb, tap offsets), 2 issuers\n");
+    run<1, 32, 2, false>("halo f16  rowb 64  SW64  N32  (L1 main)", sms, 64, 2, 4, 4, 64);
+    run<1, 64, 2, false>("halo f16  rowb 64  SW64  N64  (L2 main)", sms, 64, 2, 4, 4, 64);
+    run<1, 64, 2, false>("halo f16  rowb 128 SW128 N64  (L3 main)", sms, 128, 4, 2, 4, 64);
+    run<1, 128, 2, false>("halo f16  rowb 128 SW128 N128 (L4 main)", sms, 128, 4, 2, 4, 64);
+    run<1, 32, 2, true>("halo e4m3 rowb 32  SW32  N32  (L1 corr)", sms, 32, 1, 6, 6, 32);
+    run<1, 64, 2, true>("halo e4m3 rowb 32  SW32  N64  (L2 corr)", sms, 32, 1, 6, 6, 32);
+    run<1, 64, 2, true>("halo e4m3 rowb 64  SW64  N64  (L3 corr)", sms, 64, 2, 4, 6, 32);
+    run<1, 128, 2, true>("halo e4m3 rowb 64  SW64  N128 (L4 corr)", sms, 64, 2, 4, 6, 32);
+    run<1, 128, 2, true>("halo e4m3 rowb 128 SW128 N128 (L5 corr)", sms, 128, 4, 2, 6, 32);
+    run<1, 32, 2, false>("dense f16 SW128 N32", sms);
+    run<1, 64, 2, false>("dense f16 SW128 N64", sms);
+    run<1, 32, 1, false>("dense f16 SW128 N32 1 issuer", sms);
+    run<1, 64, 2, false>("dense f16 rowb-64-like: SW64 aligned atoms N64", sms, 0, 2, 4, 4, 64);
     return 0;
 }

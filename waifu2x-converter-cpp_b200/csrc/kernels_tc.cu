@@ -46,8 +46,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// Producer-side helpers are called by a whole converged warp; ONE elected lane executes the instruction (elect.sync inside
+// the asm block).  For the TMA / tcgen05 instructions this is what lets ptxas keep their operands in uniform registers.
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -98,13 +100,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 // bulk (1-D) copy global -> shared, completion on an mbarrier
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
@@ -122,22 +124,24 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
 }
-// All tcgen05.mma wrappers take an `issue` flag and predicate the instruction inside the asm block instead of
-// sitting under a divergent `if (lane == 0)`: with uniform control flow ptxas keeps the descriptors in uniform
-// registers, without a per-MMA R2UR waterfall (the issue loop is on the tensor pipe's critical path).
+// The issuing WARP walks the MMA loop converged; each tcgen05.mma / commit is predicated by an elect.sync inside its asm
+// block.  Together with a shuffle-derived (provably uniform) warp index and TMEM base this lets ptxas keep every
+// descriptor in uniform registers and emit back-to-back UTC*MMA -- a lane predicate or a thread-derived operand
+// costs an ELECT / R2UR / BRA.U.ANY waterfall of ~20 dependent instructions per MMA (measured ~140 cycles per MMA per
+// issuer: that, not the tensor pipe, was what bounded the narrow layers).
 #define W2X_UMMA_VARIANT(NAME, OPCODE)                                                                        \
     __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,      \
-                                         uint32_t accum, uint32_t issue) {                                     \
-        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q " OPCODE      \
+                                         uint32_t accum) {                                                     \
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t@q " OPCODE \
                      " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),                                                \
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(issue)                                \
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)                                            \
                      : "memory");                                                                              \
     }
 W2X_UMMA_VARIANT(umma_f16, "tcgen05.mma.cta_group::1.kind::f16")
 W2X_UMMA_VARIANT(umma_f8, "tcgen05.mma.cta_group::1.kind::f8f6f4")   // e4m3 x e4m3 -> f32, K = 32 per instruction, twice the f16 rate
 #undef W2X_UMMA_VARIANT
-__device__ __forceinline__ void umma_commit_if(uint32_t bar, uint32_t issue) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(issue) : "memory");
+__device__ __forceinline__ void umma_commit_one(uint32_t bar) {   // whole (converged) warp calls, one elected lane commits
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 
 // arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
@@ -158,6 +162,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also names the destination registers of the load it waits for, so the compiler cannot move their first
+// use above the wait when another tcgen05.ld has already been issued in between (software-pipelined epilogue)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -274,7 +289,7 @@ struct TcParams {
     __half *out;             // [2][Hp][Wp][COUT]
     int Wp, Hp;
     int tiles_x, n_tilesets;
-    float out_scale;         // 1 / (wscale * ACT_SCALE)
+    float out_scale;         // 1 / wscale  (accumulator -> ACT_SCALE * conv)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
@@ -302,7 +317,7 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 // block of M-tile j): conversion to the frame's planes and transposed, coalesced stores through the warp's 2 KB
 // staging tile `stg` (XOR-swizzled 16-byte units, conflict-free both ways): every store instruction then writes
 // 8 pixels x 64 B instead of 32 lanes x 16 B at a Cout*2-byte stride.
-template <int COUT, bool F8>
+template <int COUT, bool F8, bool DIRECT8 = true>
 __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const TcParams &p, uint32_t stg, int lane, int q, int j,
                                                  int tx, int ty, int cb) {
     // Two 64-byte groups per pixel: g0 = the fp16 plane (hi / xh), g1 = the fp16 lo plane, or [xh8 32 B | xl8 32 B].
@@ -311,14 +326,15 @@ __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const T
     uint32_t g0[16], g1[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const float v0 = act[2 * i] * ACT_SCALE, v1 = act[2 * i + 1] * ACT_SCALE;
+        const float v0 = act[2 * i], v1 = act[2 * i + 1];      // already x ACT_SCALE (folded into out_scale / bias)
         __half2 h = __floats2half2_rn(v0, v1);
         float2 hf = __half22float2(h);
         g0[i] = *reinterpret_cast<uint32_t *>(&h);
         if constexpr (F8) {
             // xh8 = e4m3(xh * 2^-F8_C) in g1[0..7], xl8 = e4m3((x16 - xh) * 2^F8_A) in g1[8..15]
             constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
-            const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+            const __half2 hd = __hmul2(h, __float2half2_rn(kDown));        // exact (power of two), one op for both channels
+            const uint32_t h8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hd), __NV_SATFINITE, __NV_E4M3);
             const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
             if (i & 1) { g1[i >> 1] |= h8 << 16; g1[8 + (i >> 1)] |= l8 << 16; }
             else { g1[i >> 1] = h8; g1[8 + (i >> 1)] = l8; }
@@ -360,9 +376,11 @@ __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const T
         get(0, stg);
         get(1, stg + 2048u);
         __syncwarp();
-    } else if constexpr (F8) {
+    } else if constexpr (F8 && DIRECT8) {
         // The e4m3 planes go out directly: a thread's 32 B per plane is exactly one sector, so nothing is wasted in DRAM
         // and the shared-memory pipe (saturated by the tensor core's operand fetches) sees half as many staging operations.
+        // Worth it where the layer is MMA-bound (measured: L5 7.0 -> 6.8 ms); the epilogue-bound 64->128 layer keeps
+        // the staged path (DIRECT8 = false), where the extra store instructions cost more than the staging did.
         const int oy = (q * 32 + lane) >> 3, ox = lane & 7;
         const int gy = ty * REGION + oy, gx = tx * REGION + 8 * j + ox;
         put(g0, stg);
@@ -413,7 +431,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NB);   // 4 bytes: TMEM base address
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, and with it the role branch, the M-tile index and
+    // every descriptor derived from them (uniform registers feed tcgen05.mma directly, no per-MMA R2UR waterfall)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
     unsigned long long *prof = prof_on ? p.prof + (size_t)blockIdx.x * PROF_N : nullptr;
 
@@ -442,11 +462,12 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler as well
 
     if (warp == 0) {
         // ===================== A producer: one halo'd box per (tile-set, chunk, hi|lo) ==============
-        if (lane == 0) {
+        // (whole warp walks the loop; the arrive and the TMA instructions elect one lane)
+        {
             uint32_t it = 0;
             unsigned long long w_a = 0;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
@@ -466,11 +487,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     }
                 }
             }
-            if (prof_on) prof[PROF_APROD_WAIT] += w_a;
+            if (prof_on && lane == 0) prof[PROF_APROD_WAIT] += w_a;
         }
     } else if (warp == 2) {
         // ===================== B producer: stream the packed weights in consumption order ============
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0;
             unsigned long long w_b = 0;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
@@ -482,7 +503,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
                 }
             }
-            if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
+            if (prof_on && lane == 0) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1 || warp == 7) {
         // ===================== MMA issuers (warp 1: M-tile 0, warp 7: M-tile 1) ========================
@@ -514,7 +535,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             b_ready = mbar_test(b_full(ns), np);      // consumed at the next acquire_b
         };
         auto release_b = [&]() {
-            umma_commit_if(b_empty(stage), leader);
+            umma_commit_one(b_empty(stage));
             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
         };
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
@@ -544,42 +565,42 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                         if constexpr (C::MERGE) {
                             // one stage = [wh fp16 | wh8 | wl8]: main product (two K=16 steps) + both e4m3 corrections (K=32 each)
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u, leader);
-                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
+                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u);
+                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u);
                             release_b();
                         } else if constexpr (F8) {
                             // ---- stage 1: wh (fp16): the main product xh*wh, two K=16 steps ----
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
                             release_b();
                             // ---- stage 2: [wh8 | wl8] (e4m3): corrections xl8*wh8 and xh8*wl8, one K=32 step each ----
                             acquire_b(b0);
-                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u, leader);
-                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 32u >> 4)), idesc_c, 1u, leader);
+                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u);
+                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 32u >> 4)), idesc_c, 1u);
                             release_b();
                         } else if constexpr (C::STACK) {
                             // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_2c, acc0, leader);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_2c, 1u, leader);
-                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
-                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_2c, acc0);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_2c, 1u);
+                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u);
+                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
                             release_b();
                         } else {
                             // ---- hi weights: xh*wh and xl*wh ----
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
-                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
+                            umma_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u);
+                            umma_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
                             release_b();
                             // ---- lo weights: xh*wl ----
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u, leader);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
+                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, 1u);
+                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
                             release_b();
                         }
                     }
@@ -587,9 +608,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                     tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
                 }
-                umma_commit_if(a_empty(slot), leader);   // the staged boxes may be overwritten once these MMAs retire
+                umma_commit_one(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
             }
-            umma_commit_if(acc_full(set), leader);       // this issuer's accumulators of the tile-set are final
+            umma_commit_one(acc_full(set));       // this issuer's accumulators of the tile-set are final
         }
         if (prof_on && leader && jt == 0) {
             prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
@@ -620,32 +641,33 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             float pt[9];                                   // FUSE: nine per-tap dot products of this pixel
 #pragma unroll
             for (int t = 0; t < 9; t++) pt[t] = 0.f;
+            uint32_t r[32];
+            if constexpr (!C::STACK) tmem_ld32(tcol, r);
 #pragma unroll
             for (int cb = 0; cb < COUT / 32; cb++) {
                 // ---- 32 output channels of this pixel: accumulator -> scale, bias, leaky-ReLU ----
                 float act[32];
-                {
-                    uint32_t r[32];
+                if constexpr (C::STACK) {
+                    uint32_t r2[32];
                     tmem_ld32(tcol + (uint32_t)cb * 32u, r);
-                    if constexpr (C::STACK) {
-                        uint32_t r2[32];
-                        tmem_ld32(tcol + (uint32_t)(COUT + cb * 32), r2);
-                        tmem_ld_wait();
+                    tmem_ld32(tcol + (uint32_t)(COUT + cb * 32), r2);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-                    } else {
-                        tmem_ld_wait();
+                    for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+                } else {
+                    tmem_ld_wait_dep(r);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]);
-                    }
+                    for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]);
+                    // the next 32 columns travel from TMEM while this block is converted and stored
+                    if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
-                    const float v = fmaf(act[i], p.out_scale, p.bias[cb * 32 + i]);
-                    act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
+                    const float v = fmaf(act[i], p.out_scale, p.bias[cb * 32 + i]);     // = ACT_SCALE * (conv + bias)
+                    act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
                 }
                 if constexpr (!FUSE) {
-                    epilogue_store32<COUT, F8>(act, p, stg, lane, (int)q, j, tx, ty, cb);
+                    epilogue_store32<COUT, F8, !(CIN == 64 && COUT == 128)>(act, p, stg, lane, (int)q, j, tx, ty, cb);
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll
@@ -711,13 +733,13 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
 }
 __device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
 }
@@ -726,20 +748,20 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
 }
 #define W2X_UMMA2_VARIANT(NAME, OPCODE)                                                                       \
     __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,      \
-                                         uint32_t accum, uint32_t issue) {                                     \
-        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t@q " OPCODE      \
+                                         uint32_t accum) {                                                     \
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t@q " OPCODE \
                      " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),                                                \
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(issue)                                \
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)                                            \
                      : "memory");                                                                              \
     }
 W2X_UMMA2_VARIANT(umma2_f16, "tcgen05.mma.cta_group::2.kind::f16")
 W2X_UMMA2_VARIANT(umma2_f8, "tcgen05.mma.cta_group::2.kind::f8f6f4")
 #undef W2X_UMMA2_VARIANT
-__device__ __forceinline__ void umma2_commit_if(uint32_t bar, uint32_t issue) {   // arrives on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_one(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair; one elected lane commits
     asm volatile(
-        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}" ::"r"(bar),
-        "r"(issue), "h"((uint16_t)3)
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+        "h"((uint16_t)3)
         : "memory");
 }
 
@@ -775,7 +797,9 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NBP);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: ptxas then knows it is warp-uniform, and with it the role branch, the M-tile index and
+    // every descriptor derived from them (uniform registers feed tcgen05.mma directly, no per-MMA R2UR waterfall)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const bool prof_on = p.prof != nullptr;
     unsigned long long *prof = prof_on ? p.prof + (size_t)blockIdx.x * PROF_N : nullptr;
     const uint32_t rank = cluster_ctarank();
@@ -811,7 +835,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler as well
     // this CTA's tile-set of pair-set q (a phantom region below the frame when the count is odd: loads zero-fill, stores are masked)
     auto region_of = [&](int q, int &tx, int &ty) {
         const int ts = 2 * q + (int)rank;
@@ -821,7 +845,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
 
     if (warp == 0) {
         // ===================== A producer (both CTAs): boxes land locally, completion is counted on the LEADER's barrier ====
-        if (lane == 0) {
+        {
             uint32_t it = 0;
             unsigned long long w_a = 0;
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
@@ -843,13 +867,13 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     }
                 }
             }
-            if (prof_on) prof[PROF_APROD_WAIT] += w_a;
+            if (prof_on && lane == 0) prof[PROF_APROD_WAIT] += w_a;
         }
     } else if (warp == 2) {
         // ===================== B producer (both CTAs): this CTA's 64 rows of every weight stage ========================
         // tmap_w views the packed stream as rows of 64 bytes, box = 32 rows (2 KB).  A 128-row fp16 block is 8 KB
         // (this CTA's half: 4 KB at +rank*4 KB); an e4m3 stage is [wh8 4 KB | wl8 4 KB] (halves: 2 KB at +rank*2 KB each).
-        if (lane == 0) {
+        {
             uint32_t stage = 0, phase = 0;
             unsigned long long w_b = 0;
             constexpr int N_STEPS = C::NCHUNK * 9 * C::KBLOCKS;                // one stage per (chunk, tap, 32-channel block)
@@ -873,7 +897,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
                 }
             }
-            if (prof_on) prof[PROF_BPROD_WAIT] += w_b;
+            if (prof_on && lane == 0) prof[PROF_BPROD_WAIT] += w_b;
         }
     } else if (warp == 1 || warp == 7) {
         // ===================== MMA issuers: LEADER CTA only, M = 256 across the pair ====================================
@@ -901,7 +925,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                 b_ready = mbar_test(b_full(ns), np);
             };
             auto release_b = [&]() {
-                umma2_commit_if(b_empty(stage), leader);
+                umma2_commit_one(b_empty(stage));
                 if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
             };
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl, n++) {
@@ -927,26 +951,26 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                             uint32_t b0;
                             acquire_b(b0);                  // one stage per 32-channel step: this CTA's rows of both blocks
                             if constexpr (F8) {
-                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u, leader);
-                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
+                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u);
+                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u);
                             } else {
-                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0, leader);
-                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma2_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u, leader);
-                                umma2_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u, leader);
-                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0 + (4096u >> 4)), idesc_c, 1u, leader);
-                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + (4096u >> 4) + 2u), idesc_c, 1u, leader);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
+                                umma2_f16(dj, desc(A_HI32, al), desc(B_HI32, b0), idesc_c, 1u);
+                                umma2_f16(dj, desc(A_HI32, al + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
+                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0 + (4096u >> 4)), idesc_c, 1u);
+                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + (4096u >> 4) + 2u), idesc_c, 1u);
                             }
                             release_b();
                         }
                         tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
                         tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
                     }
-                    umma2_commit_if(a_empty(slot), leader);
+                    umma2_commit_one(a_empty(slot));
                 }
-                umma2_commit_if(acc_full(set), leader);
+                umma2_commit_one(acc_full(set));
             }
             if (prof_on && leader && jt == 0) {
                 prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
@@ -978,19 +1002,19 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             float pt[9];
 #pragma unroll
             for (int t = 0; t < 9; t++) pt[t] = 0.f;
+            uint32_t r[32];
+            tmem_ld32(tcol, r);
 #pragma unroll
             for (int cb = 0; cb < COUT / 32; cb++) {
                 float act[32];
-                {
-                    uint32_t r[32];
-                    tmem_ld32(tcol + (uint32_t)cb * 32u, r);
-                    tmem_ld_wait();
+                tmem_ld_wait_dep(r);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const float v = fmaf(__uint_as_float(r[i]), p.out_scale, p.bias[cb * 32 + i]);
-                        act[i] = fminf(v, 0.f) * 0.1f + fmaxf(v, 0.f);
-                    }
+                for (int i = 0; i < 32; i++) {
+                    const float v = fmaf(__uint_as_float(r[i]), p.out_scale, p.bias[cb * 32 + i]);   // = ACT_SCALE * (conv + bias)
+                    act[i] = fmaxf(v, 0.1f * v);                                                       // leaky 0.1
                 }
+                // the next 32 columns travel from TMEM while this block is converted and stored
+                if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
                 if constexpr (FUSE) {
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
@@ -1004,7 +1028,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                         }
                     }
                 } else {
-                    epilogue_store32<COUT, F8>(act, p, stg, lane, (int)q4, j, tx, ty, cb);
+                    epilogue_store32<COUT, F8, !(CIN == 64 && COUT == 128)>(act, p, stg, lane, (int)q4, j, tx, ty, cb);
                 }
             }
             if constexpr (FUSE) {
@@ -1306,18 +1330,20 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
                             unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8, int pair) {
     TcParams p;
     p.wpack = reinterpret_cast<const uint16_t *>(wpack);
-    for (int i = 0; i < cout; i++) p.bias[i] = bias[i];      // HOST pointer
+    // ACT_SCALE (a power of two) is folded into the epilogue's affine step: leaky(16 v) = 16 leaky(v) exactly, so the
+    // kernel produces the frame's x16 values without a separate multiply; the fused last layer gets weights / 16.
+    for (int i = 0; i < cout; i++) p.bias[i] = bias[i] * ACT_SCALE;      // HOST pointer
     p.out = out;
     p.Wp = pw;
     p.Hp = ph;
     p.tiles_x = (pw + REGION - 1) / REGION;
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
-    p.out_scale = out_scale;
+    p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
     p.partial = partial;
     if (partial) {
         if (!last_w) return cudaErrorInvalidValue;
-        for (int i = 0; i < 9 * cout; i++) p.last_w[i] = last_w[i];      // HOST pointer: [9][cout]
+        for (int i = 0; i < 9 * cout; i++) p.last_w[i] = last_w[i] * (1.0f / ACT_SCALE);      // HOST pointer: [9][cout]
     }
     if (f8 && !tmap_in8) return cudaErrorInvalidValue;
     const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
