@@ -100,7 +100,7 @@ def test_tc_operand_pack_layout_and_split(w2x, oracle_models):
         data, nch, kbl, ws = m.debug_tc_pack(li)
         w = oracle_models["scale2.0x"].weights[li]
         co, ci = w.shape[:2]
-        kc_a = min(ci, 64)
+        kc_a = 32 if ci <= 64 else 64      # channels per staged activation box (tc::act_kc)
         assert nch == ci // kc_a and kbl == kc_a // 32 and ws == 2.0 ** np.floor(np.log2(1024.0 / np.abs(w).max()))
         data = data.view(np.float16).reshape(nch, 9, kbl, 2, co * 32)
         ws_w = (w * np.float32(ws)).astype(np.float32)

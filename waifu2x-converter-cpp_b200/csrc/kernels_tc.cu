@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 
 #include "kernels.h"
@@ -109,6 +110,23 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
+}
+// TMA store of one 4-D box shared -> global (bulk async-group completion); whole warp calls, one elected lane issues
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n\t}"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.commit_group;\n\t}" ::: "memory");
+}
+// the elected lane's earlier bulk stores have finished READING shared memory (the staging tile may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::: "memory");
+}
+// ... have completed (before the CTA exits)
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group 0;\n\t}" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -222,7 +240,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 // Epilogue store staging per warp: 2 KB (two shared-memory round trips per 32 channels) or 4 KB (one round trip).
 // (Measured on L4: 4 KB staging shortens the epilogue by only 4 % but costs two weight stages -> slower overall; kept off.)
-__host__ __device__ constexpr bool stage_wide(int cout) { return cout < 0; }
+// Channels per staged activation box: 32 for layers up to 64 inputs (two small boxes per tile-set instead of one 83 KB
+// one leave room for the store staging and a deep weight ring), 64 for the 128-input layers.
+__host__ __device__ constexpr int act_kc(int cin) { return cin <= 64 ? 32 : 64; }
 
 // F8 = false: three kind::f16 products xh*wh + xl*wh + xh*wl ("f16x3").
 // F8 = true : xh*wh in kind::f16, the two correction products in kind::f8f6f4 on e4m3 copies
@@ -233,7 +253,7 @@ constexpr int F8_A = 10, F8_C = 1;   // xl8 = e4m3((x16 - xh) * 2^F8_A), xh8 = e
 template <int CIN, int COUT, bool FUSE = false, bool F8 = false>
 struct Cfg {
     // ---- A operand (activations): one TMA box per (tile-set, 64-channel chunk, hi|lo) ----
-    static constexpr int KC = CIN < 64 ? CIN : 64;      // channels per activation chunk
+    static constexpr int KC = act_kc(CIN);              // channels per activation chunk
     static constexpr int NCHUNK = CIN / KC;
     static constexpr int ROWB = KC * 2;                 // bytes per pixel per chunk (= swizzle span)
     static constexpr uint32_t A_LAYOUT = ROWB == 128 ? 2u : 4u;                // SWIZZLE_128B : SWIZZLE_64B
@@ -267,7 +287,7 @@ struct Cfg {
     // ---- shared memory map: [A slots][B stages][barriers + bias (1 KB)][last-layer weights][store staging] ----
     static constexpr int BAR_BYTES = 1024;
     static constexpr int W6_BYTES = 0;                                       // (the fused last layer's weights travel as kernel parameters)
-    static constexpr int STG_WARP = stage_wide(COUT) ? 4096 : 2048;
+    static constexpr int STG_WARP = 4096;                                    // [fp16 plane 2 KB | lo plane 2 KB, or xh8 1 KB | xl8 1 KB] of 32 px x 32 ch
     static constexpr int STG_BYTES = FUSE ? 0 : 8 * STG_WARP;               // epilogue store staging per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
@@ -291,6 +311,7 @@ struct TcParams {
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / wscale  (accumulator -> ACT_SCALE * conv)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
+    int dbg;                    // W2X_DEBUG_EPI (timing experiments only, results are WRONG when set): 1 = no global stores, 2 = no staging either
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
     float *partial;             // nullptr = not fused
@@ -314,15 +335,16 @@ __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, bo
 }
 
 // Epilogue store of 32 activated output channels of ONE pixel per thread (lane = pixel inside this warp's 4x8 pixel
-// block of M-tile j): conversion to the frame's planes and transposed, coalesced stores through the warp's 2 KB
-// staging tile `stg` (XOR-swizzled 16-byte units, conflict-free both ways): every store instruction then writes
-// 8 pixels x 64 B instead of 32 lanes x 16 B at a Cout*2-byte stride.
-template <int COUT, bool F8, bool DIRECT8 = true>
-__device__ __forceinline__ void epilogue_store32(const float (&act)[32], const TcParams &p, uint32_t stg, int lane, int q, int j,
-                                                 int tx, int ty, int cb) {
-    // Two 64-byte groups per pixel: g0 = the fp16 plane (hi / xh), g1 = the fp16 lo plane, or [xh8 32 B | xl8 32 B].
-    constexpr bool WIDE = stage_wide(COUT);            // 4 KB of staging per warp: both groups in ONE shared-memory round trip
-    const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
+// block of an M-tile).  The warp converts to the frame's planes, writes them into its 4 KB staging tile in the TMA
+// swizzle pattern (conflict-free 16-byte stores) and one lane issues TMA stores of the 8x4-pixel boxes: the bytes leave
+// asynchronously while the warp converts the next 32 channels, the frame edge is clipped by the TMA unit, and the
+// shared-memory pipe (which the tensor core's operand fetches saturate) sees one pass instead of a store + load round trip.
+//   tile + 0    : fp16 plane (hi | xh), 32 px x 64 B, SWIZZLE_64B
+//   tile + 2048 : f16x3: lo plane, same shape (one store of a {32, 8, 4, 2} box covers both planes)
+//                 F8   : xh8 (32 px x 32 B) then xl8 at +1024, SWIZZLE_32B, one {32, 8, 4, 2} box of the e4m3 tensor
+template <int COUT, bool F8>
+__device__ __forceinline__ void epilogue_store32(const float (&act)[32], const CUtensorMap *tmo, const CUtensorMap *tmo8, int dbg, uint32_t stg,
+                                                 int lane, int gx0, int gy0, int cb) {
     uint32_t g0[16], g1[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -343,68 +365,36 @@ __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const T
             g1[i] = *reinterpret_cast<uint32_t *>(&l);
         }
     }
-    uint8_t *base = reinterpret_cast<uint8_t *>(p.out);
-    // Each thread holds 64 B per group of ONE pixel; stored directly that is 32 lanes x 16 B at a Cout*2-byte stride.
-    // Transpose through the warp's staging tile (2 KB per group, XOR-swizzled 16-byte units, conflict-free both ways)
-    // so that every store instruction writes 8 pixels x 64 B.
-    auto put = [&](const uint32_t *src, uint32_t tile) {
+    if (dbg & 2) {   // timing experiment: conversion only
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x ^= g0[i] ^ g1[i];
+        if (x == 0x7fc12345u) sts128(stg, make_uint4(x, x, x, x));
+        return;
+    }
+    bulk_wait_read();          // the previous boxes of this tile are on their way
+    __syncwarp();
+    const uint32_t sw64 = (uint32_t)((lane >> 1) & 3), sw32 = (uint32_t)((lane >> 2) & 1);
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+        sts128(stg + (uint32_t)lane * 64u + (((uint32_t)v ^ sw64) << 4), make_uint4(g0[4 * v], g0[4 * v + 1], g0[4 * v + 2], g0[4 * v + 3]));
+    if constexpr (F8) {
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            sts128(stg + 2048u + (uint32_t)lane * 32u + (((uint32_t)c ^ sw32) << 4), make_uint4(g1[4 * c], g1[4 * c + 1], g1[4 * c + 2], g1[4 * c + 3]));
+            sts128(stg + 3072u + (uint32_t)lane * 32u + (((uint32_t)c ^ sw32) << 4), make_uint4(g1[8 + 4 * c], g1[9 + 4 * c], g1[10 + 4 * c], g1[11 + 4 * c]));
+        }
+    } else {
 #pragma unroll
         for (int v = 0; v < 4; v++)
-            sts128(tile + (uint32_t)lane * 64u + (uint32_t)((v ^ ((lane >> 1) & 3)) << 4),
-                   make_uint4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]));
-    };
-    auto get = [&](int grp, uint32_t tile) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int P = (lane >> 2) + 8 * k, ch = lane & 3;
-            const uint4 val = lds128(tile + (uint32_t)P * 64u + (uint32_t)((ch ^ ((P >> 1) & 3)) << 4));
-            const int gy = ty * REGION + 4 * q + k, gx = tx * REGION + 8 * j + (lane >> 2);
-            if (gy < p.Hp && gx < p.Wp) {
-                const size_t pix = (size_t)gy * p.Wp + gx;
-                uint8_t *dst;
-                if (grp == 0) dst = base + (pix * COUT + cb * 32) * 2 + ch * 16;
-                else if constexpr (F8) dst = base + (size_t)(2 + (ch >> 1)) * plane_elems + pix * COUT + cb * 32 + (ch & 1) * 16;
-                else dst = base + (plane_elems + pix * COUT + cb * 32) * 2 + ch * 16;
-                *reinterpret_cast<uint4 *>(dst) = val;
-            }
-        }
-    };
-    if constexpr (WIDE) {
-        put(g0, stg);
-        put(g1, stg + 2048u);
-        __syncwarp();
-        get(0, stg);
-        get(1, stg + 2048u);
-        __syncwarp();
-    } else if constexpr (F8 && DIRECT8) {
-        // The e4m3 planes go out directly: a thread's 32 B per plane is exactly one sector, so nothing is wasted in DRAM
-        // and the shared-memory pipe (saturated by the tensor core's operand fetches) sees half as many staging operations.
-        // Worth it where the layer is MMA-bound (measured: L5 7.0 -> 6.8 ms); the epilogue-bound 64->128 layer keeps
-        // the staged path (DIRECT8 = false), where the extra store instructions cost more than the staging did.
-        const int oy = (q * 32 + lane) >> 3, ox = lane & 7;
-        const int gy = ty * REGION + oy, gx = tx * REGION + 8 * j + ox;
-        put(g0, stg);
-        if (gy < p.Hp && gx < p.Wp) {
-            const size_t pix = (size_t)gy * p.Wp + gx;
-            uint4 *d8h = reinterpret_cast<uint4 *>(base + 2 * plane_elems + pix * COUT + cb * 32);
-            uint4 *d8l = reinterpret_cast<uint4 *>(base + 3 * plane_elems + pix * COUT + cb * 32);
-            d8h[0] = make_uint4(g1[0], g1[1], g1[2], g1[3]);
-            d8h[1] = make_uint4(g1[4], g1[5], g1[6], g1[7]);
-            d8l[0] = make_uint4(g1[8], g1[9], g1[10], g1[11]);
-            d8l[1] = make_uint4(g1[12], g1[13], g1[14], g1[15]);
-        }
-        __syncwarp();
-        get(0, stg);
-        __syncwarp();
-    } else {
-        put(g0, stg);
-        __syncwarp();
-        get(0, stg);
-        __syncwarp();
-        put(g1, stg);
-        __syncwarp();
-        get(1, stg);
-        __syncwarp();
+            sts128(stg + 2048u + (uint32_t)lane * 64u + (((uint32_t)v ^ sw64) << 4), make_uint4(g1[4 * v], g1[4 * v + 1], g1[4 * v + 2], g1[4 * v + 3]));
+    }
+    fence_proxy_async();       // generic-proxy writes -> visible to the TMA unit
+    __syncwarp();
+    if (!(dbg & 1)) {
+        tma_store_4d(tmo, stg, cb * 32, gx0, gy0, 0);
+        if constexpr (F8) tma_store_4d(tmo8, stg + 2048u, cb * 32, gx0, gy0, 0);
+        bulk_commit();
     }
 }
 
@@ -413,7 +403,8 @@ __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const T
 // ================================================================================================
 template <int CIN, int COUT, bool FUSE, bool F8>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8, const TcParams p) {
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out8, const TcParams p) {
     using C = Cfg<CIN, COUT, FUSE, F8>;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: swizzle patterns repeat every 1024 B (SWIZZLE_128B) / 512 B (SWIZZLE_64B)
@@ -454,6 +445,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_in);
         if constexpr (F8) prefetch_tmap(&tmap_in8);
+        if constexpr (!FUSE) {
+            prefetch_tmap(&tmap_out);
+            if constexpr (F8) prefetch_tmap(&tmap_out8);
+        }
     }
     if (warp == 2) {
         tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -625,7 +620,6 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         const int j = warp >= 8 ? 1 : 0;                 // M-tile
         const uint32_t row = q * 32u + (uint32_t)lane;   // GEMM row = pixel inside the 8x16 M-tile
         const int oy = (int)(row >> 3), ox = (int)(row & 7u);
-        const size_t plane_elems = (size_t)p.Hp * p.Wp * COUT;
         const uint32_t stg = bar_base + C::BAR_BYTES + C::W6_BYTES + (uint32_t)(j * 4 + (int)q) * (uint32_t)C::STG_WARP;   // this warp's staging tile
         uint32_t n = 0;
         unsigned long long w_e = 0, work_e = 0;
@@ -660,6 +654,11 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]);
                     // the next 32 columns travel from TMEM while this block is converted and stored
                     if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
+                    else {   // the accumulators are in registers: hand the TMEM columns back before the last block's conversion
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(set));
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < 32; i++) {
@@ -667,7 +666,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
                 }
                 if constexpr (!FUSE) {
-                    epilogue_store32<COUT, F8, !(CIN == 64 && COUT == 128)>(act, p, stg, lane, (int)q, j, tx, ty, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll
@@ -691,11 +690,14 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(set));
+            if constexpr (C::STACK) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(set));
+            }
             if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
         }
+        if constexpr (!FUSE) bulk_wait_all();    // this warp's TMA stores are complete before the CTA may exit
         if (prof_on && warp == 3 && lane == 0) {
             prof[PROF_EPI_WAIT] += w_e;
             prof[PROF_EPI_WORK] += work_e;
@@ -781,7 +783,8 @@ struct PairCfg : Cfg<CIN, COUT, FUSE, F8> {
 template <int CIN, int COUT, bool FUSE, bool F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
-                       const __grid_constant__ CUtensorMap tmap_w, const TcParams p) {
+                       const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                       const __grid_constant__ CUtensorMap tmap_out8, const TcParams p) {
     using C = PairCfg<CIN, COUT, FUSE, F8>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -826,6 +829,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         prefetch_tmap(&tmap_in);
         prefetch_tmap(&tmap_w);
         if constexpr (F8) prefetch_tmap(&tmap_in8);
+        if constexpr (!FUSE) {
+            prefetch_tmap(&tmap_out);
+            if constexpr (F8) prefetch_tmap(&tmap_out8);
+        }
     }
     cluster_sync_all();                     // both CTAs' barriers exist before anything can signal them
     if (warp == 2) {
@@ -1015,6 +1022,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                 }
                 // the next 32 columns travel from TMEM while this block is converted and stored
                 if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
+                else {   // the accumulators are in registers: hand the TMEM columns back before the last block's conversion
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty(set), 0));
+                }
                 if constexpr (FUSE) {
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
@@ -1028,7 +1040,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                         }
                     }
                 } else {
-                    epilogue_store32<COUT, F8, !(CIN == 64 && COUT == 128)>(act, p, stg, lane, (int)q4, j, tx, ty, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4, cb);
                 }
             }
             if constexpr (FUSE) {
@@ -1039,11 +1051,9 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_rank(acc_empty(set), 0));
             if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
         }
+        if constexpr (!FUSE) bulk_wait_all();    // this warp's TMA stores are complete before the CTA may exit
         if (prof_on && warp == 3 && lane == 0) {
             prof[PROF_EPI_WAIT] += w_e;
             prof[PROF_EPI_WORK] += work_e;
@@ -1292,37 +1302,38 @@ cudaError_t init_kernels() {
 }
 
 template <int CIN, int COUT, bool FUSE, bool F8>
-static cudaError_t launch_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int grid, cudaStream_t s) {
-    tc_conv3x3_kernel<CIN, COUT, FUSE, F8><<<grid, NUM_THREADS, Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, p);
+static cudaError_t launch_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *p_out_maps, const TcParams &p, int grid, cudaStream_t s) {
+    tc_conv3x3_kernel<CIN, COUT, FUSE, F8><<<grid, NUM_THREADS, Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, p_out_maps[0], p_out_maps[1], p);
     return cudaGetLastError();
 }
 
 template <int CIN, int COUT>
-static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *omaps, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
     int grid = p.n_tilesets < num_sms ? p.n_tilesets : num_sms;
-    if (f8) return p.partial ? launch_k<CIN, COUT, true, true>(tmap, tmap8, p, grid, s) : launch_k<CIN, COUT, false, true>(tmap, tmap8, p, grid, s);
-    return p.partial ? launch_k<CIN, COUT, true, false>(tmap, tmap8, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, tmap8, p, grid, s);
+    if (f8) return p.partial ? launch_k<CIN, COUT, true, true>(tmap, tmap8, omaps, p, grid, s) : launch_k<CIN, COUT, false, true>(tmap, tmap8, omaps, p, grid, s);
+    return p.partial ? launch_k<CIN, COUT, true, false>(tmap, tmap8, omaps, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, tmap8, omaps, p, grid, s);
 }
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8);
 
 template <int CIN, bool FUSE, bool F8>
-static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const TcParams &p, int grid,
-                                 cudaStream_t s) {
-    tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8><<<grid, NUM_THREADS, PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, *tmapw, p);
+static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const CUtensorMap *p_out_maps,
+                                 const TcParams &p, int grid, cudaStream_t s) {
+    tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8><<<grid, NUM_THREADS, PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, *tmapw, p_out_maps[0], p_out_maps[1], p);
     return cudaGetLastError();
 }
 
 template <int CIN>
-static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *tmap8, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *omaps, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
     using C0 = Cfg<CIN, 128, false, false>;
     const size_t bytes = (size_t)C0::NCHUNK * 9 * C0::KBLOCKS * 2 * C0::B_BLOCK;   // both flavours stream the same number of bytes per tile-set
     CUtensorMap tmapw;
     if (make_weight_stream_map(&tmapw, p.wpack, bytes)) return cudaErrorInvalidValue;
     const int n_pair_sets = (p.n_tilesets + 1) / 2;
     int grid = 2 * (n_pair_sets < num_sms / 2 ? n_pair_sets : num_sms / 2);
-    if (f8) return p.partial ? launch_pair_k<CIN, true, true>(tmap, tmap8, &tmapw, p, grid, s) : launch_pair_k<CIN, false, true>(tmap, tmap8, &tmapw, p, grid, s);
-    return p.partial ? launch_pair_k<CIN, true, false>(tmap, tmap8, &tmapw, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, tmap8, &tmapw, p, grid, s);
+    if (f8) return p.partial ? launch_pair_k<CIN, true, true>(tmap, tmap8, &tmapw, omaps, p, grid, s) : launch_pair_k<CIN, false, true>(tmap, tmap8, &tmapw, omaps, p, grid, s);
+    return p.partial ? launch_pair_k<CIN, true, false>(tmap, tmap8, &tmapw, omaps, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, tmap8, &tmapw, omaps, p, grid, s);
 }
 
 cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out, int cin,
@@ -1340,6 +1351,8 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
+    static const int dbg_epi = std::getenv("W2X_DEBUG_EPI") ? std::atoi(std::getenv("W2X_DEBUG_EPI")) : 0;
+    p.dbg = dbg_epi;
     p.partial = partial;
     if (partial) {
         if (!last_w) return cudaErrorInvalidValue;
@@ -1347,14 +1360,18 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     }
     if (f8 && !tmap_in8) return cudaErrorInvalidValue;
     const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
+    // the epilogue's TMA stores: 8x4-pixel x 32-channel boxes of this layer's output frame (fused layers store no frame)
+    CUtensorMap omaps[2];
+    if (partial) { omaps[0] = *tmap_in; omaps[1] = *t8; }
+    else if (make_out_tensor_maps(&omaps[0], &omaps[1], out, cout, pw, ph, f8 != 0)) return cudaErrorInvalidValue;
     if (pair && cout == 128 && num_sms >= 2) {
 #define X(ci) \
-    if (cin == ci) return launch_pair<ci>(tmap_in, t8, p, num_sms, f8 != 0, s);
+    if (cin == ci) return launch_pair<ci>(tmap_in, t8, omaps, p, num_sms, f8 != 0, s);
         W2X_PAIR_CINS(X)
 #undef X
     }
 #define X(ci, co) \
-    if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, t8, p, num_sms, f8 != 0, s);
+    if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, t8, omaps, p, num_sms, f8 != 0, s);
     W2X_TC_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -1454,10 +1471,35 @@ static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t byt
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Output frame as the epilogue stores it: boxes of 32 channels x 8 px x 4 rows (one epilogue warp's pixels).
+//   f16x3: ONE map over [2][Hp][Wp][C] fp16, box {32, 8, 4, 2} (hi and lo planes in one store), SWIZZLE_64B; map8 = copy.
+//   F8:    map16 over the xh plane, box {32, 8, 4, 1}, SWIZZLE_64B; map8 over the two e4m3 planes, box {32, 8, 4, 2}, SWIZZLE_32B.
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -1;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(f8 ? 1 : 2)};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+        cuuint32_t box[4] = {32, 8, 4, (cuuint32_t)(f8 ? 1 : 2)};
+        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return (int)r;
+    }
+    if (!f8) { *map8 = *map16; return 0; }
+    char *b8 = reinterpret_cast<char *>(base) + (size_t)2 * Hp * Wp * C;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
+    cuuint32_t box[4] = {32, 8, 4, 2};
+    CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
-    const int kc = C < 64 ? C : 64;
+    const int kc = act_kc(C);
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
@@ -1472,7 +1514,7 @@ int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int H
 int make_act_tensor_maps_f8(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
-    const int kc = C < 64 ? C : 64;
+    const int kc = act_kc(C);
     cuuint32_t estr[4] = {1, 1, 1, 1};
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 1};
