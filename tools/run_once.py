@@ -14,6 +14,8 @@ engine = {"tc": w2x.ENGINE_TC, "fp32": w2x.ENGINE_FP32}[sys.argv[3] if len(sys.a
 om = oracle.OracleModel.golden("scale2.0x")
 m = w2x.Model.from_arrays(om.weights, om.biases)
 ctx = w2x.Context(0, engine=engine)      # precision: library default, or W2X_PRECISION=f16x3
+if os.environ.get("W2X_ONE_BAND"):
+    ctx.debug_set_host_bands(1)            # one whole-plane launch per layer (what bench.py's device-resident leg times)
 x = oracle.seeded_plane(size, size, 1, "uniform")
 for _ in range(passes):
     y = ctx.convert_plane(m, x)
