@@ -265,7 +265,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         const Layer &L = m->layers[0];
         logf(ctx, "Iteration #%d...", 1);
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, dm->w[0], dm->b[0], L.n_out, cur, ctx->stream, f8));
+        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, L.w.data(), dm->b_host[0].data(), L.n_out, cur, ctx->stream, f8));
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
@@ -480,7 +480,7 @@ int w2x_band_step(w2x_band *band, int step) {
     const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
     if (step == 0) {
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, dm->w[0], dm->b[0], L.n_out, band->act[0], ctx->stream, f8));
+        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8));
         band->cur = 0;
         note_kernel(ctx, 0, "first_1xN");
     } else {

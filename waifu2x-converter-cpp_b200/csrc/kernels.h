@@ -35,6 +35,7 @@ cudaError_t init_kernels();
 
 // First layer (Cin = 1): fp32 plane (ROI with stride) -> NHWC hi/lo frame of the same size (pw x ph),
 // same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
+// `wgt` ([C][9]) and `bias` ((float)bias) are HOST pointers: they travel as kernel parameters.
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
                          const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0);
 // tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.

@@ -1069,18 +1069,26 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
 // First layer (Cin = 1), last layer (Cout = 1), layout converters -- CUDA-core, HBM-bound
 // ================================================================================================
 // First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
-// writes the NHWC hi/lo frame the tcgen05 layers consume.  One thread per pixel.
+// writes the NHWC frame the tcgen05 layers consume.  One thread per pixel, 32 x 8 pixels per block.
+//   * weights and biases travel as kernel parameters: the 9*COUT FFMAs per pixel take them straight from the constant
+//     bank (as shared-memory broadcasts they were one LDS per FFMA -- the LSU, not the FP32 pipe, bounded the kernel);
+//   * 32 channels at a time are converted into a swizzled shared-memory image of the block's 8 x 32 pixels and leave
+//     through TMA stores (the same path as the tcgen05 epilogue): a thread's own 16-byte stores sat at a 64-byte stride.
+template <int COUT>
+struct FirstParams {
+    float w[COUT * 9];    // [COUT][3][3]
+    float b[COUT];        // (float)bias
+};
+constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16 KB]  or  [xh 16 KB | xh8 8 KB | xl8 8 KB]
+
 template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
-first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const float *__restrict__ wgt,
-                   const float *__restrict__ bias, __half *__restrict__ out) {
-    __shared__ float s_w[COUT * 9];
-    __shared__ float s_b[COUT];
-    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) s_w[i] = wgt[i];
-    for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_b[i] = bias[i];
-    __syncthreads();
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= pw || y >= ph) return;
+first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const __grid_constant__ CUtensorMap tmap_out,
+                   const __grid_constant__ CUtensorMap tmap_out8, const __grid_constant__ FirstParams<COUT> prm) {
+    extern __shared__ uint8_t first_smem[];
+    const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + wy;     // threads past the frame edge compute clamped copies; TMA clips them
     float v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ky++)
@@ -1089,48 +1097,67 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             int gy = min(max(y + ky - 1, 0), ph - 1), gx = min(max(x + kx - 1, 0), pw - 1);
             v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
         }
-    const size_t plane_elems = (size_t)ph * pw * COUT;
-    __half *dst_hi = out + ((size_t)y * pw + x) * COUT;
-    __half *dst_lo = dst_hi + plane_elems;
+    const uint32_t r = (uint32_t)threadIdx.x;                            // pixel index inside the block = row of the staged image
+    const uint32_t sw64 = (r >> 1) & 3u, sw32 = (r >> 2) & 1u;
 #pragma unroll 1
-    for (int c8 = 0; c8 < COUT / 8; c8++) {   // not unrolled: keeps the kernel at <= 64 registers, 4 blocks/SM (HBM-write-bound)
-        uint32_t hi[4], lo[4];
+    for (int cb = 0; cb < COUT / 32; cb++) {
+        if (cb) {   // the previous 32 channels' boxes must have left shared memory
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+        }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float a[2];
+        for (int c8 = 0; c8 < 4; c8++) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const float *w = s_w + (c8 * 8 + 2 * i + e) * 9;
-                float t = w[0] * v[0];
+            for (int i = 0; i < 4; i++) {
+                float a[2];
 #pragma unroll
-                for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
-                float r = (0.f + t) + s_b[c8 * 8 + 2 * i + e];
-                a[e] = (fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f)) * ACT_SCALE;
+                for (int e = 0; e < 2; e++) {
+                    const float *w = prm.w + (cb * 32 + c8 * 8 + 2 * i + e) * 9;
+                    float t = w[0] * v[0];
+#pragma unroll
+                    for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
+                    float rr = (0.f + t) + prm.b[cb * 32 + c8 * 8 + 2 * i + e];
+                    a[e] = (fminf(rr, 0.f) * 0.1f + fmaxf(rr, 0.f)) * ACT_SCALE;
+                }
+                __half2 h = __floats2half2_rn(a[0], a[1]);
+                float2 hf = __half22float2(h);
+                hi[i] = *reinterpret_cast<uint32_t *>(&h);
+                if constexpr (F8) {
+                    constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+                    const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+                    const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                    if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
+                    else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+                } else {
+                    __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
+                    lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                }
             }
-            __half2 h = __floats2half2_rn(a[0], a[1]);
-            float2 hf = __half22float2(h);
-            hi[i] = *reinterpret_cast<uint32_t *>(&h);
+            // 16-byte unit c8 of this pixel's 64-byte fp16 row (SWIZZLE_64B image)
+            sts128(tile + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
             if constexpr (F8) {
-                constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
-                const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
-                const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
-                if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
-                else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+                // 8 bytes of the pixel's 32-byte e4m3 rows (SWIZZLE_32B images): unit c8/2, half c8%2
+                const uint32_t off = r * 32u + ((((uint32_t)c8 >> 1) ^ sw32) << 4) + ((uint32_t)c8 & 1u) * 8u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 16384u + off), "r"(lo[0]), "r"(lo[1]) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 24576u + off), "r"(lo[2]), "r"(lo[3]) : "memory");
             } else {
-                __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
-                lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                sts128(tile + 16384u + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
             }
         }
-        reinterpret_cast<uint4 *>(dst_hi)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if constexpr (F8) {
-            uint8_t *b = reinterpret_cast<uint8_t *>(out);
-            const size_t pix = (size_t)y * pw + x;
-            *reinterpret_cast<uint2 *>(b + 2 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[0], lo[1]);
-            *reinterpret_cast<uint2 *>(b + 3 * plane_elems + pix * COUT + c8 * 8) = make_uint2(lo[2], lo[3]);
-        } else {
-            reinterpret_cast<uint4 *>(dst_lo)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            if constexpr (F8)
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out8)), "r"(tile + 16384u), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // shared memory stays valid until the boxes are out
 }
 
 // Last layer: nOutputPlanes = 1.  fp32 arithmetic in the reference's association: per input plane a
@@ -1315,7 +1342,7 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8,
 }
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8);
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w = 8, int box_h = 4);
 
 template <int CIN, bool FUSE, bool F8>
 static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const CUtensorMap *p_out_maps,
@@ -1377,21 +1404,36 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s, int f8) {
+template <int COUT>
+static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
+                                  cudaStream_t s, int f8) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    FirstParams<COUT> prm;
+    for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
+    for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
+    CUtensorMap omaps[2];
+    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8)) return cudaErrorInvalidValue;
     dim3 grid((pw + 31) / 32, (ph + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
-#define W2X_FIRST(C)                                                                                         \
-    case C:                                                                                                  \
-        if (f8) first_layer_kernel<C, true><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out);  \
-        else first_layer_kernel<C, false><<<grid, 256, 0, s>>>(in, in_stride_floats, pw, ph, wgt, bias, out);    \
-        break;
+    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, omaps[0], omaps[1], prm);
+    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, omaps[0], omaps[1], prm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
+                         int cout, __half *out, cudaStream_t s, int f8) {
     switch (cout) {
-        W2X_FIRST(32) W2X_FIRST(64) W2X_FIRST(128)
+        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
+        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
+        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
         default: return cudaErrorInvalidValue;
     }
-#undef W2X_FIRST
-    return cudaGetLastError();
 }
 
 cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt, float bias, int crop, float *dst,
@@ -1471,17 +1513,18 @@ static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t byt
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-// Output frame as the epilogue stores it: boxes of 32 channels x 8 px x 4 rows (one epilogue warp's pixels).
+// Output frame as the epilogue stores it: boxes of 32 channels x 8 px x 4 rows (one epilogue warp's pixels; the first
+// layer's blocks store 32 x 8 pixels).
 //   f16x3: ONE map over [2][Hp][Wp][C] fp16, box {32, 8, 4, 2} (hi and lo planes in one store), SWIZZLE_64B; map8 = copy.
 //   F8:    map16 over the xh plane, box {32, 8, 4, 1}, SWIZZLE_64B; map8 over the two e4m3 planes, box {32, 8, 4, 2}, SWIZZLE_32B.
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8) {
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(f8 ? 1 : 2)};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-        cuuint32_t box[4] = {32, 8, 4, (cuuint32_t)(f8 ? 1 : 2)};
+        cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)(f8 ? 1 : 2)};
         CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return (int)r;
@@ -1490,7 +1533,7 @@ static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *bas
     char *b8 = reinterpret_cast<char *>(base) + (size_t)2 * Hp * Wp * C;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
     cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
-    cuuint32_t box[4] = {32, 8, 4, 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 2};
     CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
