@@ -291,7 +291,10 @@ struct Cfg {
     static constexpr int STG_BYTES = FUSE ? 0 : 8 * STG_WARP;               // epilogue store staging per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
-    static constexpr int NB = NB_FIT > 8 ? 8 : NB_FIT;
+    // Narrow layers: ALL weight stages of a tile-set fit -> loaded once per CTA and kept (no ring traffic, no stage barriers
+    // after the first tile-set; the TMA unit is left to the activation boxes and the epilogue's stores).
+    static constexpr bool RESIDENT = STAGES_PER_TILESET <= NB_FIT && STAGES_PER_TILESET <= 24;
+    static constexpr int NB = RESIDENT ? STAGES_PER_TILESET : (NB_FIT > 8 ? 8 : NB_FIT);
     static constexpr int SMEM_BYTES = 1024 + A_SLOTS * A_SLOT + NB * B_STAGE + BAR_BYTES + W6_BYTES + STG_BYTES;
     static_assert(NB >= 3, "need at least three weight stages");
     static_assert((8 + 2 * NB) * 8 + 4 <= 512 && COUT * 4 <= 512, "barrier/bias area overflow");
@@ -491,8 +494,9 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             unsigned long long w_b = 0;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack);
+                if (C::RESIDENT && ts != (int)blockIdx.x) break;           // resident weights: one pass fills every stage for good
                 for (int blk = 0; blk < C::STAGES_PER_TILESET; blk++) {
-                    mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
+                    if constexpr (!C::RESIDENT) mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
                     mbar_arrive_expect_tx(b_full(stage), C::B_STAGE);
                     bulk_load(b_base + stage * C::B_STAGE, src + (size_t)blk * C::B_STAGE, C::B_STAGE, b_full(stage));
                     if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
@@ -522,15 +526,23 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         const long long t_begin = clock64();
         // wait for the current weight stage (usually already known to be full), then probe the NEXT one
         auto acquire_b = [&](uint32_t &b0_out) {
-            if (!b_ready) mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
-            tc_fence_after();
-            b0_out = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
-            uint32_t ns = stage + 1, np = phase;
-            if (ns == (uint32_t)C::NB) { ns = 0; np ^= 1u; }
-            b_ready = mbar_test(b_full(ns), np);      // consumed at the next acquire_b
+            if constexpr (C::RESIDENT) {
+                if (n == 0) {                             // the stages arrive once, during the first tile-set
+                    mbar_wait_prof(b_full(stage), 0u, prof_on, w_bf);
+                    tc_fence_after();
+                }
+                b0_out = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+            } else {
+                if (!b_ready) mbar_wait_prof(b_full(stage), phase, prof_on, w_bf);
+                tc_fence_after();
+                b0_out = (((b_base + stage * C::B_STAGE) >> 4) & 0x3FFFu) | LO_FIXED;
+                uint32_t ns = stage + 1, np = phase;
+                if (ns == (uint32_t)C::NB) { ns = 0; np ^= 1u; }
+                b_ready = mbar_test(b_full(ns), np);      // consumed at the next acquire_b
+            }
         };
         auto release_b = [&]() {
-            umma_commit_one(b_empty(stage));
+            if constexpr (!C::RESIDENT) umma_commit_one(b_empty(stage));
             if (++stage == (uint32_t)C::NB) { stage = 0; phase ^= 1u; }
         };
         for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x, n++) {
