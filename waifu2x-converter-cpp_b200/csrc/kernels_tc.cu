@@ -890,7 +890,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         }
     } else if (warp == 2) {
         // ===================== B producer (both CTAs): this CTA's 64 rows of every weight stage ========================
-        // tmap_w views the packed stream as rows of 64 bytes, box = 32 rows (2 KB).  A 128-row fp16 block is 8 KB
+        // tmap_w views the packed stream as rows of 1 KB, box = 2 rows (2 KB).  A 128-row fp16 block is 8 KB
         // (this CTA's half: 4 KB at +rank*4 KB); an e4m3 stage is [wh8 4 KB | wl8 4 KB] (halves: 2 KB at +rank*2 KB each).
         {
             uint32_t stage = 0, phase = 0;
@@ -902,16 +902,16 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                     if (is_leader) mbar_arrive_expect_tx(b_full(stage), 2u * (uint32_t)C::B_HALF);
                     const uint32_t bar = mapa_rank(b_full(stage), 0);
                     const uint32_t dst = b_base + stage * C::B_HALF;
-                    const int row0 = blk * (2 * C::B_BLOCK / 64);             // first 64-byte row of this step in the stream (256 rows per step)
-                    // first block (128 rows x 64 B, fp16): this CTA's rows 64*rank .. +64
-                    tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 64);
-                    tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + (int)rank * 64 + 32);
-                    if constexpr (F8) {   // [wh8 | wl8]: 128 rows x 32 B each = 64 stream rows each; this CTA's half = 32 stream rows
-                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 32);
-                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 192 + (int)rank * 32);
+                    const int row0 = blk * (2 * C::B_BLOCK / 1024);           // first 1 KB row of this step in the stream (16 rows per step)
+                    // first block (128 rows x 64 B = 8 KB, fp16): this CTA's operand rows 64*rank .. +64 = 4 KB at +rank*4 KB
+                    tma_load_2d_2cta(dst, &tmap_w, bar, 0, row0 + (int)rank * 4);
+                    tma_load_2d_2cta(dst + 2048u, &tmap_w, bar, 0, row0 + (int)rank * 4 + 2);
+                    if constexpr (F8) {   // [wh8 | wl8]: 128 rows x 32 B = 4 KB each; this CTA's half = 2 KB
+                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 8 + (int)rank * 2);
+                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 12 + (int)rank * 2);
                     } else {              // lo block (fp16)
-                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 64);
-                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 128 + (int)rank * 64 + 32);
+                        tma_load_2d_2cta(dst + 4096u, &tmap_w, bar, 0, row0 + 8 + (int)rank * 4);
+                        tma_load_2d_2cta(dst + 6144u, &tmap_w, bar, 0, row0 + 8 + (int)rank * 4 + 2);
                     }
                     if (++stage == (uint32_t)C::NBP) { stage = 0; phase ^= 1u; }
                 }
@@ -1511,15 +1511,17 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-// The packed weight stream as rows of 64 bytes, box = 32 rows (2 KB), no swizzle: the CTA-pair kernel's B loads.
+// The packed weight stream as rows of 1 KB (256 x 32-bit words), box = 2 rows (2 KB), no swizzle: the CTA-pair kernel's
+// B loads.  (Long rows matter: the TMA unit issues one request per box row, and 64-byte rows made the weight ring
+// request-bound.)
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes) {
     PFN_encodeTiled enc = get_encode();
     if (!enc || bytes % 2048) return -1;
-    cuuint64_t dims[2] = {64, (cuuint64_t)(bytes / 64)};
-    cuuint64_t strides[1] = {64};
-    cuuint32_t box[2] = {64, 32};
+    cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 1024)};
+    cuuint64_t strides[1] = {1024};
+    cuuint32_t box[2] = {256, 2};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
