@@ -11,6 +11,7 @@ from oracle import oracle  # noqa: E402
 
 w2x = w2x_loader.load()
 ctxs = {"fp32": w2x.Context(0, engine=w2x.ENGINE_FP32), "tc f16x3": w2x.Context(0, engine=w2x.ENGINE_TC), "tc f16+f8x2": w2x.Context(0, engine=w2x.ENGINE_TC)}
+ctxs["tc f16x3"].set_precision(w2x.PRECISION_F16X3)
 ctxs["tc f16+f8x2"].set_precision(w2x.PRECISION_F16_F8X2)
 print("max-abs error vs the reference's OpenCV output (tests/golden/cfg1_*.npy, 256x256), gate 1e-4")
 for name, kind in (("scale2.0x", "uniform"), ("scale2.0x", "smooth"), ("noise1", "uniform"), ("noise2", "uniform")):
