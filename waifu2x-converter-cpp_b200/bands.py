@@ -61,20 +61,22 @@ def run_band_per_layer(band, ext_in, ext_stride_bytes, d_out, out_stride_bytes, 
         import torch
     from .capi import DevBytes
     band.load(ext_in, ext_stride_bytes)
+    views = band.__dict__.setdefault("_p2p_views", {})     # zero-copy tensor views of the session's halo rows, built once
     for k in range(band.steps):
         band.step(k)
         if world == 1:
             continue
-        ops, keep = [], []
-        for (su, ru, sd, rd, nb) in band.halo(k):
-            if rank > 0:
-                ts, tr = torch.as_tensor(DevBytes(su, nb), device="cuda"), torch.as_tensor(DevBytes(ru, nb), device="cuda")
-                ops += [dist.P2POp(dist.isend, ts, rank - 1), dist.P2POp(dist.irecv, tr, rank - 1)]
-                keep += [ts, tr]
-            if rank < world - 1:
-                ts, tr = torch.as_tensor(DevBytes(sd, nb), device="cuda"), torch.as_tensor(DevBytes(rd, nb), device="cuda")
-                ops += [dist.P2POp(dist.isend, ts, rank + 1), dist.P2POp(dist.irecv, tr, rank + 1)]
-                keep += [ts, tr]
+        if k not in views:
+            v = []
+            for (su, ru, sd, rd, nb) in band.halo(k):
+                if rank > 0:
+                    v.append((torch.as_tensor(DevBytes(su, nb), device="cuda"), torch.as_tensor(DevBytes(ru, nb), device="cuda"), rank - 1))
+                if rank < world - 1:
+                    v.append((torch.as_tensor(DevBytes(sd, nb), device="cuda"), torch.as_tensor(DevBytes(rd, nb), device="cuda"), rank + 1))
+            views[k] = v
+        ops = []
+        for ts, tr, peer in views[k]:
+            ops += [dist.P2POp(dist.isend, ts, peer), dist.P2POp(dist.irecv, tr, peer)]
         for req in dist.batch_isend_irecv(ops):
-            req.wait()
+            req.wait()       # NCCL: orders the current stream after the transfer, does not block the host
     band.finish(d_out, out_stride_bytes)

@@ -494,9 +494,9 @@ int w2x_band_step(w2x_band *band, int step) {
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)step] : (const void *)dm->pack[(size_t)step],
                                          dm->b_host[(size_t)step].data(), out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
                                          ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t.data() : nullptr,
-                                         fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr));
+                                         fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr, ctx->pair));
         }
-        note_kernel(ctx, step, fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3");
+        note_kernel(ctx, step, f8 ? (fused ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
         band->cur ^= 1;
     }
     ctx->launches++;
@@ -852,7 +852,7 @@ int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, con
             LayerTimer t(ctx, layer);
             CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)layer] : (const void *)dm->pack[(size_t)layer],
                                          dm->b_host[(size_t)layer].data(), fout, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)layer], f8,
-                                         ctx->num_sms, ctx->stream, nullptr, nullptr, nullptr, f8 ? &map8 : nullptr));
+                                         ctx->num_sms, ctx->stream, nullptr, nullptr, nullptr, f8 ? &map8 : nullptr, ctx->pair));
         }
         CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream, f8));
         note_kernel(ctx, layer, f8 ? "tcgen05_f16+f8x2" : "tcgen05_f16x3");
