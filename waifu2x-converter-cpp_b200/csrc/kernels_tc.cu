@@ -4,27 +4,33 @@
 // once): out[o](y,x) = leaky( sum_i sum_{ky,kx} W[o][i][ky][kx] * in[i](y+ky-1, x+kx-1) + bias[o] ).
 //
 // How: implicit GEMM, D[pixel][o] += A[pixel][(tap,i)] * B[(tap,i)][o], on the 5th-generation
-// tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM).  fp32 fidelity comes from a
-// 2-term fp16 split of both operands (x = xh + xl, w = wh + wl) and three MMA passes
+// tensor cores (tcgen05.mma, fp32 accumulators in TMEM).  fp32 fidelity comes from a 2-term split of
+// both operands (x = xh + xl, w = wh + wl, h = the fp16 rounding) and three accumulated products
 // xh*wh + xl*wh + xh*wl (the dropped xl*wl term is ~2^-22 relative); SURVEY.md section 7 shows a
-// single fp16/tf32 pass misses the 1e-4 gate by 10x.
+// single fp16/tf32 pass misses the 1e-4 gate by 10x.  Two arithmetic modes (template flag F8):
+//   f16x3      all three products as kind::f16 MMAs on fp16 hi/lo planes
+//   f16+f8x2   xh*wh as kind::f16; the two correction products as kind::f8f6f4 MMAs on e4m3 copies of the
+//              operands (K = 32 per instruction, twice the rate) -- the default, 2.0 instead of 3.0 passes
 //
-// Data layout in HBM: every activation is an NHWC "frame" [2 (hi,lo)][Hp][Wp][C] of fp16 holding
-// value*ACT_SCALE; all layers of one pass share the frame size (the padded plane), reads outside
-// the frame are zero-filled by TMA, so each layer is a same-size convolution whose polluted ring
-// grows by one pixel per layer and is cropped at the end -- the same argument that makes the
-// reference's per-layer BORDER_REPLICATE harmless.
+// Data layout in HBM: every activation is an NHWC "frame" of 4 bytes per element holding value*ACT_SCALE,
+// [hi fp16][lo fp16] or [xh fp16][xh8 e4m3][xl8 e4m3] planes of [Hp][Wp][C]; all layers of one pass share
+// the frame size (the padded plane), reads outside the frame are zero-filled by TMA, so each layer is a
+// same-size convolution whose polluted ring grows by one pixel per layer and is cropped at the end -- the
+// same argument that makes the reference's per-layer BORDER_REPLICATE harmless.
 //
 // Per CTA (persistent, 1 per SM, 12 warps):
-//   warp 0      A producer   one TMA box {KC ch, 18, 18} per (tile-set, channel chunk, hi|lo): the
+//   warp 0      A producer   one TMA box {KC ch, 18, 18} per (tile-set, channel chunk, plane): the
 //                            16x16 output region plus a 1-pixel ring, staged ONCE and addressed nine
 //                            times (the 3x3 taps are UMMA-descriptor start-address offsets into it)
-//   warps 1, 7  MMA issuers  one per M-tile (8 wide x 16 tall pixels): tcgen05.mma cta_group::1, M=128,
-//                            N=Cout (N=2*Cout with [wh;wl] stacked when Cout<=64), K=16 per instruction
-//   warp 2      B producer   pre-swizzled 32-channel weight stages streamed with cp.async.bulk; owns TMEM
-//   warps 3-6, 8-11 epilogue one set per M-tile: tcgen05.ld -> scale, +bias, leaky-ReLU -> either re-split to
-//                            fp16 hi/lo + transposed, coalesced NHWC stores, or (FUSE) the last layer's nine
-//                            tap partials; overlaps the next tile-set (TMEM double buffer)
+//   warps 1, 7  MMA issuers  one per M-tile (8 wide x 16 tall pixels): tcgen05.mma, M=128 (M=256 across a CTA
+//                            pair for the 128-wide layers), N=Cout, K=16 (fp16) / 32 (e4m3) per instruction;
+//                            operands provably warp-uniform, so the MMAs issue back to back from uniform registers
+//   warp 2      B producer   pre-swizzled 32-channel weight stages: a cp.async.bulk ring, or resident for the
+//                            narrow layers; owns TMEM
+//   warps 3-6, 8-11 epilogue one set per M-tile: tcgen05.ld -> scale, +bias, leaky-ReLU -> either the frame's
+//                            planes, staged in the TMA swizzle pattern and TMA-stored, or (FUSE) the last
+//                            layer's nine tap partials; overlaps the next tile-set (TMEM double buffer)
+//
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -238,8 +244,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // ================================================================================================
 // Per-layer configuration
 // ================================================================================================
-// Epilogue store staging per warp: 2 KB (two shared-memory round trips per 32 channels) or 4 KB (one round trip).
-// (Measured on L4: 4 KB staging shortens the epilogue by only 4 % but costs two weight stages -> slower overall; kept off.)
 // Channels per staged activation box: 32 for layers up to 64 inputs (two small boxes per tile-set instead of one 83 KB
 // one leave room for the store staging and a deep weight ring), 64 for the 128-input layers.
 __host__ __device__ constexpr int act_kc(int cin) { return cin <= 64 ? 32 : 64; }
@@ -277,7 +281,7 @@ struct Cfg {
     static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
     // F8: per 32-channel block ONE stage [wh fp16 (Cout x 64 B) | wh8 | wl8 (e4m3, Cout x 32 B each)]: four MMAs per
     // issuer per barrier round trip.
-    static constexpr bool MERGE = F8 && (COUT <= 64 || FUSE);   // (a 128-wide layer with store staging has room for only two 16 KB stages)
+    static constexpr bool MERGE = F8 && (COUT <= 64 || FUSE);   // (a stored 128-in/128-out layer has no room for 16 KB stages beside its two 83 KB activation slots)
     static constexpr int B_STAGE = (STACK || MERGE) ? 2 * B_BLOCK : B_BLOCK;
     static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * ((STACK || MERGE) ? 1 : 2);
     // ---- accumulators ----
@@ -506,7 +510,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         }
     } else if (warp == 1 || warp == 7) {
         // ===================== MMA issuers (warp 1: M-tile 0, warp 7: M-tile 1) ========================
-        // The whole warp walks the loop, lane 0's instructions are predicated inside the asm blocks.
+        // The whole warp walks the loop converged; each MMA / commit elects one lane inside its asm block.
         const uint32_t leader = lane == 0 ? 1u : 0u;
         const uint32_t jt = warp == 1 ? 0u : 1u;
         constexpr uint32_t idesc_c = make_idesc(128, COUT);          // N = Cout
