@@ -6,8 +6,11 @@
 Workload (BASELINE.json config 3, the one the metric is quoted on): one full scale2.0x model pass
 (7 layers, 574 272 algorithmic FLOP per output pixel) over a synthetic 4096x4096 fp32 Y plane.
 With N > 1 ranks (torchrun, one process per GPU) the plane is 4096 wide x 4096*N tall, cut into N
-row bands; every rank trades 7 input rows with each neighbour (torch.distributed send/recv over
-NCCL) and then runs its band -- weak scaling, no collective between layers.
+row bands (weak scaling).  Default exchange (--halo per-layer, the north_star): after every layer each
+rank sends its boundary row of the fresh activation to the neighbour (torch.distributed send/recv over
+NCCL/NVLink on zero-copy views of the library's band-session buffers); --halo input trades 7 input rows
+once and recomputes the overlap.  --strong cuts ONE size x size plane into N bands instead (BASELINE
+config 4: --size 8192 --strong).
 
 metric  Mpix/s = output pixels / time of the whole pass.
 value   inputs already resident in HBM, device entry point (w2x_convert_plane_device).
@@ -35,7 +38,6 @@ sys.path.insert(0, ROOT)
 FLOP_PER_PIXEL = 574272           # 2 * 9 * sum(Cin*Cout), SURVEY.md section 8(d)
 LAYER_MACS = [288, 9216, 18432, 36864, 73728, 147456, 1152]   # per pixel, L0..L6
 MODEL = "scale2.0x"
-MMA_PASSES = 3
 
 
 def load_peaks():
@@ -166,6 +168,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = H = args.size
+    if args.strong and world > 1:
+        if H % world:
+            raise SystemExit("--strong needs the plane height to divide by the number of ranks")
+        H = H // world                         # ONE size x size plane, cut into `world` row bands
     n_model = 7
     om = oracle_mod.OracleModel.golden(MODEL)
     model = w2x.Model.from_arrays(om.weights, om.biases)
@@ -314,7 +320,7 @@ def run_ours(args):
             cpu = {"value": 498 * 498 / s / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind,
                    "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} (reference default -j 4)"}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
                 "dtype": ("f32" if args.engine == "fp32" else "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.precision == "f16x3"
                           else "f16 + 2x e4m3 correction products, f32 accumulate (fp32-faithful to ~3e-5)"),
                 "data": "synthetic",
@@ -343,6 +349,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--precision", default="f8", choices=["f16x3", "f8"],
                     help="tcgen05 arithmetic: fp16 + two e4m3 correction products (the library default) or three fp16 products")
+    ap.add_argument("--strong", action="store_true", help="multi-GPU: cut ONE size x size plane into N row bands (strong scaling) instead of one plane per GPU")
     ap.add_argument("--check", action="store_true", help="multi-GPU: verify the per-layer result against the one-shot band mode, bit for bit")
     ap.add_argument("--halo", default="per-layer", choices=["input", "per-layer"],
                     help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")
