@@ -126,14 +126,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.commit_group;\n\t}" ::: "memory");
 }
-// the elected lane's earlier bulk stores have finished READING shared memory (the staging tile may be rewritten)
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group.read 0;\n\t}" ::: "memory");
-}
+// Every lane waits for ITS OWN bulk groups (lanes that issued none return at once), so whichever lane the elect.sync of
+// tma_store_4d / bulk_commit picked is covered; callers follow with __syncwarp().
+// ... have finished READING shared memory (the staging tile may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // ... have completed (before the CTA exits)
-__device__ __forceinline__ void bulk_wait_all() {
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q cp.async.bulk.wait_group 0;\n\t}" ::: "memory");
-}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
