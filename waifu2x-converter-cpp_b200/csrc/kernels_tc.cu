@@ -316,7 +316,7 @@ struct TcParams {
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / wscale  (accumulator -> ACT_SCALE * conv)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off
-    int dbg;                    // W2X_DEBUG_EPI (timing experiments only, results are WRONG when set): 1 = no global stores, 2 = no staging either
+    int dbg;                    // always 0 in product builds; -DW2X_EPI_EXPERIMENTS + W2X_DEBUG_EPI: 1 = no global stores, 2 = no staging either (timing only, results WRONG)
     // fused last layer (FUSE kernels only): this layer's activations never reach HBM; instead each pixel's
     // nine tap partials P[t] = sum_c act[c] * w_last[c][t] are written ([Hp][Wp][12] fp32, 3 pad words).
     float *partial;             // nullptr = not fused
@@ -1392,8 +1392,12 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
+#ifdef W2X_EPI_EXPERIMENTS   // timing experiments only (results are wrong): build with -DW2X_EPI_EXPERIMENTS, then W2X_DEBUG_EPI=1|2
     static const int dbg_epi = std::getenv("W2X_DEBUG_EPI") ? std::atoi(std::getenv("W2X_DEBUG_EPI")) : 0;
     p.dbg = dbg_epi;
+#else
+    p.dbg = 0;
+#endif
     p.partial = partial;
     if (partial) {
         if (!last_w) return cudaErrorInvalidValue;
