@@ -27,9 +27,13 @@ class _Layer(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    """Compile oracle/w2x_oracle.c -> oracle/_ref/libw2x_oracle.so (gcc only)."""
+    """Compile oracle/w2x_oracle.c -> oracle/_ref/libw2x_oracle.so (gcc only) and, where the reference tree is present
+    (the authoring container), the reference's own hot-path sources against oracle/cvshim -> oracle/_ref/libw2x_reference.so
+    (see oracle/reference_lib.py; on the GPU box the prebuilt file is used as it is)."""
     src = os.path.join(_HERE, "w2x_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    ref_so = os.path.join(_HERE, "_ref", "libw2x_reference.so")
+    ref_missing = os.path.exists("/root/reference/src/modelHandler.cpp") and not os.path.exists(ref_so)
+    if force or ref_missing or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
     return _SO
 

@@ -1,0 +1,108 @@
+"""The reference's OWN hot-path sources (src/modelHandler.cpp, src/convertRoutine.cpp), compiled where they lie
+against the OpenCV API shim in oracle/cvshim (oracle/Makefile -> oracle/_ref/libw2x_reference.so), pin the restated
+oracle and the golden vectors against the reference's real control flow: picojson model loading, the thread partition
+of Model::filter, the layer loop, replicate padding, the block-split arithmetic, crop and stitch.
+
+The library is built only where /root/reference exists (the authoring container) and travels prebuilt to the GPU box;
+nothing here reads /root/reference at run time (the model JSONs are re-written from tests/golden/models)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_path
+from oracle import reference_lib as R
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libw2x_reference.so not built (needs /root/reference at build time)")
+
+# restated fp32 arithmetic of the shim vs OpenCV's SIMD kernels: re-association / FMA only
+SHIM_VS_CV2_TOL = 3e-6
+
+
+@pytest.fixture(scope="module")
+def ref_models(json_models):
+    R.configure(4, 9)                         # the reference's defaults: -j 4, 512x512 blocks
+    ms = {n: R.ReferenceModels(p) for n, p in json_models.items()}
+    yield ms
+    for m in ms.values():
+        m.close()
+    R.configure(4, 9)
+
+
+def test_reference_loader_reads_the_model_files(ref_models, oracle_models):
+    for name, rm in ref_models.items():
+        assert rm.n == 7 and rm.dims == [tuple(d) for d in oracle_models[name].dims]
+
+
+@pytest.mark.parametrize("name", ["scale2.0x", "noise1"])
+@pytest.mark.parametrize("n_job", [1, 3, 4])
+def test_oracle_is_bit_identical_to_the_reference_control_flow(ref_models, oracle_mod, oracle_models, name, n_job):
+    """convertWithModels, no-split path (src/convertRoutine.cpp:31-48), for every thread partition the reference forms
+    (nOutputPlanes / nJob with the remainder on the last thread, src/modelHandler.cpp:46-65)."""
+    R.configure(n_job, 9)
+    for (w, h, seed) in ((1, 1, 11), (15, 13, 25), (37, 61, 47), (64, 48, 3)):
+        x = oracle_mod.seeded_plane(w, h, seed, "uniform")
+        y_ref = ref_models[name].convert(x, True)
+        y_orc = oracle_models[name].convert(x, n_job=n_job)
+        assert y_ref.shape == (h, w)
+        assert np.array_equal(y_ref, y_orc), (w, h)
+    R.configure(4, 9)
+
+
+def test_block_split_path_is_bit_identical(ref_models, oracle_mod, oracle_models):
+    """convertWithModelsBlockSplit (src/convertRoutine.cpp:84-169) with 64x64 blocks (threshold 64*64*3/2 = 6144 px):
+    block rectangles, last-block handling, crop and stitch -- against the oracle's restatement and against no-split."""
+    R.configure(4, 6)
+    try:
+        om, rm = oracle_models["scale2.0x"], ref_models["scale2.0x"]
+        for (w, h, seed) in ((120, 90, 4), (101, 64, 5), (51, 121, 6), (150, 50, 7)):
+            assert w * h > 6144
+            x = oracle_mod.seeded_plane(w, h, seed, "uniform")
+            y_split = rm.convert(x, True)
+            assert np.array_equal(y_split, om.convert(x, True, block=(64, 64))), (w, h)
+            assert np.abs(y_split - rm.convert(x, False)).max() <= 1e-6, (w, h)
+        x = oracle_mod.seeded_plane(96, 64, 8, "uniform")            # exactly AT the threshold: the reference does not split
+        assert np.array_equal(rm.convert(x, True), om.convert(x, True, block=(64, 64)))
+    finally:
+        R.configure(4, 9)
+
+
+def test_model_filter_per_layer(ref_models, oracle_models):
+    """Model::filter of every layer on the golden 32x24 inputs: bit-equal to the oracle, within fp32 re-association of cv2."""
+    z = np.load(golden_path("layers_32x24.npz"))
+    rm, om = ref_models["scale2.0x"], oracle_models["scale2.0x"]
+    for li in range(rm.n):
+        out = rm.filter(li, z[f"in{li}"])
+        assert np.array_equal(out, om.filter(li, z[f"in{li}"], n_job=4)), li
+        assert np.abs(out - z[f"out{li}"]).max() <= SHIM_VS_CV2_TOL * max(1.0, float(np.abs(z[f"out{li}"]).max())), li
+
+
+def test_reference_control_flow_reproduces_the_cv2_golden_odd_sizes(ref_models, oracle_mod):
+    z = np.load(golden_path("odd_sizes.npz"))
+    for (w, h) in ((1, 1), (15, 13), (37, 61)):
+        x = oracle_mod.seeded_plane(w, h, 10 + w, "uniform")
+        assert np.abs(ref_models["scale2.0x"].convert(x, True) - z[f"out_{w}x{h}"]).max() <= SHIM_VS_CV2_TOL
+
+
+@pytest.mark.slow
+def test_cfg1_256_reference_control_flow_vs_cv2_golden(ref_models, oracle_mod, ncpu):
+    """BASELINE config 1 through the reference's own code (shim arithmetic) against the output of real OpenCV arithmetic."""
+    R.configure(ncpu, 9)
+    try:
+        x = oracle_mod.seeded_plane(256, 256, 0, "uniform")
+        y = ref_models["scale2.0x"].convert(x, True)
+        g = np.load(golden_path("cfg1_scale2.0x_uniform.npy"))
+        assert np.abs(y - g).max() <= SHIM_VS_CV2_TOL
+    finally:
+        R.configure(4, 9)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/models/scale2.0x_model.json"), reason="reference tree not present (GPU box)")
+def test_shipped_model_files_equal_the_golden_weights(ref_models, oracle_mod):
+    """Authoring container only: the reference's real JSON files through its real loader give the same output bits as the
+    JSON re-written from tests/golden/models (i.e. the committed weights ARE the shipped weights after double->float)."""
+    x = oracle_mod.seeded_plane(40, 30, 9, "smooth")
+    for name in ("scale2.0x", "noise1", "noise2"):
+        real = R.ReferenceModels(f"/root/reference/models/{name}_model.json")
+        assert np.array_equal(real.convert(x, True), ref_models[name].convert(x, True)), name
+        real.close()
