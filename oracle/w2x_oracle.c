@@ -23,7 +23,11 @@
  * C++).  This restatement is therefore pinned against outputs of the
  * reference's own arithmetic backend (OpenCV, through Python cv2 running the
  * identical cv::filter2D / add / max / min / scaleAdd / copyMakeBorder calls,
- * see oracle/ref_cv2.py) committed under tests/golden/.
+ * see oracle/ref_cv2.py) committed under tests/golden/ -- AND against the
+ * reference's own sources: src/modelHandler.cpp and src/convertRoutine.cpp compile
+ * unmodified against the OpenCV API shim in oracle/cvshim into
+ * oracle/_ref/libw2x_reference.so (oracle/Makefile); this restatement is bit-identical
+ * to that library on every path (tests/test_reference_build.py).
  *
  * Arithmetic follows the reference op for op in fp32:
  *   per (o,i): tmp = sum over the 9 taps, row-major (ky,kx), starting from 0
