@@ -15,6 +15,10 @@
 //   cv::add / max / min / scaleAdd   element-wise fp32; double scalars are rounded to float first (OpenCV converts
 //                  the scalar to the array depth: bias -> (float)bias, 0.1 -> 0.1f)
 //   cv::copyMakeBorder   BORDER_REPLICATE
+// For src/main.cpp (the CLI around the hot path) the image plumbing calls are adapters onto the repo's own host
+// restatements, which tests/test_cli.py pins against cv2: imread / imwrite -> host/imageio.hpp; convertTo, cvtColor
+// (RGB2YUV / YUV2RGB), resize (NEAREST / LINEAR / CUBIC) -> host/imgproc.hpp; split / merge are plain copies.  Those are
+// only compiled in when W2X_CVSHIM_WITH_IMGPROC is defined (the reference CLI build, oracle/Makefile).
 // Nothing outside tests/, oracle/ and bench.py's CPU-baseline leg may use this.
 #ifndef W2X_ORACLE_CVSHIM_OPENCV_HPP_
 #define W2X_ORACLE_CVSHIM_OPENCV_HPP_
@@ -26,10 +30,20 @@
 #include <cstring>
 #include <memory>
 #include <ostream>
+#include <string>
 #include <vector>
 
+#ifdef W2X_CVSHIM_WITH_IMGPROC
+#include "imageio.hpp"
+#include "imgproc.hpp"
+#endif
+
+#define CV_8U 0
 #define CV_32F 5
-#define CV_32FC1 5
+#define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 
 namespace cv {
 
@@ -66,26 +80,30 @@ public:
     Mat(Size s, int type) { create(s.height, s.width, type); }
     static Mat zeros(int r, int c, int type) {
         Mat m(r, c, type);
-        for (int y = 0; y < r; y++) std::memset(m.data + (size_t)y * m.step, 0, (size_t)c * sizeof(float));
+        for (int y = 0; y < r; y++) std::memset(m.data + (size_t)y * m.step, 0, (size_t)c * m.elemSize());
         return m;
     }
     static Mat zeros(Size s, int type) { return zeros(s.height, s.width, type); }
 
     void create(int r, int c, int type) {
-        assert(type == CV_32FC1);
-        (void)type;
-        if (data && rows == r && cols == c) return;          // same shape: keep the storage (views included)
-        owner_ = std::shared_ptr<float>(new float[(size_t)std::max(r, 0) * std::max(c, 0) + 1], std::default_delete<float[]>());
+        assert((type & 7) == CV_32F || (type & 7) == CV_8U);
+        if (data && rows == r && cols == c && type_ == type) return;   // same shape: keep the storage (views included)
+        type_ = type;
+        const size_t bytes = (size_t)std::max(r, 0) * std::max(c, 0) * elemSize() + 16;
+        owner_ = std::shared_ptr<float>(new float[(bytes + 3) / 4], std::default_delete<float[]>());
         data = reinterpret_cast<unsigned char *>(owner_.get());
         rows = r;
         cols = c;
-        step = (size_t)c * sizeof(float);
+        step = (size_t)c * elemSize();
     }
     void create(Size s, int type) { create(s.height, s.width, type); }
 
     Size size() const { return Size(cols, rows); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
-    int type() const { return CV_32FC1; }
+    int type() const { return type_; }
+    int depth() const { return type_ & 7; }
+    int channels() const { return (type_ >> 3) + 1; }
+    size_t elemSize() const { return (size_t)channels() * (depth() == CV_8U ? 1 : 4); }
     template <typename T> T &at(int r, int c) { return *reinterpret_cast<T *>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T> const T &at(int r, int c) const { return *reinterpret_cast<const T *>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <typename T> T *ptr(int r = 0) { return reinterpret_cast<T *>(data + (size_t)r * step); }
@@ -93,7 +111,7 @@ public:
 
     Mat operator()(const Range &rr, const Range &cr) const {
         Mat v(*this);
-        v.data = data + (size_t)rr.start * step + (size_t)cr.start * sizeof(float);
+        v.data = data + (size_t)rr.start * step + (size_t)cr.start * elemSize();
         v.rows = rr.end - rr.start;
         v.cols = cr.end - cr.start;
         return v;
@@ -104,9 +122,9 @@ public:
     Mat colRange(const Range &r) const { return colRange(r.start, r.end); }
 
     void copyTo(Mat &dst) const {
-        if (dst.data == data && dst.rows == rows && dst.cols == cols && dst.step == step) return;
-        dst.create(rows, cols, CV_32FC1);
-        for (int y = 0; y < rows; y++) std::memmove(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols * sizeof(float));
+        if (dst.data == data && dst.rows == rows && dst.cols == cols && dst.step == step && dst.type_ == type_) return;
+        dst.create(rows, cols, type_);
+        for (int y = 0; y < rows; y++) std::memmove(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols * elemSize());
     }
     Mat clone() const {
         Mat m;
@@ -114,9 +132,35 @@ public:
         return m;
     }
     inline UMat getUMat(int flags) const;
+#ifdef W2X_CVSHIM_WITH_IMGPROC
+    // image.convertTo(image, CV_32F, 1/255.) and image.convertTo(image, CV_8U, 255.) (src/main.cpp:75,172); dst may be *this
+    void convertTo(Mat &dst, int rtype, double alpha = 1.0, double beta = 0.0) const {
+        assert(beta == 0.0 && channels() == 3 && step == (size_t)cols * elemSize());
+        (void)beta;
+        if ((rtype & 7) == CV_32F && depth() == CV_8U) {
+            Mat out(rows, cols, CV_32FC3);
+            const float a = static_cast<float>(alpha);
+            const unsigned char *s = data;
+            float *d = out.ptr<float>();
+            for (size_t i = 0; i < (size_t)rows * cols * 3; i++) d[i] = static_cast<float>(s[i]) * a;
+            dst = out;
+        } else if ((rtype & 7) == CV_8U && depth() == CV_32F) {
+            assert(alpha == 255.0);
+            w2ximg::Image3f im(cols, rows);
+            std::memcpy(im.data.data(), data, im.data.size() * sizeof(float));
+            std::vector<uint8_t> u8 = w2ximg::to_u8(im);
+            Mat out(rows, cols, CV_8UC3);
+            std::memcpy(out.data, u8.data(), u8.size());
+            dst = out;
+        } else {
+            assert(!"convertTo: unsupported conversion in the shim");
+        }
+    }
+#endif
 
 private:
     std::shared_ptr<float> owner_;
+    int type_ = CV_32FC1;
 };
 
 class UMat {
@@ -224,6 +268,74 @@ inline void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int le
     }
     dst = out;
 }
+
+#ifdef W2X_CVSHIM_WITH_IMGPROC
+enum ImreadModes { IMREAD_COLOR = 1 };
+enum ColorConversionCodes { COLOR_RGB2YUV = 83, COLOR_YUV2RGB = 85 };
+enum InterpolationFlags { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2 };
+
+namespace shim_detail {
+inline w2ximg::Image3f to_image(const Mat &m) {
+    assert(m.type() == CV_32FC3);
+    w2ximg::Image3f im(m.cols, m.rows);
+    for (int y = 0; y < m.rows; y++) std::memcpy(&im.data[(size_t)y * m.cols * 3], m.ptr<float>(y), (size_t)m.cols * 3 * sizeof(float));
+    return im;
+}
+inline Mat from_image(const w2ximg::Image3f &im) {
+    Mat m(im.height, im.width, CV_32FC3);
+    std::memcpy(m.data, im.data.data(), im.data.size() * sizeof(float));
+    return m;
+}
+}  // namespace shim_detail
+
+// cv::imread(path, IMREAD_COLOR): 8-bit B,G,R; an empty Mat when the file cannot be read (src/main.cpp:74)
+inline Mat imread(const std::string &path, int /*flags*/ = IMREAD_COLOR) {
+    w2xio::Image8 im = w2xio::imread(path);
+    if (im.empty()) return Mat();
+    Mat m(im.height, im.width, CV_8UC3);
+    std::memcpy(m.data, im.bgr.data(), im.bgr.size());
+    return m;
+}
+inline bool imwrite(const std::string &path, const Mat &m) {
+    assert(m.type() == CV_8UC3 && m.step == (size_t)m.cols * 3);
+    return w2xio::imwrite(path, m.data, m.cols, m.rows);
+}
+inline void cvtColor(const Mat &src, Mat &dst, int code) {
+    w2ximg::Image3f im = shim_detail::to_image(src);
+    if (code == COLOR_RGB2YUV) w2ximg::rgb2yuv(im);
+    else if (code == COLOR_YUV2RGB) w2ximg::yuv2rgb(im);
+    else assert(!"cvtColor: unsupported code in the shim");
+    dst = shim_detail::from_image(im);
+}
+inline void resize(const Mat &src, Mat &dst, Size dsize, double /*fx*/ = 0, double /*fy*/ = 0, int interpolation = INTER_LINEAR) {
+    const w2ximg::Interp ip = interpolation == INTER_NEAREST ? w2ximg::NEAREST : interpolation == INTER_CUBIC ? w2ximg::CUBIC : w2ximg::LINEAR;
+    dst = shim_detail::from_image(w2ximg::resize(shim_detail::to_image(src), dsize.width, dsize.height, ip));
+}
+inline void split(const Mat &src, std::vector<Mat> &planes) {
+    assert(src.type() == CV_32FC3);
+    planes.clear();
+    for (int c = 0; c < 3; c++) {
+        Mat p(src.rows, src.cols, CV_32FC1);
+        for (int y = 0; y < src.rows; y++) {
+            const float *s = src.ptr<float>(y);
+            float *d = p.ptr<float>(y);
+            for (int x = 0; x < src.cols; x++) d[x] = s[3 * x + c];
+        }
+        planes.push_back(p);
+    }
+}
+inline void merge(const std::vector<Mat> &planes, Mat &dst) {
+    assert(planes.size() == 3);
+    Mat out(planes[0].rows, planes[0].cols, CV_32FC3);
+    for (int c = 0; c < 3; c++)
+        for (int y = 0; y < out.rows; y++) {
+            const float *s = planes[(size_t)c].ptr<float>(y);
+            float *d = out.ptr<float>(y);
+            for (int x = 0; x < out.cols; x++) d[3 * x + c] = s[x];
+        }
+    dst = out;
+}
+#endif  // W2X_CVSHIM_WITH_IMGPROC
 
 // std::cout << mat (Model::printWeightMatrix, debugging only): "[a, b, c;\n d, e, f]"
 inline std::ostream &operator<<(std::ostream &os, const Mat &m) {

@@ -101,7 +101,7 @@ struct CmdLine {
             }
         }
         for (auto &a : args)
-            if (a.required && !a.set) parse_error("Required argument missing: " + a.name, "Required argument missing: " + a.name);
+            if (a.required && !a.set) parse_error(" ", "Required argument missing: " + a.name);   // TCLAP: CmdLineParseException with argId " "
     }
     const std::string &get(const char *name) const {
         for (auto &a : args) if (a.name == name) return a.value;
