@@ -16,9 +16,11 @@ metric  Mpix/s = output pixels / time of the whole pass.
 value   inputs already resident in HBM, device entry point (w2x_convert_plane_device).
 e2e     same pass through the host-buffer C-ABI call (w2x_convert_plane): pinned host input,
         H2D and D2H copies inside the timed region.
---impl reference   the reference's own CPU arithmetic (OpenCV via cv2 driven exactly like
-        Model::filterWorker, oracle/ref_cv2.py; falls back to oracle/w2x_oracle.c if cv2 is
-        missing) on the host cores, one 512x512 block per step.
+--impl reference   the reference's own CPU code on the host cores, one 512x512 block per step:
+        oracle/_ref/libw2x_reference.so = the reference's src/modelHandler.cpp + src/convertRoutine.cpp
+        compiled against the OpenCV API shim (falls back to OpenCV's kernels through cv2 driven like
+        Model::filterWorker, then to oracle/w2x_oracle.c), with the most worker threads the
+        reference's own plane partition can use (32).
 """
 from __future__ import annotations
 
@@ -95,37 +97,73 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU path on the host cores
 # ---------------------------------------------------------------------------------------------------
+def reference_jobs():
+    """Worker threads for the reference's CPU path.  Model::filter gives each of nJob threads nOutputPlanes / nJob planes and
+    the remainder to the last one (src/modelHandler.cpp:46-65): with more jobs than output planes (32 on the narrowest layers)
+    every thread but the last gets ZERO planes and the layer runs serially, so 32 is the most parallel setting the
+    reference's own scheme supports (its default is -j 4)."""
+    return max(1, min(os.cpu_count() or 4, 32))
+
+
+_CPU_REF = {}
+
+
 def cpu_reference_block(n_job, repeats=1):
-    """One 512x512 block (498x498 output pixels) of the workload plane through the reference's CPU
-    path.  Returns (seconds per block, kind, description)."""
+    """One 512x512 block (498x498 output pixels) of the workload plane through the reference's CPU path.
+    Returns (seconds per block, kind, description).  Preference order:
+      1. oracle/_ref/libw2x_reference.so -- the reference's OWN src/modelHandler.cpp + src/convertRoutine.cpp compiled against
+         the OpenCV API shim (oracle/cvshim): its threads, its loops ("reference");
+      2. OpenCV's kernels through cv2, driven call-for-call like Model::filterWorker (oracle/ref_cv2.py, "port");
+      3. the scalar C restatement (oracle/w2x_oracle.c, "port").
+    W2X_BENCH_CPU=cv2|oracle forces one of the fallbacks."""
     from oracle import oracle
     x = oracle.seeded_plane(4096, 4096, 1, "uniform")[:498, :498]
-    try:
-        from oracle import ref_cv2
-        if ref_cv2.cv2 is None:
-            raise ImportError
-        om = oracle.OracleModel.golden(MODEL)
-        models = []
-        for w, b in zip(om.weights, om.biases):
-            models.append(ref_cv2.Model({"nInputPlane": w.shape[1], "nOutputPlane": w.shape[0], "kW": 3, "kH": 3,
-                                         "weight": w.astype(np.float64), "bias": b}))
-        fn = lambda: ref_cv2.convert_with_models(x, models, block_splitting=True, n_job=n_job)
-        desc = "OpenCV (cv2 %s) driven call-for-call like Model::filterWorker" % ref_cv2.cv2.__version__
-    except Exception:
-        om = oracle.OracleModel.golden(MODEL)
+    want = os.environ.get("W2X_BENCH_CPU", "")
+    om = oracle.OracleModel.golden(MODEL)
+    fn = kind = desc = None
+    if want in ("", "reference"):
+        try:
+            from oracle import reference_lib
+            if reference_lib.available():
+                if "ref" not in _CPU_REF:
+                    import tempfile
+                    path = os.path.join(tempfile.mkdtemp(prefix="w2x_bench_"), f"{MODEL}_model.json")
+                    om.write_json(path)                       # the golden weights in the reference's JSON format
+                    _CPU_REF["ref"] = reference_lib.ReferenceModels(path)
+                reference_lib.configure(n_job, 9)
+                rm = _CPU_REF["ref"]
+                fn = lambda: rm.convert(x, True)
+                kind, desc = "reference", ("the reference's own src/modelHandler.cpp + src/convertRoutine.cpp (compiled against the OpenCV API shim "
+                                           "oracle/cvshim: its loader, threads and loops; fp32 filter2D/add/max/min/scaleAdd restated, AVX2 auto-vectorised)")
+        except Exception:
+            fn = None
+    if fn is None and want in ("", "cv2", "reference"):
+        try:
+            from oracle import ref_cv2
+            if ref_cv2.cv2 is None:
+                raise ImportError
+            models = []
+            for w, b in zip(om.weights, om.biases):
+                models.append(ref_cv2.Model({"nInputPlane": w.shape[1], "nOutputPlane": w.shape[0], "kW": 3, "kH": 3,
+                                             "weight": w.astype(np.float64), "bias": b}))
+            fn = lambda: ref_cv2.convert_with_models(x, models, block_splitting=True, n_job=n_job)
+            kind, desc = "port", "OpenCV (cv2 %s) driven call-for-call like Model::filterWorker" % ref_cv2.cv2.__version__
+        except Exception:
+            fn = None
+    if fn is None:
         fn = lambda: om.convert(x, n_job=n_job)
-        desc = "oracle/w2x_oracle.c scalar restatement"
+        kind, desc = "port", "oracle/w2x_oracle.c scalar restatement"
     ts = []
     for _ in range(repeats):
         t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
-    return min(ts), "port", desc
+    return min(ts), kind, desc
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_job = os.cpu_count() or 4
+    n_job = reference_jobs()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_block(n_job)
     t0 = time.perf_counter()
@@ -135,7 +173,7 @@ def run_reference_arm(args):
         per.append(s)
     total = time.perf_counter() - t0
     mpix = 498 * 498 * args.steps / sum(per) / 1e6
-    sample = f"{args.steps} x one 512x512 block (498x498 output px) of the 4096x4096 plane; {desc}; -j {n_job}"
+    sample = f"{args.steps} x one 512x512 block (498x498 output px) of the 4096x4096 plane; {desc}; -j {n_job} of {os.cpu_count()} host threads (the reference's plane partition cannot use more, default -j 4)"
     line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -315,10 +353,10 @@ def run_ours(args):
                     "whole_pass_algorithmic_tflops": FLOP_PER_PIXEL * pix_total / (ms_step * 1e-3) / 1e12 / world}
         cpu = None
         if world == 1 and not args.no_cpu:
-            nj = os.cpu_count() or 4
+            nj = reference_jobs()
             s, kind, desc = cpu_reference_block(nj)
             cpu = {"value": 498 * 498 / s / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind,
-                   "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} (reference default -j 4)"}
+                   "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} of {os.cpu_count()} host threads (the reference's plane partition cannot use more; default -j 4)"}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
                 "dtype": ("f32" if args.engine == "fp32" else "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.precision == "f16x3"

@@ -188,27 +188,29 @@ inline void filter2D(const UMat &src, UMat &dst, int /*ddepth*/, const UMat &ker
     (void)borderType;
     const Mat &s = src.m, &k = kernel.m;
     const int ax = anchor.x < 0 ? k.cols / 2 : anchor.x, ay = anchor.y < 0 ? k.rows / 2 : anchor.y;
-    Mat out;
-    Mat &d = (dst.m.data == s.data) ? out : dst.m;       // never filter in place
-    d.create(s.rows, s.cols, CV_32FC1);
+    // replicate-padded copy once, then every tap is a contiguous (vectorisable) row sweep; per pixel the taps are still
+    // accumulated in row-major order starting from delta, one multiply and one add each (-ffp-contract=off)
+    const int pw = s.cols + k.cols - 1, ph = s.rows + k.rows - 1;
+    std::vector<float> pad((size_t)pw * ph);
+    for (int y = 0; y < ph; y++) {
+        const float *row = s.ptr<float>(std::min(std::max(y - ay, 0), s.rows - 1));
+        float *p = &pad[(size_t)y * pw];
+        for (int x = 0; x < pw; x++) p[x] = row[std::min(std::max(x - ax, 0), s.cols - 1)];
+    }
+    dst.m.create(s.rows, s.cols, CV_32FC1);              // (the padded copy makes in-place filtering safe)
     const float d0 = static_cast<float>(delta);
     for (int y = 0; y < s.rows; y++) {
-        float *o = d.ptr<float>(y);
-        for (int x = 0; x < s.cols; x++) {
-            float acc = d0;
-            for (int ky = 0; ky < k.rows; ky++) {
-                const int yy = std::min(std::max(y + ky - ay, 0), s.rows - 1);
-                const float *row = s.ptr<float>(yy);
-                const float *kr = k.ptr<float>(ky);
-                for (int kx = 0; kx < k.cols; kx++) {
-                    const int xx = std::min(std::max(x + kx - ax, 0), s.cols - 1);
-                    acc = acc + kr[kx] * row[xx];
-                }
+        float *o = dst.m.ptr<float>(y);
+        for (int x = 0; x < s.cols; x++) o[x] = d0;
+        for (int ky = 0; ky < k.rows; ky++) {
+            const float *kr = k.ptr<float>(ky);
+            for (int kx = 0; kx < k.cols; kx++) {
+                const float kv = kr[kx];
+                const float *p = &pad[(size_t)(y + ky) * pw + kx];
+                for (int x = 0; x < s.cols; x++) o[x] = o[x] + kv * p[x];
             }
-            o[x] = acc;
         }
     }
-    if (&d == &out) out.copyTo(dst.m);
 }
 
 inline void add(const UMat &a, const UMat &b, UMat &dst) {
