@@ -354,7 +354,12 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             nj = reference_jobs()
-            s, kind, desc = cpu_reference_block(nj)
+            try:
+                s, kind, desc = cpu_reference_block(nj)
+            except Exception as e:                      # never lose the GPU measurement to the baseline leg
+                os.environ["W2X_BENCH_CPU"] = "oracle"
+                s, kind, desc = cpu_reference_block(nj)
+                desc += f" (preferred baseline failed: {type(e).__name__}: {e})"
             cpu = {"value": 498 * 498 / s / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind,
                    "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} of {os.cpu_count()} host threads (the reference's plane partition cannot use more; default -j 4)"}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
