@@ -6,8 +6,10 @@
 // oracle/_ref/libw2x_reference.so when /root/reference is present; used by tests/test_reference_build.py to pin the
 // restated oracle (oracle/w2x_oracle.c) and the golden vectors against the reference's real control flow.
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <streambuf>
 #include <string>
 #include <vector>
@@ -66,6 +68,29 @@ int w2xr_convert(void *h, const float *in, int w, int hgt, long in_stride_floats
     Quiet q;
     cv::Mat src = wrap(in, w, hgt, in_stride_floats), dst;
     if (!w2xc::convertWithModels(src, dst, H->models, block_splitting != 0)) return -1;
+    if (dst.size().width != w || dst.size().height != hgt) return -2;
+    for (int y = 0; y < hgt; y++)
+        for (int x = 0; x < w; x++) out[(long)y * out_stride_floats + x] = dst.at<float>(y, x);
+    return 0;
+}
+// convertWithModels with the reference's progress output ("Iteration #k...", "start process block (c,r) ...",
+// src/convertRoutine.cpp:67,133-134) captured into `log` (NUL-terminated, truncated to cap): the processing order is
+// the observable trace of its block arithmetic.
+int w2xr_convert_log(void *h, const float *in, int w, int hgt, long in_stride_floats, float *out, long out_stride_floats, int block_splitting,
+                     char *log, int cap) {
+    Handle *H = static_cast<Handle *>(h);
+    std::ostringstream cap_os;
+    std::streambuf *old = std::cout.rdbuf(cap_os.rdbuf());
+    cv::Mat src = wrap(in, w, hgt, in_stride_floats), dst;
+    const bool ok = w2xc::convertWithModels(src, dst, H->models, block_splitting != 0);
+    std::cout.rdbuf(old);
+    if (log && cap > 0) {
+        const std::string t = cap_os.str();
+        const size_t n = std::min(t.size(), (size_t)cap - 1);
+        std::memcpy(log, t.data(), n);
+        log[n] = 0;
+    }
+    if (!ok) return -1;
     if (dst.size().width != w || dst.size().height != hgt) return -2;
     for (int y = 0; y < hgt; y++)
         for (int x = 0; x < w; x++) out[(long)y * out_stride_floats + x] = dst.at<float>(y, x);

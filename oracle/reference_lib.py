@@ -36,6 +36,7 @@ def lib():
         L.w2xr_config.argtypes = [C.c_int, C.c_int]
         L.w2xr_convert.argtypes = [C.c_void_p, fp, C.c_int, C.c_int, C.c_long, fp, C.c_long, C.c_int]
         L.w2xr_filter.argtypes = [C.c_void_p, C.c_int, fp, C.c_int, C.c_int, fp]
+        L.w2xr_convert_log.argtypes = [C.c_void_p, fp, C.c_int, C.c_int, C.c_long, fp, C.c_long, C.c_int, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -86,6 +87,18 @@ class ReferenceModels:
         if rc != 0:
             raise RuntimeError(f"convertWithModels failed (rc={rc})")
         return out
+
+    def convert_with_log(self, plane, block_splitting=True, cap=1 << 20):
+        """convertWithModels plus the text the reference printed to std::cout while doing it (layer and block progress)."""
+        x = np.ascontiguousarray(plane, np.float32)
+        h, w = x.shape
+        out = np.empty((h, w), np.float32)
+        fp = C.POINTER(C.c_float)
+        buf = C.create_string_buffer(cap)
+        rc = lib().w2xr_convert_log(self._h, x.ctypes.data_as(fp), w, h, w, out.ctypes.data_as(fp), w, int(bool(block_splitting)), buf, cap)
+        if rc != 0:
+            raise RuntimeError(f"convertWithModels failed (rc={rc})")
+        return out, buf.value.decode()
 
     def filter(self, layer, in_planes):
         """w2xc::Model::filter of one layer on planar [n_in][h][w] input"""

@@ -106,3 +106,37 @@ def test_shipped_model_files_equal_the_golden_weights(ref_models, oracle_mod):
         real = R.ReferenceModels(f"/root/reference/models/{name}_model.json")
         assert np.array_equal(real.convert(x, True), ref_models[name].convert(x, True)), name
         real.close()
+
+
+def _identity_model_json(path, n_layers=7):
+    """n_layers of 1 -> 1 planes, kernel = delta, bias 0: convertWithModels becomes the identity on positive input, cheap
+    enough to push the reference's block-split code through full-size planes."""
+    import json
+    layer = {"nInputPlane": 1, "nOutputPlane": 1, "kW": 3, "kH": 3, "weight": [[[[0, 0, 0], [0, 1, 0], [0, 0, 0]]]], "bias": [0.0]}
+    with open(path, "w") as f:
+        json.dump([layer] * n_layers, f)
+
+
+@pytest.mark.parametrize("w,h", [(512, 768), (513, 768), (768, 512), (499, 1), (1, 1), (1920, 1080), (3840, 2160), (4096, 4096), (1234, 3211)])
+def test_block_order_and_split_decision_of_the_reference_at_full_size(w2x, oracle_mod, tmp_path, w, h):
+    """BASELINE shapes through the reference's own convertWithModels with a 7-layer identity model: the split decision and
+    the (c, r) processing order it prints (src/convertRoutine.cpp:25-26,100-134) are the product's w2x_requires_splitting /
+    w2x_block_table, block for block; and the stitched output is the input (every pixel written exactly once)."""
+    import re
+    p = str(tmp_path / "identity.json")
+    _identity_model_json(p)
+    R.configure(4, 9)
+    rm = R.ReferenceModels(p)
+    x = oracle_mod.seeded_plane(w, h, 3, "uniform") + np.float32(0.25)
+    y, log = rm.convert_with_log(x, True)
+    rm.close()
+    assert np.array_equal(y, x)
+    blocks = [(int(c), int(r)) for c, r in re.findall(r"start process block \((\d+),(\d+)\)", log)]
+    assert (len(blocks) > 0) == w2x.requires_splitting(w, h)
+    if blocks:
+        tab, sc, sr = w2x.block_table(w, h, 7)
+        assert [(int(t[1]), int(t[0])) for t in tab] == blocks          # table rows are (r, c, ...): reference order = r outer, c inner
+        assert sc * sr == len(blocks)
+        assert log.count("Iteration #7...") == len(blocks)
+    else:
+        assert log.count("Iteration #7...") == 1
