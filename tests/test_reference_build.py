@@ -140,3 +140,39 @@ def test_block_order_and_split_decision_of_the_reference_at_full_size(w2x, oracl
         assert log.count("Iteration #7...") == len(blocks)
     else:
         assert log.count("Iteration #7...") == 1
+
+
+def test_block_arithmetic_against_the_reference_on_random_shapes(w2x, oracle_mod, tmp_path):
+    """Seeded random plane sizes x block sizes 2^5..2^9: the reference's own split decision and block order (traced through
+    its progress output with the identity model) against w2x_requires_splitting / w2x_block_table -- including planes
+    thinner than a block, last blocks of 1 row / column, and sizes exactly at the split threshold."""
+    import re
+    p = str(tmp_path / "identity.json")
+    _identity_model_json(p)
+    rm = R.ReferenceModels(p)
+    rng = np.random.default_rng(2024)
+    cases = []
+    for exp in (5, 6, 7, 9):
+        b = 1 << exp
+        for _ in range(8):
+            cases.append((exp, int(rng.integers(1, 6 * b)), int(rng.integers(1, 6 * b))))
+        thr = b * b * 3 // 2
+        cases += [(exp, thr // 8, 8), (exp, thr // 8 + 1, 8), (exp, b - 14, 3 * b), (exp, 2 * (b - 14) + 1, b)]   # at / just past the threshold, exact multiples of the stride
+    try:
+        for exp, w, h in cases:
+            if exp == 9 and w * h > 1500 * 1500:
+                w, h = min(w, 1500), min(h, 1500)
+            R.configure(4, exp)
+            w2x.set_block_size_exp2_square(exp)
+            x = oracle_mod.seeded_plane(w, h, exp, "uniform") + np.float32(0.25)
+            y, log = rm.convert_with_log(x, True)
+            assert np.array_equal(y, x), (exp, w, h)
+            blocks = [(int(c), int(r)) for c, r in re.findall(r"start process block \((\d+),(\d+)\)", log)]
+            assert (len(blocks) > 0) == w2x.requires_splitting(w, h), (exp, w, h)
+            if blocks:
+                tab, sc, sr = w2x.block_table(w, h, 7)
+                assert [(int(t[1]), int(t[0])) for t in tab] == blocks, (exp, w, h)
+    finally:
+        R.configure(4, 9)
+        w2x.set_block_size_exp2_square(9)
+        rm.close()
