@@ -176,3 +176,60 @@ def test_block_arithmetic_against_the_reference_on_random_shapes(w2x, oracle_mod
         R.configure(4, 9)
         w2x.set_block_size_exp2_square(9)
         rm.close()
+
+
+def _fmt_number(rng, v):
+    """one of the spellings a JSON writer may produce for the double v"""
+    k = int(rng.integers(0, 8))
+    if k == 0:
+        return repr(float(v))
+    if k == 1:
+        return "%.17g" % v
+    if k == 2:
+        return "%.20e" % v
+    if k == 3:
+        return ("%.12E" % v).replace("E-0", "E-").replace("E+0", "E+")
+    if k == 4:
+        return "%.25f" % v
+    if k == 5:
+        return ("%.15g" % v).replace("e-0", "e-")
+    if k == 6:
+        return "%.9g" % v              # fewer digits than fp32 needs: a different double, same test (both loaders see it)
+    return "%.30g" % v
+
+
+def test_json_number_parsing_agrees_with_the_reference_loader(w2x, oracle_mod, tmp_path):
+    """The product's loader (csrc/model.cpp: hand-written JSON reader, std::from_chars, double -> float) against the
+    reference's (picojson + strtod, src/modelHandler.cpp:74-115) on model files whose numbers are spelt every which way
+    (long decimals, exponents, subnormal magnitudes, integers, -0), with shuffled keys and odd whitespace.  The weights
+    the product parsed are run through the oracle, the same file goes through the reference's own loader and
+    convertWithModels: one differing ulp in any weight or bias would show up in the output bits."""
+    rng = np.random.default_rng(77)
+    dims = [(1, 3), (3, 2), (2, 1)]
+    x = oracle_mod.seeded_plane(23, 17, 5, "uniform")
+    R.configure(2, 9)
+    for trial in range(12):
+        layers = []
+        for (ci, co) in dims:
+            scale = 10.0 ** float(rng.integers(-3, 1))
+            w = rng.standard_normal((co, ci, 3, 3)) * scale
+            b = rng.standard_normal(co) * 0.1
+            if trial % 3 == 0:
+                w.flat[0], w.flat[1], w.flat[2], b[0] = 1.0, -0.0, 1e-42, 0.0          # integer-valued, negative zero, fp32-subnormal
+            wtxt = "[" + ",".join("[" + ",".join("[" + ",".join("[" + ", ".join(_fmt_number(rng, v) for v in row) + "]" for row in k) + "]" for k in o) + "]" for o in w) + "]"
+            btxt = "[" + ",\n ".join(_fmt_number(rng, v) for v in b) + "]"
+            items = [('"nInputPlane"', str(ci)), ('"nOutputPlane"', str(co)), ('"kW"', "3"), ('"kH"', "3.0" if trial % 2 else "3"), ('"weight"', wtxt), ('"bias"', btxt)]
+            order = rng.permutation(len(items))
+            sep = ["", " ", "\n", "\t  "][trial % 4]
+            layers.append("{" + ("," + sep).join(items[i][0] + sep + ":" + sep + items[i][1] for i in order) + "}")
+        path = str(tmp_path / f"fuzz{trial}.json")
+        with open(path, "w") as f:
+            f.write("[" + ",\n".join(layers) + "]\n")
+        m = w2x.Model.load_json(path)
+        ws, bs = zip(*[m.params(li) for li in range(len(dims))])
+        ours = oracle_mod.OracleModel(list(ws), list(bs)).convert(x, n_job=2)
+        rm = R.ReferenceModels(path)
+        ref = rm.convert(x, True)
+        rm.close()
+        assert np.array_equal(ours, ref), trial
+    R.configure(4, 9)
