@@ -195,7 +195,6 @@ def run_ours(args):
     w2x = w2x_loader.load()
     if not os.path.exists(w2x.lib_path()):
         raise SystemExit("libw2x_b200.so missing: run __graft_entry__.build() first (no fallback path exists)")
-    from oracle import oracle as oracle_mod   # model fixture + synthetic plane helpers only (never timed here)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,8 +210,10 @@ def run_ours(args):
             raise SystemExit("--strong needs the plane height to divide by the number of ranks")
         H = H // world                         # ONE size x size plane, cut into `world` row bands
     n_model = 7
-    om = oracle_mod.OracleModel.golden(MODEL)
-    model = w2x.Model.from_arrays(om.weights, om.biases)
+    # the shipped scale2.0x weights as committed fixtures (tests/golden/models, written by oracle/gen_golden.py from the reference's JSON)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "models", f"{MODEL}_model.npz"))
+    n_layers = int(z["n_layers"])
+    model = w2x.Model.from_arrays([z[f"w{i}"] for i in range(n_layers)], [z[f"b{i}"] for i in range(n_layers)])
     engine = {"auto": w2x.ENGINE_AUTO, "tc": w2x.ENGINE_TC, "fp32": w2x.ENGINE_FP32}[args.engine]
     ctx = w2x.Context(local, engine=engine)
     ctx.set_precision(w2x.PRECISION_F16_F8X2 if args.precision == "f8" else w2x.PRECISION_F16X3)
@@ -223,7 +224,7 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
 
     # this rank's band of the (H*world) x W plane, seeded per rank
-    host_in = torch.from_numpy(oracle_mod.seeded_plane(W, H, 1 + rank, "uniform")).pin_memory()
+    host_in = torch.from_numpy(np.random.default_rng(1 + rank).random((H, W), dtype=np.float32)).pin_memory()   # uniform [0,1) noise, SURVEY 8(d)
     host_out = torch.empty((H, W), dtype=torch.float32).pin_memory()
     up, down = (rank - 1 if rank > 0 else None), (rank + 1 if rank < world - 1 else None)
     ra, rb = (n_model if up is not None else 0), (n_model if down is not None else 0)
