@@ -25,7 +25,7 @@ def cli(w2x):
 def imgtool(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("cpp") / "test_imgproc")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(PKG, "host"),
-                           os.path.join(ROOT, "tests", "cpp", "test_imgproc.cpp"), "-o", out, "-lz"])
+                           os.path.join(ROOT, "tests", "cpp", "test_imgproc.cpp"), "-o", out, "-lz", "-pthread"])
     return out
 
 
@@ -77,6 +77,29 @@ def test_yuv2rgb_to_u8_and_png_write_match_cv2(imgtool, tmp_path):
     ref = np.clip(np.rint(f * np.float32(255.0)), 0, 255).astype(np.uint8)   # convertTo(CV_8U, 255): cvRound + saturate
     diff = np.abs(got.astype(int) - ref.astype(int))
     assert diff.max() <= 1 and (diff > 0).mean() < 0.002              # only float-rounding ties may differ
+
+
+def test_row_parallel_paths_match_cv2_on_a_large_image(imgtool, tmp_path):
+    """640x400 pushes every imgproc routine past its single-thread threshold: the row-parallel sweeps must give the same
+    numbers (per-pixel arithmetic does not depend on the split)."""
+    w, h = 640, 400
+    bgr = _test_image(w, h, 21)
+    cv2.imwrite(str(tmp_path / "in.png"), bgr)
+    subprocess.check_call([imgtool, "yuv", str(tmp_path / "in.png"), str(tmp_path / "yuv.f32")])
+    got = np.fromfile(tmp_path / "yuv.f32", np.float32).reshape(bgr.shape)
+    yuv = cv2.cvtColor(bgr.astype(np.float32) * np.float32(1.0 / 255.0), cv2.COLOR_RGB2YUV)
+    assert np.abs(got - yuv).max() <= 2e-7
+    yuv.tofile(tmp_path / "s.f32")
+    for interp, flag, dw, dh, tol in (("nearest", cv2.INTER_NEAREST, 2 * w, 2 * h, 0), ("cubic", cv2.INTER_CUBIC, 2 * w, 2 * h, 2e-6),
+                                      ("linear", cv2.INTER_LINEAR, 480, 300, 2e-6)):
+        subprocess.check_call([imgtool, "resize", str(tmp_path / "s.f32"), str(w), str(h), str(dw), str(dh), interp, str(tmp_path / "d.f32")])
+        got = np.fromfile(tmp_path / "d.f32", np.float32).reshape(dh, dw, 3)
+        assert np.abs(got - cv2.resize(yuv, (dw, dh), interpolation=flag)).max() <= tol, interp
+    subprocess.check_call([imgtool, "rgb8", str(tmp_path / "s.f32"), str(w), str(h), str(tmp_path / "o.png")])
+    got8 = cv2.imread(str(tmp_path / "o.png"), cv2.IMREAD_COLOR)
+    ref8 = np.clip(np.rint(cv2.cvtColor(yuv, cv2.COLOR_YUV2RGB) * np.float32(255.0)), 0, 255).astype(np.uint8)
+    diff = np.abs(got8.astype(int) - ref8.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.002
 
 
 def test_cli_flag_surface_and_exit_codes(cli, tmp_path, json_models):

@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     main_cpp = os.path.join(HERE, "host", "main.cpp")
     if os.path.exists(main_cpp) and (force or _newer(CLI, [main_cpp, LIB] + _headers())):
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
-               main_cpp, "-o", CLI, "-L", HERE, "-lw2x_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+               main_cpp, "-o", CLI, "-L", HERE, "-lw2x_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"CLI build failed:\n{r.stdout}\n{r.stderr}")

@@ -145,6 +145,7 @@ int main(int argc, char **argv) {
     w2ximg::rgb2yuv(image);
 
     w2xc::modelUtility::getInstance().setNumberOfJobs(std::atoi(cmd.get("jobs").c_str()));   // :79
+    // (-j bounds the reference's filter threads; here it bounds the host image plumbing's row workers, the GPU does the filtering)
 
     // ===== Noise Reduction Phase ===== (:82-100)
     if (mode == "noise" || mode == "noise_scale") {
