@@ -97,6 +97,11 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU path on the host cores
 # ---------------------------------------------------------------------------------------------------
+def workload_text(W, H, world):
+    return (f"{W}x{H} fp32 Y plane per GPU, scale2.0x_model.json weights (7x conv3x3 + bias + leaky-ReLU 0.1), "
+            f"block_splitting=on; plane {W}x{H * world} in {world} row band(s)")
+
+
 def reference_jobs():
     """Worker threads for the reference's CPU path.  Model::filter gives each of nJob threads nOutputPlanes / nJob planes and
     the remainder to the last one (src/modelHandler.cpp:46-65): with more jobs than output planes (32 on the narrowest layers)
@@ -177,8 +182,8 @@ def run_reference_arm(args):
     line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "4096x4096 Y plane, scale2.0x_model (7x conv3x3+leaky-ReLU), bounded sample: one 512x512 block per step",
-                       "model": MODEL, "wall_s": total},
+            "config": {"workload": workload_text(args.size, args.size, max(1, args.gpus)), "weights": f"{MODEL}_model.json",
+                       "sample": "bounded: one 512x512 block (498x498 output px) of that plane per step, on the host cores", "wall_s": total},
             "cpu_baseline": {"value": mpix, "unit": "Mpix/s", "cores": n_job, "kind": kind, "sample": sample},
             "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -368,9 +373,8 @@ def run_ours(args):
                 "dtype": ("f32" if args.engine == "fp32" else "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.precision == "f16x3"
                           else "f16 + 2x e4m3 correction products, f32 accumulate (fp32-faithful to ~3e-5)"),
                 "data": "synthetic",
-                "config": {"workload": f"{W}x{H} fp32 Y plane per GPU, scale2.0x_model.json weights (7x conv3x3 + bias + leaky-ReLU 0.1), "
-                                       f"block_splitting=on; plane {W}x{H * world} in {world} row band(s)",
-                           "model": MODEL, "engine": args.engine, "halo_exchange": ("none" if world == 1 else "7 input rows per neighbour once, NCCL send/recv" if band is None
+                "config": {"workload": workload_text(W, H, world),
+                           "weights": f"{MODEL}_model.json", "engine": args.engine, "halo_exchange": ("none" if world == 1 else "7 input rows per neighbour once, NCCL send/recv" if band is None
                                              else "1 row of every intermediate activation per neighbour after every layer, NCCL send/recv"),
                            "l2": "no explicit flush: each step streams ~17 GB of activations per GPU, far beyond the 126 MB L2"},
                 "e2e": {"value": mpix_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
