@@ -154,7 +154,11 @@ int main() {
         run<2, 128, 2, true>("cta_group::2 M256 N128 e4m3 2 issuers", grid);
     }
     // the conv kernel's operand addressing (one halo box, taps = start offsets), 2 issuers, full grid
-    std::printf("halo-box operand addressing (A = 18x18 px box, SBO = 18*rowb, tap offsets), 2 issuers\n");
+    std::printf("halo-box operand addressing (A = 18x18 px box, SBO = 18*rowb, tap offsets), 2 issuers\n"
+                "NOTE: these rows are bounded by THIS loop's own per-MMA address arithmetic in the single issuing thread (~150 cycles per\n"
+                "MMA per issuer, i.e. ~75 with two) -- every shape reads the same.  That observation is what exposed the issue-side\n"
+                "bottleneck of the conv kernel (descriptor operands in vector registers -> ELECT/R2UR waterfall per MMA, DESIGN.md 3.2);\n"
+                "the pipe rates are the dense rows above.\n");
     run<1, 32, 2, false>("halo f16  rowb 64  SW64  N32  (L1 main)", sms, 64, 2, 4, 4, 64);
     run<1, 64, 2, false>("halo f16  rowb 64  SW64  N64  (L2 main)", sms, 64, 2, 4, 4, 64);
     run<1, 64, 2, false>("halo f16  rowb 128 SW128 N64  (L3 main)", sms, 128, 4, 2, 4, 64);
