@@ -38,7 +38,7 @@ def _headers():
     hs = [os.path.join(ROOT, "include", "w2x_b200.h")]
     for d in (CSRC, os.path.join(HERE, "host")):
         if os.path.isdir(d):
-            hs += [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".h", ".hpp"))]
+            hs += [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".h", ".hpp", ".cuh"))]
     return hs
 
 

@@ -1,0 +1,211 @@
+// tc_edge_kernels.cuh -- CUDA-core kernels at the edges of the stack: first layer, last layer, fused-last gather, layout converters
+// Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
+//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_edge_kernels.cuh
+// (pure code organisation: the generated SASS is the same as with one file).
+
+// ================================================================================================
+// First layer (Cin = 1), last layer (Cout = 1), layout converters -- CUDA-core, HBM-bound
+// ================================================================================================
+// First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
+// writes the NHWC frame the tcgen05 layers consume.  One thread per pixel, 32 x 8 pixels per block.
+//   * weights and biases travel as kernel parameters: the 9*COUT FFMAs per pixel take them straight from the constant
+//     bank (as shared-memory broadcasts they were one LDS per FFMA -- the LSU, not the FP32 pipe, bounded the kernel);
+//   * 32 channels at a time are converted into a swizzled shared-memory image of the block's 8 x 32 pixels and leave
+//     through TMA stores (the same path as the tcgen05 epilogue): a thread's own 16-byte stores sat at a 64-byte stride.
+template <int COUT>
+struct FirstParams {
+    float w[COUT * 9];    // [COUT][3][3]
+    float b[COUT];        // (float)bias
+};
+constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16 KB]  or  [xh 16 KB | xh8 8 KB | xl8 8 KB]
+
+template <int COUT, bool F8>
+__global__ void __launch_bounds__(256, 4)
+first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const __grid_constant__ CUtensorMap tmap_out,
+                   const __grid_constant__ CUtensorMap tmap_out8, const __grid_constant__ FirstParams<COUT> prm) {
+    extern __shared__ uint8_t first_smem[];
+    const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + wy;     // threads past the frame edge compute clamped copies; TMA clips them
+    float v[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+            int gy = min(max(y + ky - 1, 0), ph - 1), gx = min(max(x + kx - 1, 0), pw - 1);
+            v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
+        }
+    const uint32_t r = (uint32_t)threadIdx.x;                            // pixel index inside the block = row of the staged image
+    const uint32_t sw64 = (r >> 1) & 3u, sw32 = (r >> 2) & 1u;
+#pragma unroll 1
+    for (int cb = 0; cb < COUT / 32; cb++) {
+        if (cb) {   // the previous 32 channels' boxes must have left shared memory
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 4; c8++) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const float *w = prm.w + (cb * 32 + c8 * 8 + 2 * i + e) * 9;
+                    float t = w[0] * v[0];
+#pragma unroll
+                    for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
+                    float rr = (0.f + t) + prm.b[cb * 32 + c8 * 8 + 2 * i + e];
+                    a[e] = (fminf(rr, 0.f) * 0.1f + fmaxf(rr, 0.f)) * ACT_SCALE;
+                }
+                __half2 h = __floats2half2_rn(a[0], a[1]);
+                float2 hf = __half22float2(h);
+                hi[i] = *reinterpret_cast<uint32_t *>(&h);
+                if constexpr (F8) {
+                    constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+                    const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
+                    const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                    if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
+                    else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
+                } else {
+                    __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
+                    lo[i] = *reinterpret_cast<uint32_t *>(&l);
+                }
+            }
+            // 16-byte unit c8 of this pixel's 64-byte fp16 row (SWIZZLE_64B image)
+            sts128(tile + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            if constexpr (F8) {
+                // 8 bytes of the pixel's 32-byte e4m3 rows (SWIZZLE_32B images): unit c8/2, half c8%2
+                const uint32_t off = r * 32u + ((((uint32_t)c8 >> 1) ^ sw32) << 4) + ((uint32_t)c8 & 1u) * 8u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 16384u + off), "r"(lo[0]), "r"(lo[1]) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 24576u + off), "r"(lo[2]), "r"(lo[3]) : "memory");
+            } else {
+                sts128(tile + 16384u + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            if constexpr (F8)
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out8)), "r"(tile + 16384u), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // shared memory stays valid until the boxes are out
+}
+
+// Last layer: nOutputPlanes = 1.  fp32 arithmetic in the reference's association: per input plane a
+// 9-tap sum, planes added in ascending order, then bias and leaky-ReLU.  One thread per pixel.
+template <int CIN, bool F8>
+__global__ void __launch_bounds__(256)
+last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__restrict__ wgt, float bias, int crop,
+                  float *__restrict__ dst, long dst_stride) {
+    __shared__ float s_w[CIN * 9];
+    for (int i = threadIdx.x; i < CIN * 9; i += blockDim.x) s_w[i] = wgt[i];
+    __syncthreads();
+    const int x = crop + blockIdx.x * 32 + (threadIdx.x & 31), y = crop + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw - crop || y >= ph - crop) return;
+    const size_t plane_elems = (size_t)ph * pw * CIN;
+    const float inv = 1.0f / ACT_SCALE;
+    float acc = 0.f;
+    for (int c8 = 0; c8 < CIN / 8; c8++) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) t[e] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+                // frame reads outside [0,pw)x[0,ph) cannot happen: crop >= 1 keeps the 3x3 window inside
+                const size_t pixo = ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * CIN + c8 * 8;
+                const __half *ph_ = in + pixo;
+                uint4 uh = __ldg(reinterpret_cast<const uint4 *>(ph_));
+                const __half2 *h2 = reinterpret_cast<const __half2 *>(&uh);
+                uint4 ul = make_uint4(0, 0, 0, 0);
+                uint2 ul8 = make_uint2(0, 0);
+                if constexpr (F8) ul8 = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + 3 * plane_elems + pixo));
+                else ul = __ldg(reinterpret_cast<const uint4 *>(ph_ + plane_elems));
+                const __half2 *l2 = reinterpret_cast<const __half2 *>(&ul);
+                const __nv_fp8x2_storage_t *l8 = reinterpret_cast<const __nv_fp8x2_storage_t *>(&ul8);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float2 hf = __half22float2(h2[i]), lf;
+                    if constexpr (F8) {
+                        __half2_raw r = __nv_cvt_fp8x2_to_halfraw2(l8[i], __NV_E4M3);
+                        lf = __half22float2(*reinterpret_cast<__half2 *>(&r));
+                        lf.x *= 1.0f / (float)(1 << F8_A);
+                        lf.y *= 1.0f / (float)(1 << F8_A);
+                    } else lf = __half22float2(l2[i]);
+                    float a0 = (hf.x + lf.x) * inv, a1 = (hf.y + lf.y) * inv;
+                    const int tap = ky * 3 + kx;
+                    t[2 * i] = fmaf(s_w[(c8 * 8 + 2 * i) * 9 + tap], a0, t[2 * i]);
+                    t[2 * i + 1] = fmaf(s_w[(c8 * 8 + 2 * i + 1) * 9 + tap], a1, t[2 * i + 1]);
+                }
+            }
+#pragma unroll
+        for (int e = 0; e < 8; e++) acc += t[e];
+    }
+    float r = acc + bias;
+    dst[(long)(y - crop) * dst_stride + (x - crop)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
+}
+
+// Second half of the fused last layer: out(y,x) = leaky(bias + sum_t P[(y+ky-1, x+kx-1)][t]), taps in
+// row-major order, for the interior [crop, ph-crop) x [crop, pw-crop).
+__global__ void __launch_bounds__(256)
+last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias, int crop_x, int crop_top,
+                   int crop_bottom, float *__restrict__ dst, long dst_stride) {
+    const int x = crop_x + blockIdx.x * 32 + (threadIdx.x & 31), y = crop_top + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= pw - crop_x || y >= ph - crop_bottom) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++)
+            acc += __ldg(partial + ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * 12 + ky * 3 + kx);
+    const float r = acc + bias;
+    dst[(long)(y - crop_top) * dst_stride + (x - crop_x)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
+}
+
+__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8) {
+    const int pw = w + 2, ph = h + 2;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)pw * ph * C;
+    if (idx >= total) return;
+    int c = (int)(idx % C);
+    long pix = idx / C;
+    int x = (int)(pix % pw), y = (int)(pix / pw);
+    int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1);
+    float a = in[((long)c * h + sy) * w + sx] * ACT_SCALE;
+    __half hh = __float2half_rn(a);
+    out[idx] = hh;
+    if (f8) {
+        uint8_t *b = reinterpret_cast<uint8_t *>(out);
+        const float hf = __half2float(hh);
+        b[2 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
+        b[3 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
+    } else {
+        out[idx + total] = __float2half_rn(a - __half2float(hh));
+    }
+}
+
+__global__ void nhwc_to_planar_kernel(const __half *__restrict__ in, int C, int w, int h, float *__restrict__ out, int f8) {
+    const int pw = w + 2, ph = h + 2;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)w * h * C;
+    if (idx >= total) return;
+    int x = (int)(idx % w);
+    long r = idx / w;
+    int y = (int)(r % h), c = (int)(r / h);
+    long src = ((long)(y + 1) * pw + (x + 1)) * C + c;
+    long plane = (long)pw * ph * C;
+    float lo;
+    if (f8) {
+        __half_raw r = __nv_cvt_fp8_to_halfraw(reinterpret_cast<const uint8_t *>(in)[3 * plane + src], __NV_E4M3);
+        lo = __half2float(*reinterpret_cast<__half *>(&r)) * (1.0f / (float)(1 << F8_A));
+    } else lo = __half2float(in[src + plane]);
+    out[idx] = (__half2float(in[src]) + lo) * (1.0f / ACT_SCALE);
+}
