@@ -7,7 +7,7 @@ hardware units do with shared memory:
 
 with swz(a) = a ^ (((a >> 7) & (ROWB/16 - 1)) << 4) applied to the shared-memory ADDRESS
 (CUTLASS: Swizzle<B,4,3> o smem_ptr).  The test proves that the descriptor offsets used in
-csrc/kernels_tc.cu ((ky*18 + 8j + kx)*ROWB + 32*s, SBO = 18*ROWB) address exactly the 3x3-shifted
+csrc/tc_kernel.cuh ((ky*18 + 8j + kx)*ROWB + 32*s, SBO = 18*ROWB) address exactly the 3x3-shifted
 windows of the ONE staged 18x18 box -- i.e. that no per-tap reload is needed."""
 import numpy as np
 import pytest
@@ -49,7 +49,7 @@ def test_descriptor_fields_fit():
 
 
 def test_epilogue_staging_tile_is_the_tma_store_image():
-    """The epilogue (csrc/kernels_tc.cu::epilogue_store32) writes each lane's 32 channels of ONE pixel into the warp's
+    """The epilogue (csrc/tc_epilogue.cuh::epilogue_store32) writes each lane's 32 channels of ONE pixel into the warp's
     staging tile at 16-byte units XOR-ed with ((lane >> 1) & 3) (fp16 rows of 64 B) / ((lane >> 2) & 1) (e4m3 rows of
     32 B); the TMA store (SWIZZLE_64B / SWIZZLE_32B box {32 ch, 8 px, 4 rows}) reads box element e from
     swz(tile + logical_offset(e)).  Both must describe the same bytes: pixel (h, w) of the box = lane h*8 + w."""

@@ -55,7 +55,7 @@ cudaError_t launch_last_gather(const float *partial, int pw, int ph, float bias,
 cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bias, int crop_x, int crop_top,
                                   int crop_bottom, float *dst, long dst_stride_floats, cudaStream_t s);
 inline size_t partial_bytes(int Wp, int Hp) { return (size_t)Hp * Wp * 12 * sizeof(float); }
-constexpr int PROF_WORDS = 16;      // per-CTA profile record (see kernels_tc.cu PROF_*)
+constexpr int PROF_WORDS = 16;      // per-CTA profile record (see tc_config.cuh PROF_*)
 constexpr int PROF_MAX_CTAS = 256;
 // Last layer (Cout = 1): NHWC hi/lo frame -> fp32 plane, interior only: out(y,x) for
 // y in [crop, ph-crop), x in [crop, pw-crop) is written to dst[(y-crop)*stride + (x-crop)].
