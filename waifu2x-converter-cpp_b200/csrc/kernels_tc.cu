@@ -192,6 +192,14 @@ template <int COUT>
 static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
                                   cudaStream_t s, int f8) {
     static_assert(FIRST_TILE_BYTES + 1024 <= 48 * 1024, "the first layer's staging tile stays under the default dynamic shared memory limit");
+    // (under 48 KB no opt-in is required; the attribute is set anyway, once per process, as every other kernel of the engine does)
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
     FirstParams<COUT> prm;
     for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
     for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
