@@ -1,4 +1,8 @@
-"""parity_report.py -- max-abs error of every engine / precision against the reference goldens (run under gpurun)."""
+"""parity_report.py -- max-abs error of every engine / precision against the reference goldens and, at the BASELINE sizes,
+of the default precision over the WHOLE plane against the fp32 engine (run under gpurun):
+
+    python tools/parity_report.py > gpurun_out/parity_report.txt
+"""
 import os
 import sys
 
@@ -20,8 +24,11 @@ for name, kind in (("scale2.0x", "uniform"), ("scale2.0x", "smooth"), ("noise1",
     x = oracle.seeded_plane(256, 256, 0, kind)
     g = np.load(os.path.join(ROOT, "tests", "golden", f"cfg1_{name}_{kind}.npy"))
     print(f"  {name:10s} {kind:8s} " + "  ".join(f"{k}: {np.abs(c.convert_plane(m, x) - g).max():.2e}" for k, c in ctxs.items()))
-om = oracle.OracleModel.golden("scale2.0x")
-m = w2x.Model.from_arrays(om.weights, om.biases)
-x = oracle.seeded_plane(2048, 2048, 7, "uniform")
-ref = ctxs["fp32"].convert_plane(m, x)
-print("2048x2048 white noise, max-abs vs the fp32 engine: " + "  ".join(f"{k}: {np.abs(c.convert_plane(m, x) - ref).max():.2e}" for k, c in ctxs.items() if k != "fp32"))
+print("whole plane, white noise (default_rng), max-abs vs the fp32 engine (pinned to the oracle at 5e-6):")
+for size, seed in ((2048, 7), (4096, 1), (8192, 2)):
+    x = oracle.seeded_plane(size, size, seed, "uniform")
+    for name in oracle.MODEL_NAMES:
+        om = oracle.OracleModel.golden(name)
+        m = w2x.Model.from_arrays(om.weights, om.biases)
+        ref = ctxs["fp32"].convert_plane(m, x)
+        print(f"  {size}x{size} {name:10s} " + "  ".join(f"{k}: {np.abs(c.convert_plane(m, x) - ref).max():.2e}" for k, c in ctxs.items() if k != "fp32"), flush=True)

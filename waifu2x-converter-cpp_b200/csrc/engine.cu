@@ -35,6 +35,7 @@ struct DevModel {                       // device-resident copy of one model
     std::vector<std::vector<float>> b_host;   // the same on the host (the tcgen05 kernels take them as kernel parameters)
     std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
     std::vector<uint8_t *> pack8;       // same for the "f8" flavour (fp16 main product + e4m3 corrections)
+    std::vector<uint8_t *> strip, strip8;   // row-strip kernel images of the narrow layers (nullptr otherwise), both flavours
     std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
     std::vector<float> last_w_t;        // HOST: last layer's weights transposed to [9][Cin] (fused last layer, passed as kernel parameters)
 };
@@ -51,6 +52,7 @@ struct w2x_ctx {
     int walk = W2X_WALK_FUSED;
     bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
     int precision = W2X_PRECISION_F16_F8X2;   // default; W2X_PRECISION=f16x3 in the environment or w2x_ctx_set_precision() selects the 3 x fp16 scheme
+    int strip = 1;                     // 1 = run the narrow layers (Cin, Cout <= 64) on the row-strip kernel; w2x_debug_set_strip(0) = 16x16-tile kernel
     int pair = 1;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2); w2x_debug_set_pair(0) = single-CTA kernels
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -125,6 +127,8 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
     dm.b.assign(n, nullptr);
     dm.pack.assign(n, nullptr);
     dm.pack8.assign(n, nullptr);
+    dm.strip.assign(n, nullptr);
+    dm.strip8.assign(n, nullptr);
     dm.out_scale.assign(n, 1.f);
     for (size_t i = 0; i < n; i++) {
         const Layer &L = m->layers[i];
@@ -143,6 +147,12 @@ int get_dev_model(w2x_ctx *ctx, const w2x_model *m, DevModel **out) {
             dm.out_scale[i] = 1.0f / (P.wscale * tc::ACT_SCALE);
             CU_CHECK(cudaMalloc(&dm.pack8[i], P.bytes8.size()));
             CU_CHECK(cudaMemcpyAsync(dm.pack8[i], P.bytes8.data(), P.bytes8.size(), cudaMemcpyHostToDevice, ctx->stream));
+            if (!P.strip.empty()) {
+                CU_CHECK(cudaMalloc(&dm.strip[i], P.strip.size()));
+                CU_CHECK(cudaMemcpyAsync(dm.strip[i], P.strip.data(), P.strip.size(), cudaMemcpyHostToDevice, ctx->stream));
+                CU_CHECK(cudaMalloc(&dm.strip8[i], P.strip8.size()));
+                CU_CHECK(cudaMemcpyAsync(dm.strip8[i], P.strip8.data(), P.strip8.size(), cudaMemcpyHostToDevice, ctx->stream));
+            }
         }
     }
     if (m->tc_eligible) {
@@ -217,6 +227,27 @@ int ensure_tc(w2x_ctx *ctx) {
     return W2X_OK;
 }
 
+// One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).
+int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, const __half *in, __half *out, int pw, int ph,
+                    bool fused, bool profile) {
+    const Layer &L = m->layers[(size_t)li];
+    const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
+    const bool strip = ctx->strip && !fused && tc::strip_supported(L.n_in, L.n_out);
+    {
+        LayerTimer t(ctx, li);
+        CU_CHECK(tc::launch_tc_layer(in, f8 ? (const void *)dm->pack8[(size_t)li] : (const void *)dm->pack[(size_t)li],
+                                     strip ? (f8 ? (const void *)dm->strip8[(size_t)li] : (const void *)dm->strip[(size_t)li]) : nullptr,
+                                     dm->b_host[(size_t)li].data(), out, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
+                                     ctx->num_sms, ctx->stream,
+                                     profile && ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
+                                     fused ? dm->last_w_t.data() : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr, ctx->pair));
+    }
+    note_kernel(ctx, li, f8 ? (fused ? "tcgen05_f16+f8x2+last" : strip ? "tcgen05_f16+f8x2_strip" : "tcgen05_f16+f8x2")
+                            : (fused ? "tcgen05_f16x3+last" : strip ? "tcgen05_f16x3_strip" : "tcgen05_f16x3"));
+    ctx->launches++;
+    return W2X_OK;
+}
+
 // ---- convertWithModelsBasic on an already padded ROI ------------------------------------------
 // src: pw x ph fp32 region (row stride src_stride floats) that already contains the n-pixel ring.
 // dst: receives the (pw-2n) x (ph-2n) interior.
@@ -271,23 +302,9 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
     }
     const bool fuse = ctx->fuse_last && n >= 3 && !dm->last_w_t.empty();
     for (int li = 1; li + 1 < n; li++) {
-        const Layer &L = m->layers[(size_t)li];
         logf(ctx, "Iteration #%d...", li + 1);
-        CUtensorMap map, map8;
-        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, cur, L.n_in, pw, ph) : tc::make_act_tensor_map(&map, cur, L.n_in, pw, ph);
-        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, li);
-        const bool fused_here = fuse && li == n - 2;
-        {
-            LayerTimer t(ctx, li);
-            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)li] : (const void *)dm->pack[(size_t)li],
-                                         dm->b_host[(size_t)li].data(), nxt, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
-                                         ctx->num_sms, ctx->stream,
-                                         ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
-                                         fused_here ? dm->last_w_t.data() : nullptr, fused_here ? reinterpret_cast<float *>(nxt) : nullptr,
-                                         f8 ? &map8 : nullptr, ctx->pair));
-        }
-        note_kernel(ctx, li, f8 ? (fused_here ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused_here ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
-        ctx->launches++;
+        rc = launch_layer_tc(ctx, m, dm, li, cur, nxt, pw, ph, fuse && li == n - 2, true);
+        if (rc) return rc;
         std::swap(cur, nxt);
     }
     {
@@ -483,23 +500,12 @@ int w2x_band_step(w2x_band *band, int step) {
         CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8));
         band->cur = 0;
         note_kernel(ctx, 0, "first_1xN");
+        ctx->launches++;
     } else {
-        __half *in = band->act[band->cur], *out = band->act[band->cur ^ 1];
-        CUtensorMap map, map8;
-        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, in, L.n_in, band->pw, band->hf) : tc::make_act_tensor_map(&map, in, L.n_in, band->pw, band->hf);
-        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for layer %d", e, step);
-        const bool fused = step == band->n - 2;
-        {
-            LayerTimer t(ctx, step);
-            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)step] : (const void *)dm->pack[(size_t)step],
-                                         dm->b_host[(size_t)step].data(), out, L.n_in, L.n_out, band->pw, band->hf, dm->out_scale[(size_t)step], f8,
-                                         ctx->num_sms, ctx->stream, nullptr, fused ? dm->last_w_t.data() : nullptr,
-                                         fused ? reinterpret_cast<float *>(out) : nullptr, f8 ? &map8 : nullptr, ctx->pair));
-        }
-        note_kernel(ctx, step, f8 ? (fused ? "tcgen05_f16+f8x2+last" : "tcgen05_f16+f8x2") : (fused ? "tcgen05_f16x3+last" : "tcgen05_f16x3"));
+        int rc = launch_layer_tc(ctx, m, dm, step, band->act[band->cur], band->act[band->cur ^ 1], band->pw, band->hf, step == band->n - 2, false);
+        if (rc) return rc;
         band->cur ^= 1;
     }
-    ctx->launches++;
     band->last_step = step;
     return W2X_OK;
 }
@@ -622,6 +628,8 @@ void w2x_ctx_destroy(w2x_ctx *ctx) {
         for (auto p : kv.second.b) cudaFree(p);
         for (auto p : kv.second.pack) cudaFree(p);
         for (auto p : kv.second.pack8) cudaFree(p);
+        for (auto p : kv.second.strip) cudaFree(p);
+        for (auto p : kv.second.strip8) cudaFree(p);
     }
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->buf[i]);
@@ -728,6 +736,13 @@ W2X_API int w2x_debug_tc_profile_read(w2x_ctx *ctx, int layer, unsigned long lon
 W2X_API int w2x_debug_set_pair(w2x_ctx *ctx, int on) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
     ctx->pair = on != 0;
+    return W2X_OK;
+}
+
+// Probe switch (not part of the stable ABI): 1 = row-strip kernel for the narrow layers (default), 0 = the 16x16-tile kernel.
+W2X_API int w2x_debug_set_strip(w2x_ctx *ctx, int on) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    ctx->strip = on != 0;
     return W2X_OK;
 }
 
@@ -845,18 +860,10 @@ int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, con
         __half *fin = static_cast<__half *>(ctx->buf[0]), *fout = static_cast<__half *>(ctx->buf[1]);
         const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
         CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream, f8));
-        CUtensorMap map, map8;
-        int e = f8 ? tc::make_act_tensor_maps_f8(&map, &map8, fin, L.n_in, pw, ph) : tc::make_act_tensor_map(&map, fin, L.n_in, pw, ph);
-        if (e) return fail(W2X_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", e);
-        {
-            LayerTimer t(ctx, layer);
-            CU_CHECK(tc::launch_tc_layer(&map, f8 ? (const void *)dm->pack8[(size_t)layer] : (const void *)dm->pack[(size_t)layer],
-                                         dm->b_host[(size_t)layer].data(), fout, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)layer], f8,
-                                         ctx->num_sms, ctx->stream, nullptr, nullptr, nullptr, f8 ? &map8 : nullptr, ctx->pair));
-        }
+        rc = launch_layer_tc(ctx, model, dm, layer, fin, fout, pw, ph, false, false);
+        if (rc) return rc;
         CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream, f8));
-        note_kernel(ctx, layer, f8 ? "tcgen05_f16+f8x2" : "tcgen05_f16x3");
-        ctx->launches += 3;
+        ctx->launches += 2;
         return W2X_OK;
     }
     {

@@ -38,14 +38,17 @@ cudaError_t init_kernels();
 // `wgt` ([C][9]) and `bias` ((float)bias) are HOST pointers: they travel as kernel parameters.
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
                          const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0);
-// tcgen05 layer: in/out NHWC hi/lo frames (pw x ph); tmap describes `in`.
+// tcgen05 layer: in/out NHWC frames (pw x ph); the tensor maps are built inside.
 // `bias` is a HOST pointer to the layer's (float)bias values (they travel as kernel parameters).
-// f8 = 0: "f16x3" frames [hi][lo] + wpack = TcPack::bytes; f8 = 1: frames [xh][xh8][xl8], wpack = TcPack::bytes8 and
-// tmap_in8 describing the two e4m3 planes (see make_act_tensor_maps_f8).
-cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out,
+// f8 = 0: "f16x3" frames [hi][lo], wpack = TcPack::bytes, wstrip = TcPack::strip;
+// f8 = 1: frames [xh][xh8][xl8], wpack = TcPack::bytes8, wstrip = TcPack::strip8.
+// wstrip (device copy of the row-strip image, nullptr if the layer has none) selects the row-strip kernel for the
+// narrow layers (Cin, Cout <= 64, not fused); the choice depends on the layer shape only, never on the frame size.
+cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out,
                             int cin, int cout, int pw, int ph, float out_scale, int f8, int num_sms,
                             cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
-                            float *partial = nullptr, const CUtensorMap *tmap_in8 = nullptr, int pair = 0);
+                            float *partial = nullptr, int pair = 0);
+bool strip_supported(int cin, int cout);
 // Fused last layer: launch_tc_layer(..., last_w = HOST pointer to [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
 // tcgen05 layer emit per-pixel tap partials instead of activations; launch_last_gather sums the 3x3
 // neighbourhood of partials, adds the bias, applies the leaky-ReLU and writes the cropped fp32 plane.
@@ -66,9 +69,6 @@ cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *
 // NHWC hi/lo frame (h+2) x (w+2) -> planar fp32 [C][h][w] (interior)
 cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s, int f8 = 0);
 
-// Host: build the 4-D TMA descriptor {C, Wp, Hp, 2} with box {kc, HALO, HALO, 1}.
-int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp);
-int make_act_tensor_maps_f8(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp);
 }  // namespace tc
 
 }  // namespace w2x

@@ -50,6 +50,7 @@ namespace tc {
 #include "tc_epilogue.cuh"
 #include "tc_kernel.cuh"
 #include "tc_pair_kernel.cuh"
+#include "tc_strip_kernel.cuh"
 #include "tc_edge_kernels.cuh"
 
 // ================================================================================================
@@ -105,6 +106,13 @@ cudaError_t init_kernels() {
     if ((e = set_attr<ci, co>()) != cudaSuccess) return e;
     W2X_TC_SHAPES(X)
 #undef X
+#define X(ci, co)                                                                                                                          \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
+                                  StripCfg<ci, co, false>::SMEM_BYTES)) != cudaSuccess) return e;                                           \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                  StripCfg<ci, co, true>::SMEM_BYTES)) != cudaSuccess) return e;
+    X(32, 32) X(32, 64) X(64, 32) X(64, 64)
+#undef X
     return cudaSuccess;
 }
 
@@ -122,6 +130,7 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8,
 }
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
+static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h);
 static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w = 8, int box_h = 4);
 
 template <int CIN, bool FUSE, bool F8>
@@ -143,9 +152,58 @@ static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *tmap8
     return p.partial ? launch_pair_k<CIN, true, false>(tmap, tmap8, &tmapw, omaps, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, tmap8, &tmapw, omaps, p, grid, s);
 }
 
-cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const float *bias, __half *out, int cin,
+// ---- row-strip kernel (narrow layers) ----
+bool strip_supported(int cin, int cout) { return (cin == 32 || cin == 64) && (cout == 32 || cout == 64); }
+
+static int strip_seg_rows() {   // rows per work unit (tuning knob: W2X_STRIP_ROWS)
+    static const int v = [] {
+        const char *e = std::getenv("W2X_STRIP_ROWS");
+        const int n = e ? std::atoi(e) : 0;
+        return n >= 2 && n <= 4096 ? n : 32;
+    }();
+    return v;
+}
+
+template <int CIN, int COUT, bool F8>
+static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p, int num_sms, cudaStream_t s) {
+    using C = StripCfg<CIN, COUT, F8>;
+    const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+    tc_conv3x3_strip_kernel<CIN, COUT, F8><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    return cudaGetLastError();
+}
+
+#define W2X_STRIP_SHAPES(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
+
+static cudaError_t launch_strip(const __half *in, const void *wstrip, const float *bias, __half *out, int cin, int cout, int pw, int ph,
+                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof) {
+    StripParams p;
+    p.wpack = reinterpret_cast<const uint8_t *>(wstrip);
+    for (int i = 0; i < cout; i++) p.bias[i] = bias[i] * ACT_SCALE;
+    p.Wp = pw;
+    p.Hp = ph;
+    p.seg_rows = strip_seg_rows();
+    p.ncols = (pw + STRIP_W - 1) / STRIP_W;
+    p.n_units = p.ncols * ((ph + p.seg_rows - 1) / p.seg_rows);
+    p.out_scale = out_scale * ACT_SCALE;
+    p.prof = prof;
+    CUtensorMap maps[4];
+    if (make_act_maps(&maps[0], &maps[1], in, cin, pw, ph, f8 != 0, 32, STRIP_BOXW, 1)) return cudaErrorInvalidValue;
+    if (make_out_tensor_maps(&maps[2], &maps[3], out, cout, pw, ph, f8 != 0, 32, 1)) return cudaErrorInvalidValue;
+#define X(ci, co)                                                                                       \
+    if (cin == ci && cout == co)                                                                        \
+        return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, s);
+    W2X_STRIP_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial, const CUtensorMap *tmap_in8, int pair) {
+                            unsigned long long *prof, const float *last_w, float *partial, int pair) {
+    if (wstrip && !partial && strip_supported(cin, cout))
+        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof);
+    CUtensorMap tmap_in, tmap_in8;
+    if (make_act_maps(&tmap_in, &tmap_in8, in, cin, pw, ph, f8 != 0, act_kc(cin), HALO, HALO)) return cudaErrorInvalidValue;
     TcParams p;
     p.wpack = reinterpret_cast<const uint16_t *>(wpack);
     // ACT_SCALE (a power of two) is folded into the epilogue's affine step: leaky(16 v) = 16 leaky(v) exactly, so the
@@ -169,20 +227,18 @@ cudaError_t launch_tc_layer(const CUtensorMap *tmap_in, const void *wpack, const
         if (!last_w) return cudaErrorInvalidValue;
         for (int i = 0; i < 9 * cout; i++) p.last_w[i] = last_w[i] * (1.0f / ACT_SCALE);      // HOST pointer: [9][cout]
     }
-    if (f8 && !tmap_in8) return cudaErrorInvalidValue;
-    const CUtensorMap *t8 = tmap_in8 ? tmap_in8 : tmap_in;
     // the epilogue's TMA stores: 8x4-pixel x 32-channel boxes of this layer's output frame (fused layers store no frame)
     CUtensorMap omaps[2];
-    if (partial) { omaps[0] = *tmap_in; omaps[1] = *t8; }
+    if (partial) { omaps[0] = tmap_in; omaps[1] = tmap_in8; }
     else if (make_out_tensor_maps(&omaps[0], &omaps[1], out, cout, pw, ph, f8 != 0)) return cudaErrorInvalidValue;
     if (pair && cout == 128 && num_sms >= 2) {
 #define X(ci) \
-    if (cin == ci) return launch_pair<ci>(tmap_in, t8, omaps, p, num_sms, f8 != 0, s);
+    if (cin == ci) return launch_pair<ci>(&tmap_in, &tmap_in8, omaps, p, num_sms, f8 != 0, s);
         W2X_PAIR_CINS(X)
 #undef X
     }
 #define X(ci, co) \
-    if (cin == ci && cout == co) return launch_one<ci, co>(tmap_in, t8, omaps, p, num_sms, f8 != 0, s);
+    if (cin == ci && cout == co) return launch_one<ci, co>(&tmap_in, &tmap_in8, omaps, p, num_sms, f8 != 0, s);
     W2X_TC_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -327,46 +383,32 @@ static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *bas
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-int make_act_tensor_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp) {
+// Input frame as the layer kernels stage it: boxes of box_c channels x box_w pixels x box_h rows of ONE plane.
+//   f16x3: map16 over [2][Hp][Wp][C] fp16 (plane index = 4th coordinate); map8 = copy.
+//   F8:    frames are [xh fp16 [Hp][Wp][C]] [xh8 [Hp][Wp][C]] [xl8 [Hp][Wp][C]] (bytes 2 + 1 + 1 per element):
+//          map16 over the xh plane, map8 over the two e4m3 planes.
+// Swizzle = the box's inner extent in bytes (64 B / 128 B for fp16, 32 B / 64 B for e4m3).
+static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
-    const int kc = act_kc(C);
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(f8 ? 1 : 2)};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
+        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return (int)r;
+    }
+    if (!f8) { *map8 = *map16; return 0; }
+    const char *b8 = reinterpret_cast<const char *>(base) + (size_t)2 * Hp * Wp * C;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
+    CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(b8), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
-}
-
-// F8 frames: [xh fp16 [Hp][Wp][C]] [xh8 [Hp][Wp][C]] [xl8 [Hp][Wp][C]]  (bytes 2 + 1 + 1 per element)
-int make_act_tensor_maps_f8(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return -1;
-    const int kc = act_kc(C);
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 1};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
-        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return (int)r;
-    }
-    {
-        const char *b8 = reinterpret_cast<const char *>(base) + (size_t)2 * Hp * Wp * C;
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
-        cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
-        cuuint32_t box[4] = {(cuuint32_t)kc, HALO, HALO, 1};
-        CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(b8), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, kc == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return (int)r;
-    }
-    return 0;
 }
 
 }  // namespace tc

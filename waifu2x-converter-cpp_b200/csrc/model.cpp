@@ -385,6 +385,42 @@ static void pack_tc_layer_f8(const Layer &L, TcPack &P) {
             }
 }
 
+// Operand images of the row-strip kernel (csrc/tc_strip_kernel.cuh; narrow layers, Cin and Cout <= 64): per
+// (32-channel chunk c, tap column kx) ONE stage whose rows are ky-major, row = ky * n_out + n, so that an N = 3*n_out MMA
+// multiplies one staged input row by the three taps W(ky = 0..2, kx) at once:
+//   strip   (f16x3): [wh: 3*n_out rows x 64 B, SWIZZLE_64B][wl: same]
+//   strip8  (f8)   : [wh: 3*n_out rows x 64 B, SWIZZLE_64B][wh8 : 3*n_out rows x 32 B, SWIZZLE_32B][wl8: same]
+// Same values (wscale, fp16 / e4m3 roundings) as the tap-major packs above.
+static void pack_tc_layer_strip(const Layer &L, TcPack &P) {
+    if (L.n_in > 64 || L.n_out > 64) return;
+    const int nch = L.n_in / 32, nrows = 3 * L.n_out;
+    const size_t stage = (size_t)nrows * 128;
+    P.strip.assign((size_t)nch * 3 * stage, 0);
+    P.strip8.assign((size_t)nch * 3 * stage, 0);
+    const float up = std::ldexp(1.0f, F8_C), down = std::ldexp(1.0f, -F8_A);
+    for (int c = 0; c < nch; c++)
+        for (int kx = 0; kx < 3; kx++) {
+            uint8_t *s16 = P.strip.data() + ((size_t)c * 3 + kx) * stage, *s8 = P.strip8.data() + ((size_t)c * 3 + kx) * stage;
+            uint16_t *wh = reinterpret_cast<uint16_t *>(s16), *wl = reinterpret_cast<uint16_t *>(s16 + (size_t)nrows * 64);
+            uint16_t *wh_f8 = reinterpret_cast<uint16_t *>(s8);
+            uint8_t *wh8 = s8 + (size_t)nrows * 64, *wl8 = wh8 + (size_t)nrows * 32;
+            for (int ky = 0; ky < 3; ky++)
+                for (int n = 0; n < L.n_out; n++)
+                    for (int k = 0; k < 32; k++) {
+                        const size_t row = (size_t)ky * L.n_out + n;
+                        const float w = L.w[((size_t)n * L.n_in + (c * 32 + k)) * 9 + ky * 3 + kx] * P.wscale;   // exact (power of two)
+                        const uint16_t h = f32_to_f16_rn(w);
+                        const float hf = f16_to_f32(h);
+                        const size_t o16 = swizzled_offset(row * 64 + 2 * (size_t)k, 64) / 2, o8 = swizzle32(row * 32 + (size_t)k);
+                        wh[o16] = h;
+                        wl[o16] = f32_to_f16_rn(w - hf);
+                        wh_f8[o16] = h;
+                        wh8[o8] = f32_to_e4m3_rn(hf * down);
+                        wl8[o8] = f32_to_e4m3_rn((w - hf) * up);
+                    }
+        }
+}
+
 int finalize_model(w2x_model *m) {
     if (m->layers.empty()) return fail(W2X_ERR_MODEL, "Error : model has no layers");
     for (size_t i = 0; i < m->layers.size(); i++) {
@@ -408,6 +444,7 @@ int finalize_model(w2x_model *m) {
         if (okc(L.n_in) && okc(L.n_out)) {
             pack_tc_layer(L, m->tc[i]);
             pack_tc_layer_f8(L, m->tc[i]);
+            pack_tc_layer_strip(L, m->tc[i]);
         }
     }
     m->uid = g_uid.fetch_add(1);
@@ -492,6 +529,16 @@ W2X_API int w2x_debug_tc_pack(const w2x_model *model, int layer, const uint16_t 
     if (n_chunk) *n_chunk = P.n_chunk;
     if (wscale) *wscale = P.wscale;
     if (kblocks) *kblocks = P.kblocks;
+    return W2X_OK;
+}
+
+// f8 = 0: TcPack::strip ([wh | wl]), f8 = 1: TcPack::strip8 ([wh | wh8 | wl8]); empty for layers the row-strip kernel does not run.
+W2X_API int w2x_debug_tc_strip(const w2x_model *model, int layer, int f8, const uint8_t **data, size_t *n_bytes) {
+    if (!model || layer < 0 || layer >= (int)model->tc.size())
+        return w2x::fail(W2X_ERR_ARG, "w2x_debug_tc_strip: bad model or layer index");
+    const std::vector<uint8_t> &v = f8 ? model->tc[(size_t)layer].strip8 : model->tc[(size_t)layer].strip;
+    if (data) *data = v.data();
+    if (n_bytes) *n_bytes = v.size();
     return W2X_OK;
 }
 

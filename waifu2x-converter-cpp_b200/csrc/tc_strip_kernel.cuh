@@ -1,0 +1,314 @@
+// tc_strip_kernel.cuh -- tc_conv3x3_strip_kernel: the narrow layers (Cin, Cout <= 64) as row strips with the three ky taps
+// stacked along N
+// Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
+//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
+//
+// Why: an M128 x N x K16 tcgen05.mma fetches (128 + N) operand rows of 32 B from shared memory at 128 B/clk whatever N is
+// (profiles/r01_umma_microbench.txt), while its math takes N/2 clocks.  With N = Cout = 32 / 64 the fetch (40 / 48 clk)
+// hides the math (16 / 32 clk): the 16x16-tile kernel ran L1..L3 at 32 / 59 / 64 % tensor-pipe activity with the
+// shared-memory pipe at 80..95 %.  Here one A fetch feeds THREE taps:
+//
+//   * an M-tile is 128 consecutive pixels of ONE frame row r (a "strip"); tap kx is the descriptor start offset
+//     kx * ROWB into the staged row (130 pixels: the strip plus one pixel either side);
+//   * the B operand of tap column kx is [W(ky=0,kx) ; W(ky=1,kx) ; W(ky=2,kx)], N = 3 * Cout rows: input row r
+//     contributes W(ky) to output row r + 1 - ky, so the three N-blocks of one MMA belong to three different OUTPUT rows;
+//   * output rows own TMEM column blocks of Cout columns laid out in DESCENDING row order, block(n) = NB-1 - (n mod NB):
+//     the blocks of rows r+1, r, r-1 are then adjacent ascending columns and ONE N = 3*Cout MMA accumulates into all
+//     three.  The tensor core sums the ky taps; nothing is added in the epilogue.  Where the ring wraps (2 of NB strips)
+//     the MMA is issued as two (N = Cout + 2*Cout).
+//   * every accumulate flag is 1: the epilogue re-zeroes a block (tcgen05.st) right after draining it.
+//
+// Per MMA: N = 96 -> fetch 56 clk, math 48;  N = 192 -> fetch 80, math 96 (math-bound).  Each input row is staged once per
+// 128-pixel column (130/128 L2->SMEM amplification instead of 1.27x), all weights stay resident in shared memory
+// (36..144 KB), the frame is walked in units of `seg_rows` rows x 128 columns, static round-robin over the CTAs.
+//
+// Every output element still sees the same operations in the same order whatever the unit/strip geometry:
+//   for ky (= strips r-1, r, r+1): for 32-channel chunk c: for kx: [xh*wh k0, xh*wh k1, corrections]
+// so block-split, whole-plane, banded and multi-GPU runs stay bit-identical to each other.
+
+constexpr int STRIP_W = 128;            // pixels per strip = GEMM M
+constexpr int STRIP_BOXW = STRIP_W + 2;  // staged pixels per row
+
+template <int CIN, int COUT, bool F8>
+struct StripCfg {
+    static_assert((CIN == 32 || CIN == 64) && (COUT == 32 || COUT == 64), "strip kernel: narrow layers only");
+    static constexpr int NCH = CIN / 32;                                     // 32-channel chunks
+    static constexpr int ROWB = 64, ROWB8 = 32;                              // bytes per pixel per chunk: fp16 / e4m3 planes
+    static constexpr int A16_PLANE = STRIP_BOXW * ROWB, A16_PAD = (A16_PLANE + 511) / 512 * 512;      // SWIZZLE_64B repeats every 512 B
+    static constexpr int A8_PLANE = STRIP_BOXW * ROWB8, A8_PAD = (A8_PLANE + 255) / 256 * 256;        // SWIZZLE_32B repeats every 256 B
+    static constexpr int A_SLOT = F8 ? A16_PAD + 2 * A8_PAD : 2 * A16_PAD;   // [xh | xh8 | xl8]  or  [hi | lo]
+    static constexpr int A_TX = F8 ? A16_PLANE + 2 * A8_PLANE : 2 * A16_PLANE;
+    static constexpr int NROWS = 3 * COUT;                                   // B rows of one stage: ky-major
+    static constexpr int W_STAGE = NROWS * 128;                              // per (chunk, kx): [wh 64 B rows | wh8 | wl8 32 B rows] or [wh | wl]
+    static constexpr int W_BYTES = NCH * 3 * W_STAGE;
+    static constexpr int NB = 512 / COUT;                                    // accumulator blocks (output rows in flight) in TMEM
+    static constexpr int SMEM_MAX = 227 * 1024;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STG_WARP = 4096;
+    // two epilogue warp sets (alternate output rows) when the resident weights leave room for their staging tiles
+    static constexpr int EPI_SETS = (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - 8 * STG_WARP) / A_SLOT >= 3 ? 2 : 1;
+    static constexpr int STG_BYTES = EPI_SETS * 4 * STG_WARP;
+    static constexpr int A_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - STG_BYTES) / A_SLOT;
+    static constexpr int A_SLOTS = A_FIT > 6 ? 6 : A_FIT;
+    static constexpr int SMEM_BYTES = 1024 + W_BYTES + A_SLOTS * A_SLOT + STG_BYTES + BAR_BYTES;
+    static constexpr int THREADS = (4 + 4 * EPI_SETS) * 32;                  // warps: 0 A producer | 1 MMA issuer | 2 weights + TMEM | 3 idle | 4.. epilogue
+    static_assert(A_SLOTS >= 3, "need at least three staged rows");
+    static_assert((1 + 2 * A_SLOTS + 2 * NB) * 8 + 4 <= BAR_BYTES, "barrier area overflow");
+    static_assert(W_STAGE % 512 == 0 && A_SLOT % 512 == 0 && (NROWS * 64) % 256 == 0, "swizzle pattern alignment");
+    static_assert(NB % 2 == 0, "block ownership alternates between the epilogue sets");
+};
+
+struct StripParams {
+    const uint8_t *wpack;       // [chunk][kx] stages, exact shared-memory images (model.cpp: pack_tc_layer_strip)
+    float bias[64];             // (float)bias * ACT_SCALE
+    int Wp, Hp;
+    int ncols, n_units, seg_rows;   // units = 128-pixel columns x segments of seg_rows rows, unit u = seg * ncols + col
+    float out_scale;
+    unsigned long long *prof;
+};
+
+template <int CIN, int COUT, bool F8>
+__global__ void __launch_bounds__(StripCfg<CIN, COUT, F8>::THREADS, 1)
+tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
+                        const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out8, const StripParams p) {
+    using C = StripCfg<CIN, COUT, F8>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = smem_base;
+    const uint32_t a_base = w_base + C::W_BYTES;
+    const uint32_t stg_base = a_base + C::A_SLOTS * C::A_SLOT;
+    const uint32_t bar_base = stg_base + C::STG_BYTES;
+    const uint32_t w_full = bar_base;
+    auto a_full = [&](uint32_t i) { return bar_base + 8u * (1u + i); };
+    auto a_empty = [&](uint32_t i) { return bar_base + 8u * (1u + C::A_SLOTS + i); };
+    auto blk_full = [&](uint32_t i) { return bar_base + 8u * (1u + 2u * C::A_SLOTS + i); };
+    auto blk_empty = [&](uint32_t i) { return bar_base + 8u * (1u + 2u * C::A_SLOTS + C::NB + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (1u + 2u * C::A_SLOTS + 2u * C::NB);
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const bool prof_on = p.prof != nullptr;
+    unsigned long long *prof = prof_on ? p.prof + (size_t)blockIdx.x * PROF_N : nullptr;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (uint32_t i = 0; i < (uint32_t)C::A_SLOTS; i++) {
+            mbar_init(a_full(i), 1);
+            mbar_init(a_empty(i), 1);
+        }
+        for (uint32_t i = 0; i < (uint32_t)C::NB; i++) {
+            mbar_init(blk_full(i), 1);
+            mbar_init(blk_empty(i), 4);   // the four lane-quarter warps of the owning epilogue set
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_in);
+        prefetch_tmap(&tmap_out);
+        if constexpr (F8) {
+            prefetch_tmap(&tmap_in8);
+            prefetch_tmap(&tmap_out8);
+        }
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+
+    // unit u -> frame rows [y0, y1), column col
+    auto unit_of = [&](int u, int &col, int &y0, int &y1) {
+        const int seg = u / p.ncols;
+        col = u - seg * p.ncols;
+        y0 = seg * p.seg_rows;
+        y1 = min(y0 + p.seg_rows, p.Hp);
+    };
+    constexpr uint32_t NB = (uint32_t)C::NB;
+    auto blk_of = [](uint32_t n) { return NB - 1u - (n % NB); };   // descending: rows n, n+1 own adjacent blocks b, b-1
+
+    if (warp == 0) {
+        // ===================== A producer: one staged row (130 px x 32 ch, all planes) per (strip, chunk) =====================
+        uint32_t it = 0;
+        unsigned long long w_a = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            int col, y0, y1;
+            unit_of(u, col, y0, y1);
+            const int r_first = max(y0 - 1, 0), r_last = min(y1, p.Hp - 1);
+            const int x0 = col * STRIP_W - 1;
+            for (int r = r_first; r <= r_last; r++) {
+                for (int c = 0; c < C::NCH; c++, it++) {
+                    const uint32_t slot = it % (uint32_t)C::A_SLOTS, round = it / (uint32_t)C::A_SLOTS;
+                    mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
+                    mbar_arrive_expect_tx(a_full(slot), (uint32_t)C::A_TX);
+                    const uint32_t dst = a_base + slot * C::A_SLOT;
+                    tma_load_4d(dst, &tmap_in, a_full(slot), c * 32, x0, r, 0);
+                    if constexpr (F8) {
+                        tma_load_4d(dst + C::A16_PAD, &tmap_in8, a_full(slot), c * 32, x0, r, 0);                 // xh8
+                        tma_load_4d(dst + C::A16_PAD + C::A8_PAD, &tmap_in8, a_full(slot), c * 32, x0, r, 1);     // xl8
+                    } else {
+                        tma_load_4d(dst + C::A16_PAD, &tmap_in, a_full(slot), c * 32, x0, r, 1);                  // lo
+                    }
+                }
+            }
+        }
+        if (prof_on && lane == 0) prof[PROF_APROD_WAIT] += w_a;
+    } else if (warp == 2) {
+        // ===================== weights: every stage once, resident for the whole launch =====================================
+        mbar_arrive_expect_tx(w_full, (uint32_t)C::W_BYTES);
+        for (int s = 0; s < C::NCH * 3; s++)
+            bulk_load(w_base + (uint32_t)s * C::W_STAGE, p.wpack + (size_t)s * C::W_STAGE, C::W_STAGE, w_full);
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one converged warp, an elected lane issues) =====================================
+        constexpr uint32_t LO_FIXED = 1u << 16;
+        constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB, 4u) >> 32);     // 8-pixel groups are contiguous: SBO = 512 B
+        constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB8, 6u) >> 32);
+        constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(8 * 64, 4u) >> 32);
+        constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
+        auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
+        auto lo14 = [&](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | LO_FIXED; };
+        uint32_t a_it = 0, nrow = 0, n_strips = 0;
+        unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
+        const long long t_begin = clock64();
+        mbar_wait_prof(w_full, 0u, prof_on, w_bf);
+        tc_fence_after();
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            int col, y0, y1;
+            unit_of(u, col, y0, y1);
+            const int rows = y1 - y0;
+            const int r_first = max(y0 - 1, 0), r_last = min(y1, p.Hp - 1);
+            int next_new = 0, next_done = 0;                 // output rows (unit-relative) not yet acquired / not yet committed
+            for (int r = r_first; r <= r_last; r++, n_strips++) {
+                // input row r feeds output row r + 1 - ky with W(ky): the rows of this unit it reaches
+                const int ky_lo = max(0, r + 2 - y1), ky_hi = min(2, r + 1 - y0);
+                const int i_top = r + 1 - ky_lo - y0;         // unit-relative output row of ky_lo (the highest row index)
+                for (; next_new <= i_top; next_new++) {      // first contribution to these rows: their blocks must be drained + zeroed
+                    const uint32_t n = nrow + (uint32_t)next_new;
+                    mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
+                }
+                tc_fence_after();
+                // ky ascending = output row descending = block ascending (mod NB): at most two runs of adjacent blocks
+                const uint32_t b0 = blk_of(nrow + (uint32_t)i_top), nky = (uint32_t)(ky_hi - ky_lo + 1);
+                const uint32_t cnt0 = min(nky, NB - b0), cnt1 = nky - cnt0;
+                const uint32_t d0 = tmem_base + b0 * COUT, d1 = tmem_base;
+                const uint32_t row0 = (uint32_t)ky_lo * COUT, row1 = row0 + cnt0 * COUT;      // first B row of each run
+                const uint32_t id0 = make_idesc(128, (int)(cnt0 * COUT)), id1 = make_idesc(128, (int)(cnt1 * COUT));
+                for (int c = 0; c < C::NCH; c++, a_it++) {
+                    const uint32_t slot = a_it % (uint32_t)C::A_SLOTS;
+                    mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
+                    tc_fence_after();
+                    const uint32_t ab = a_base + slot * C::A_SLOT;
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        const uint32_t sb = w_base + (uint32_t)(c * 3 + kx) * C::W_STAGE;
+                        const uint32_t ah = lo14(ab + kx * C::ROWB);
+#pragma unroll
+                        for (int s = 0; s < 2; s++) {
+                            const uint32_t cnt = s ? cnt1 : cnt0;
+                            if (cnt == 0) continue;
+                            const uint32_t d = s ? d1 : d0, idesc = s ? id1 : id0, brow = s ? row1 : row0;
+                            const uint32_t bh = lo14(sb + brow * 64u);
+                            umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bh), idesc, 1u);
+                            umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
+                            if constexpr (F8) {
+                                const uint32_t a8h = lo14(ab + C::A16_PAD + kx * C::ROWB8), a8l = lo14(ab + C::A16_PAD + C::A8_PAD + kx * C::ROWB8);
+                                const uint32_t b8h = lo14(sb + C::NROWS * 64u + brow * 32u), b8l = lo14(sb + C::NROWS * 96u + brow * 32u);
+                                umma_f8(d, desc(A8_HI32, a8l), desc(B8_HI32, b8h), idesc, 1u);       // xl8 * wh8
+                                umma_f8(d, desc(A8_HI32, a8h), desc(B8_HI32, b8l), idesc, 1u);       // xh8 * wl8
+                            } else {
+                                const uint32_t al = lo14(ab + C::A16_PAD + kx * C::ROWB), bl = lo14(sb + C::NROWS * 64u + brow * 64u);
+                                umma_f16(d, desc(A_HI32, al), desc(B_HI32, bh), idesc, 1u);          // xl * wh
+                                umma_f16(d, desc(A_HI32, al + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
+                                umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bl), idesc, 1u);          // xh * wl
+                                umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bl + 2u), idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit_one(a_empty(slot));
+                }
+                // complete after this strip: output rows <= r - 1 (their ky = 2 tap), or every row after the unit's last strip
+                const int i_done = r == r_last ? rows - 1 : r - 1 - y0;
+                for (; next_done <= i_done; next_done++) umma_commit_one(blk_full(blk_of(nrow + (uint32_t)next_done)));
+            }
+            nrow += (uint32_t)rows;
+        }
+        if (prof_on && lane == 0) {
+            prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
+            prof[PROF_MMA_WAIT_ACC] += w_acc;
+            prof[PROF_MMA_WAIT_A] += w_af;
+            prof[PROF_MMA_WAIT_B] += w_bf;
+            prof[PROF_TILESETS] += n_strips;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: set e drains output rows n with n % EPI_SETS == e ===================================
+        const uint32_t q = (uint32_t)warp & 3u;                  // TMEM lane quarter = 32 pixels of the strip
+        const uint32_t e = ((uint32_t)warp - 4u) >> 2;
+        const uint32_t stg = stg_base + (e * 4u + q) * (uint32_t)C::STG_WARP;
+        const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
+        unsigned long long w_e = 0, work_e = 0;
+        // all accumulate flags are 1: hand every block over zeroed
+        for (uint32_t n = e; n < NB; n += (uint32_t)C::EPI_SETS) {
+#pragma unroll
+            for (int cb = 0; cb < COUT / 32; cb++) tmem_st32_zero(lane_base + blk_of(n) * COUT + (uint32_t)cb * 32u);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t n = e; n < NB; n += (uint32_t)C::EPI_SETS) mbar_arrive(blk_empty(blk_of(n)));
+        uint32_t nrow = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+            int col, y0, y1;
+            unit_of(u, col, y0, y1);
+            const int rows = y1 - y0;
+            const int gx0 = col * STRIP_W + (int)q * 32;
+            for (int i = 0; i < rows; i++) {
+                const uint32_t n = nrow + (uint32_t)i;
+                if (n % (uint32_t)C::EPI_SETS != e) continue;
+                const uint32_t blk = blk_of(n);
+                mbar_wait_prof(blk_full(blk), (n / NB) & 1u, prof_on, w_e);
+                const long long t_work = prof_on ? clock64() : 0;
+                tc_fence_after();
+                const uint32_t tcol = lane_base + blk * COUT;
+                uint32_t r[32];
+                tmem_ld32(tcol, r);
+#pragma unroll
+                for (int cb = 0; cb < COUT / 32; cb++) {
+                    float act[32];
+                    tmem_ld_wait_dep(r);
+#pragma unroll
+                    for (int k = 0; k < 32; k++) act[k] = __uint_as_float(r[k]);
+                    if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
+                    else {   // the row is in registers: zero its block and hand it back before the last conversion
+#pragma unroll
+                        for (int z = 0; z < COUT / 32; z++) tmem_st32_zero(tcol + (uint32_t)z * 32u);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(blk_empty(blk));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32; k++) {
+                        const float v = fmaf(act[k], p.out_scale, p.bias[cb * 32 + k]);     // = ACT_SCALE * (conv + bias)
+                        act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
+                    }
+                    if (gx0 < p.Wp) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, 0, stg, lane, gx0, y0 + i, cb);
+                }
+                if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
+            }
+            nrow += (uint32_t)rows;
+        }
+        bulk_wait_all();
+        if (prof_on && warp == 4 && lane == 0) {
+            prof[PROF_EPI_WAIT] += w_e;
+            prof[PROF_EPI_WORK] += work_e;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}

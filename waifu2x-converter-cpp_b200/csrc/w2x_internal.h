@@ -34,6 +34,9 @@ struct TcPack {
     //   [wh fp16: n_out rows x 64 B, SWIZZLE_64B][wh8 = e4m3(wh * 2^-F8_A): n_out rows x 32 B, SWIZZLE_32B]
     //   [wl8 = e4m3((w*wscale - wh) * 2^F8_C): n_out rows x 32 B, SWIZZLE_32B]
     std::vector<uint8_t> bytes8;
+    // Row-strip kernel images (Cin, Cout <= 64 only, else empty): [chunk][kx] stages with ky-major rows, see model.cpp
+    // pack_tc_layer_strip.  strip = f16x3 flavour [wh | wl], strip8 = f8 flavour [wh | wh8 | wl8].
+    std::vector<uint8_t> strip, strip8;
 };
 // Scale exponents of the e4m3 correction operands: activations store xl8 = e4m3((x16 - xh) * 2^F8_A) and
 // xh8 = e4m3(xh * 2^-F8_C); the weight side carries the inverse so both correction products land on the
