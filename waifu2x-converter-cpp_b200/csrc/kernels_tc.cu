@@ -186,6 +186,12 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
     p.n_units = p.ncols * ((ph + p.seg_rows - 1) / p.seg_rows);
     p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
+#ifdef W2X_EPI_EXPERIMENTS
+    static const int dbg_strip = std::getenv("W2X_DEBUG_STRIP") ? std::atoi(std::getenv("W2X_DEBUG_STRIP")) : 0;
+    p.dbg = dbg_strip;
+#else
+    p.dbg = 0;
+#endif
     CUtensorMap maps[4];
     if (make_act_maps(&maps[0], &maps[1], in, cin, pw, ph, f8 != 0, 32, STRIP_BOXW, 1)) return cudaErrorInvalidValue;
     if (make_out_tensor_maps(&maps[2], &maps[3], out, cout, pw, ph, f8 != 0, 32, 1)) return cudaErrorInvalidValue;

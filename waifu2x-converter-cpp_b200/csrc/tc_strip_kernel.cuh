@@ -65,6 +65,8 @@ struct StripParams {
     int ncols, n_units, seg_rows;   // units = 128-pixel columns x segments of seg_rows rows, unit u = seg * ncols + col
     float out_scale;
     unsigned long long *prof;
+    int dbg;                    // always 0 in product builds; -DW2X_EPI_EXPERIMENTS + W2X_DEBUG_STRIP (timing only, results WRONG):
+                                // 1 = no TMA stores, 2 = no staging either, 4 = no activation loads, 8 = no MMAs
 };
 
 template <int CIN, int COUT, bool F8>
@@ -143,6 +145,10 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 for (int c = 0; c < C::NCH; c++, it++) {
                     const uint32_t slot = it % (uint32_t)C::A_SLOTS, round = it / (uint32_t)C::A_SLOTS;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
+                    if (p.dbg & 4) {
+                        if (lane == 0) mbar_arrive(a_full(slot));
+                        continue;
+                    }
                     mbar_arrive_expect_tx(a_full(slot), (uint32_t)C::A_TX);
                     const uint32_t dst = a_base + slot * C::A_SLOT;
                     tma_load_4d(dst, &tmap_in, a_full(slot), c * 32, x0, r, 0);
@@ -208,7 +214,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
 #pragma unroll
                         for (int s = 0; s < 2; s++) {
                             const uint32_t cnt = s ? cnt1 : cnt0;
-                            if (cnt == 0) continue;
+                            if (cnt == 0 || (p.dbg & 8)) continue;
                             const uint32_t d = s ? d1 : d0, idesc = s ? id1 : id0, brow = s ? row1 : row0;
                             const uint32_t bh = lo14(sb + brow * 64u);
                             umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bh), idesc, 1u);
@@ -295,7 +301,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         const float v = fmaf(act[k], p.out_scale, p.bias[cb * 32 + k]);     // = ACT_SCALE * (conv + bias)
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
-                    if (gx0 < p.Wp) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, 0, stg, lane, gx0, y0 + i, cb);
+                    if (gx0 < p.Wp) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, y0 + i, cb);
                 }
                 if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
             }
