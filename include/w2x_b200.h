@@ -169,27 +169,83 @@ W2X_API int w2x_convert_band_device(w2x_ctx *ctx, const w2x_model *model, const 
                                     size_t in_stride_bytes, float *d_out, size_t out_stride_bytes);
 
 /* ---- multi-GPU row-band mode with a halo exchange BETWEEN LAYERS ------------------------------ */
-/* The variant BASELINE.json's north_star names: each rank keeps only its own rows (+1 halo row per
+/* The variant BASELINE.json's north_star names: each GPU keeps only its own rows (+1 halo row per
  * neighbour side) of every intermediate activation and trades ONE boundary row with each neighbour
- * after every layer (the caller moves the bytes, e.g. ncclSend/ncclRecv or torch.distributed P2P).
- * Sequence per band (n = layer count, all calls asynchronous on the context's stream):
+ * after every layer.  A session is one GPU's band; all calls are asynchronous on the context's stream.
+ *
+ * Exchange inside the library (the product path): the neighbours' frames are peer-mapped and
+ * w2x_band_exchange stores the boundary rows straight into them over NVLink -- one small kernel per
+ * layer (rows, a flag in the receiver's memory, wait for the neighbours' flags); no host round trip.
+ *     w2x_band_connect_local(band, up, down)        neighbours in the same process (cudaDeviceEnablePeerAccess), or
+ *     w2x_band_export(band, blob) + w2x_band_connect(band, up_blob, down_blob)   between processes (CUDA IPC):
+ *                                                   every rank exports, the blobs travel over any host channel
+ *     w2x_band_run(band, d_in, stride, d_out, stride)   one pass: own rows in -> own rows out
+ *         = w2x_band_load_rows; w2x_band_exchange(-1); { w2x_band_step(k); w2x_band_exchange(k) } k = 0..n-2; w2x_band_finish
+ * Every rank of a group must run the same sequence of exchanges (they are numbered).
+ *
+ * Exchange by the caller (cross-check path; ncclSend/ncclRecv, torch.distributed P2P):
  *     w2x_band_load(band, d_in, stride)            input: band rows + 1 real row per neighbour side
- *     for k in 0 .. n-2:  w2x_band_step(band, k);  w2x_band_halo(band, k, ...) -> exchange the segments
- *     w2x_band_finish(band, d_out, stride)         last layer's gather -> band_rows output rows
- * Step n-2 is the tcgen05 layer with the last layer folded into its epilogue; its halo segments are
- * rows of per-pixel tap partials instead of activations.  Requires the tcgen05 engine. */
+ *     for k in 0 .. n-2:  w2x_band_step(band, k);  w2x_band_halo(band, k, ...) -> move the segments
+ *     w2x_band_finish(band, d_out, stride)
+ * Step n-2 is the tcgen05 layer with the last layer folded into its epilogue; its rows are per-pixel tap
+ * partials instead of activations.  Requires the tcgen05 engine.  The layer kernels never store a band's
+ * halo rows, so a neighbour's row may arrive at any time after the previous exchange. */
 typedef struct w2x_band w2x_band;
 W2X_API int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows,
                             int has_up_neighbour, int has_down_neighbour, w2x_band **out_band);
 W2X_API void w2x_band_destroy(w2x_band *band);
 W2X_API int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes);
+W2X_API int w2x_band_load_rows(w2x_band *band, const float *d_in_own_rows, size_t in_stride_bytes);
 W2X_API int w2x_band_step(w2x_band *band, int step);
-/* Segments to exchange after `step` was queued: n_segments (<= 4) contiguous device ranges of
+/* Segments to move after `step` was queued: n_segments (<= 4) contiguous device ranges of
  * seg_bytes each per direction; send_* hold this rank's boundary row, recv_* its halo row.
  * Pointers for a missing neighbour are NULL.  Arrays must have room for 4 entries. */
 W2X_API int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up,
                           void **send_down, void **recv_down, size_t *seg_bytes);
 W2X_API int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes);
+#define W2X_BAND_BLOB_BYTES 320
+W2X_API int w2x_band_export(w2x_band *band, void *blob /* W2X_BAND_BLOB_BYTES */);
+W2X_API int w2x_band_connect(w2x_band *band, const void *up_blob, const void *down_blob);
+W2X_API int w2x_band_connect_local(w2x_band *band, w2x_band *up, w2x_band *down);
+W2X_API int w2x_band_exchange(w2x_band *band, int step /* -1 after w2x_band_load_rows */);
+W2X_API int w2x_band_run(w2x_band *band, const float *d_in_own_rows, size_t in_stride_bytes, float *d_out,
+                         size_t out_stride_bytes);
+
+/* ---- independent planes of one shape in one pass ---------------------------------------------- */
+/* The reference's block loop (src/convertRoutine.cpp:114-165) and BASELINE config 5 (64 x 512x512 tiles):
+ * n_tiles planes, each converted exactly like w2x_convert_plane(block_splitting = 0) would -- bit-identical --
+ * but stacked into ONE frame so that every layer is one launch for the whole batch.  HOST pointers. */
+W2X_API int w2x_convert_tiles(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles,
+                              float *const *out_tiles, int n_tiles, int width, int height,
+                              size_t in_stride_bytes, size_t out_stride_bytes);
+/* Same, returns once everything is queued (pinned host memory makes it truly asynchronous);
+ * w2x_ctx_synchronize completes it. */
+W2X_API int w2x_convert_tiles_async(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles,
+                                    float *const *out_tiles, int n_tiles, int width, int height,
+                                    size_t in_stride_bytes, size_t out_stride_bytes);
+/* Same on dense DEVICE batches d_in [n_tiles][height][width] -> d_out; asynchronous. */
+W2X_API int w2x_convert_tiles_device(w2x_ctx *ctx, const w2x_model *model, const float *d_in, float *d_out,
+                                     int n_tiles, int width, int height);
+
+/* ---- one process, N GPUs ---------------------------------------------------------------------- */
+/* The sibling of the reference's -j (src/main.cpp:58-60, modelUtility::setNumberOfJobs): N contexts driven by
+ * one host thread.  w2x_multi_convert_plane = w2x_convert_plane with the plane cut into N row bands and the
+ * per-layer halo exchange above between them (bit-identical to one GPU); planes too small to cut run on the
+ * first GPU.  w2x_multi_convert_tiles = w2x_convert_tiles with tile t on GPU t mod N (no exchange).
+ * devices == NULL means 0 .. n_devices-1. */
+typedef struct w2x_multi w2x_multi;
+W2X_API int w2x_multi_create(const int *devices, int n_devices, w2x_multi **out);
+W2X_API void w2x_multi_destroy(w2x_multi *multi);
+W2X_API int w2x_multi_device_count(const w2x_multi *multi);
+W2X_API w2x_ctx *w2x_multi_ctx(w2x_multi *multi, int index);   /* the i-th GPU's context (settings, timing) */
+W2X_API int w2x_multi_set_precision(w2x_multi *multi, int precision);
+W2X_API int w2x_multi_set_log(w2x_multi *multi, w2x_log_fn fn, void *user);
+W2X_API int w2x_multi_convert_plane(w2x_multi *multi, const w2x_model *model, const float *in, int width,
+                                    int height, size_t in_stride_bytes, float *out, size_t out_stride_bytes,
+                                    int block_splitting);
+W2X_API int w2x_multi_convert_tiles(w2x_multi *multi, const w2x_model *model, const float *const *in_tiles,
+                                    float *const *out_tiles, int n_tiles, int width, int height,
+                                    size_t in_stride_bytes, size_t out_stride_bytes);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* Number of kernels of THIS library launched by the context so far. */

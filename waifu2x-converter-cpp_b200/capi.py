@@ -33,8 +33,12 @@ ABI_SYMBOLS = (
     "w2x_ctx_set_scratch_limit", "w2x_convert_plane", "w2x_convert_plane_device", "w2x_filter_layer",
     "w2x_filter_layer_device", "w2x_convert_band_device", "w2x_ctx_launch_count", "w2x_ctx_set_timing",
     "w2x_ctx_layer_times", "w2x_ctx_layer_kernel_name", "w2x_band_create", "w2x_band_destroy", "w2x_band_load",
-    "w2x_band_step", "w2x_band_halo", "w2x_band_finish",
+    "w2x_band_step", "w2x_band_halo", "w2x_band_finish", "w2x_band_load_rows", "w2x_band_export", "w2x_band_connect",
+    "w2x_band_connect_local", "w2x_band_exchange", "w2x_band_run", "w2x_convert_tiles", "w2x_convert_tiles_async",
+    "w2x_convert_tiles_device", "w2x_multi_create", "w2x_multi_destroy", "w2x_multi_device_count", "w2x_multi_ctx",
+    "w2x_multi_set_precision", "w2x_multi_set_log", "w2x_multi_convert_plane", "w2x_multi_convert_tiles",
 )
+BAND_BLOB_BYTES = 320
 
 
 class W2xError(RuntimeError):
@@ -108,6 +112,25 @@ def lib():
     L.w2x_band_step.argtypes = [vp, ci]
     L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
     L.w2x_band_finish.argtypes = [vp, vp, cs]
+    L.w2x_band_load_rows.argtypes = [vp, vp, cs]
+    L.w2x_band_export.argtypes = [vp, vp]
+    L.w2x_band_connect.argtypes = [vp, vp, vp]
+    L.w2x_band_connect_local.argtypes = [vp, vp, vp]
+    L.w2x_band_exchange.argtypes = [vp, ci]
+    L.w2x_band_run.argtypes = [vp, vp, cs, vp, cs]
+    L.w2x_convert_tiles.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), ci, ci, ci, cs, cs]
+    L.w2x_convert_tiles_async.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), ci, ci, ci, cs, cs]
+    L.w2x_convert_tiles_device.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+    L.w2x_multi_create.argtypes = [C.POINTER(ci), ci, C.POINTER(vp)]
+    L.w2x_multi_destroy.argtypes = [vp]
+    L.w2x_multi_destroy.restype = None
+    L.w2x_multi_device_count.argtypes = [vp]
+    L.w2x_multi_ctx.argtypes = [vp, ci]
+    L.w2x_multi_ctx.restype = vp
+    L.w2x_multi_set_precision.argtypes = [vp, ci]
+    L.w2x_multi_set_log.argtypes = [vp, LOG_FN, vp]
+    L.w2x_multi_convert_plane.argtypes = [vp, vp, vp, ci, ci, cs, vp, cs, ci]
+    L.w2x_multi_convert_tiles.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), ci, ci, ci, cs, cs]
     L.w2x_debug_set_host_bands.argtypes = [vp, ci]
     L.w2x_debug_set_pair.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
@@ -318,6 +341,21 @@ class Context:
         _check(lib().w2x_convert_band_device(self._h, model._h, C.c_void_p(d_in), w, band_h, rows_above, rows_below,
                                              in_stride_bytes, C.c_void_p(d_out), out_stride_bytes))
 
+    # n independent planes of one shape in one batched pass (the reference's block loop; BASELINE config 5)
+    def convert_tiles(self, model: Model, tiles):
+        x = np.ascontiguousarray(tiles, np.float32)
+        if x.ndim != 3:
+            raise ValueError("tiles must be [n][h][w]")
+        n, h, w = x.shape
+        out = np.empty_like(x)
+        ip = (C.c_void_p * n)(*[x[i].ctypes.data for i in range(n)])
+        op = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        _check(lib().w2x_convert_tiles(self._h, model._h, ip, op, n, w, h, w * 4, w * 4))
+        return out
+
+    def convert_tiles_device(self, model: Model, d_in, d_out, n, w, h):
+        _check(lib().w2x_convert_tiles_device(self._h, model._h, C.c_void_p(d_in), C.c_void_p(d_out), n, w, h))
+
     # w2xc::Model::filter on host planes [n_in][h][w] -> [n_out][h][w]
     def filter_layer(self, model: Model, layer, in_planes):
         x = np.ascontiguousarray(in_planes, np.float32)
@@ -361,9 +399,68 @@ class Band:
     def step(self, k): _check(lib().w2x_band_step(self._h, k))
     def finish(self, d_out, out_stride_bytes): _check(lib().w2x_band_finish(self._h, C.c_void_p(d_out), out_stride_bytes))
 
+    def load_rows(self, d_in, in_stride_bytes): _check(lib().w2x_band_load_rows(self._h, C.c_void_p(d_in), in_stride_bytes))
+    def exchange(self, k): _check(lib().w2x_band_exchange(self._h, k))
+
+    def run(self, d_in, in_stride_bytes, d_out, out_stride_bytes):
+        """One pass of a connected band: own rows in, own rows out (exchanges inside the library, peer memory)."""
+        _check(lib().w2x_band_run(self._h, C.c_void_p(d_in), in_stride_bytes, C.c_void_p(d_out), out_stride_bytes))
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(BAND_BLOB_BYTES)
+        _check(lib().w2x_band_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, up_blob, down_blob):
+        """Map the neighbour ranks' sessions (CUDA IPC); blobs come from their export()."""
+        _check(lib().w2x_band_connect(self._h, up_blob, down_blob))
+
+    def connect_local(self, up, down):
+        _check(lib().w2x_band_connect_local(self._h, up._h if up is not None else None, down._h if down is not None else None))
+
     def halo(self, k):
         """-> list of (send_up, recv_up, send_down, recv_down, nbytes) device-pointer tuples (None = no neighbour)."""
         n, nb = C.c_int(), C.c_size_t()
         su, ru, sd, rd = ((C.c_void_p * 4)() for _ in range(4))
         _check(lib().w2x_band_halo(self._h, k, C.byref(n), su, ru, sd, rd, C.byref(nb)))
         return [(su[i], ru[i], sd[i], rd[i], nb.value) for i in range(n.value)]
+
+
+# ---- one process, N GPUs ------------------------------------------------------------------------
+class Multi:
+    """w2x_multi_*: N contexts driven by one host thread (row bands + peer-memory halo exchange, or tile-per-GPU)."""
+
+    def __init__(self, devices):
+        devs = list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        _check(lib().w2x_multi_create(arr, len(devs), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.w2x_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_precision(self, precision): _check(lib().w2x_multi_set_precision(self._h, precision))
+
+    def convert_plane(self, model: Model, plane, block_splitting=True, out=None):
+        x = np.ascontiguousarray(plane, np.float32)
+        h, w = x.shape
+        if out is None:
+            out = np.empty((h, w), np.float32)
+        _check(lib().w2x_multi_convert_plane(self._h, model._h, C.c_void_p(x.ctypes.data), w, h, x.strides[0],
+                                             C.c_void_p(out.ctypes.data), out.strides[0], int(bool(block_splitting))))
+        return out
+
+    def convert_tiles(self, model: Model, tiles, out=None):
+        x = np.ascontiguousarray(tiles, np.float32)
+        n, h, w = x.shape
+        if out is None:
+            out = np.empty_like(x)
+        ip = (C.c_void_p * n)(*[x[i].ctypes.data for i in range(n)])
+        op = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        _check(lib().w2x_multi_convert_tiles(self._h, model._h, ip, op, n, w, h, w * 4, w * 4))
+        return out

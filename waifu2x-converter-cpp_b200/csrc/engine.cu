@@ -22,84 +22,12 @@
 #include <string>
 #include <vector>
 
-#include "kernels.h"
-#include "w2x_internal.h"
+#include "engine_internal.h"
 
 using namespace w2x;
 
-namespace {
-
-struct DevModel {                       // device-resident copy of one model
-    std::vector<float *> w;             // per layer [Cout][Cin][9] fp32
-    std::vector<float *> b;             // per layer [Cout] fp32  ((float)bias, src/modelHandler.cpp:147)
-    std::vector<std::vector<float>> b_host;   // the same on the host (the tcgen05 kernels take them as kernel parameters)
-    std::vector<uint16_t *> pack;       // per layer tcgen05 operand image (nullptr if not eligible)
-    std::vector<uint8_t *> pack8;       // same for the "f8" flavour (fp16 main product + e4m3 corrections)
-    std::vector<uint8_t *> strip, strip8;   // row-strip kernel images of the narrow layers (nullptr otherwise), both flavours
-    std::vector<float> out_scale;       // 1 / (wscale * ACT_SCALE)
-    std::vector<float> last_w_t;        // HOST: last layer's weights transposed to [9][Cin] (fused last layer, passed as kernel parameters)
-};
-
-struct TimedSpan { int layer; cudaEvent_t e0, e1; };
-
-}  // namespace
-
-struct w2x_ctx {
-    int device = 0;
-    int num_sms = 0;
-    int cc_major = 0, cc_minor = 0;
-    int engine = W2X_ENGINE_AUTO;
-    int walk = W2X_WALK_FUSED;
-    bool fuse_last = true;             // fold the N->1 last layer into the preceding tcgen05 layer's epilogue
-    int precision = W2X_PRECISION_F16_F8X2;   // default; W2X_PRECISION=f16x3 in the environment or w2x_ctx_set_precision() selects the 3 x fp16 scheme
-    int strip = 1;                     // 1 = run the narrow layers (Cin, Cout <= 64) on the row-strip kernel; w2x_debug_set_strip(0) = 16x16-tile kernel
-    int pair = 1;                      // 1 = run the 128-wide layers on CTA pairs (cta_group::2); w2x_debug_set_pair(0) = single-CTA kernels
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    size_t scratch_limit = (size_t)16 << 30;
-    w2x_log_fn log = nullptr;
-    void *log_user = nullptr;
-    uint64_t launches = 0;
-    bool timing = false;
-    std::vector<TimedSpan> spans;
-    std::vector<cudaEvent_t> event_pool;
-    std::vector<std::string> layer_kernel;
-    std::map<uint64_t, DevModel> models;
-    // scratch
-    void *buf[2] = {nullptr, nullptr};
-    size_t buf_bytes[2] = {0, 0};
-    float *pad_buf = nullptr;
-    size_t pad_bytes = 0;
-    float *io_buf[2] = {nullptr, nullptr};   // device staging for the host-buffer entry points
-    size_t io_bytes[2] = {0, 0};
-    bool tc_ready = false;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host<->device copies of w2x_convert_plane overlap the compute stream
-    cudaEvent_t ev_in[8] = {}, ev_done[8] = {};
-    int host_bands = 0;                                   // 0 = automatic (up to 4 bands of >= 512 rows), 1 = no pipelining
-    unsigned long long *prof_buf = nullptr;   // [16 layers][PROF_MAX_CTAS][PROF_WORDS], debug profile
-};
-
-namespace {
-
-#define CU_CHECK(expr)                                                                              \
-    do {                                                                                            \
-        cudaError_t e__ = (expr);                                                                   \
-        if (e__ != cudaSuccess)                                                                     \
-            return fail(W2X_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, \
-                        cudaGetErrorString(e__));                                                   \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
+namespace w2x {
+namespace eng {
 
 int ensure(void **p, size_t *have, size_t need) {
     if (*have >= need) return W2X_OK;
@@ -178,26 +106,6 @@ cudaEvent_t take_event(w2x_ctx *ctx) {
     return e;
 }
 
-struct LayerTimer {   // brackets one layer launch with events when timing is on
-    w2x_ctx *ctx;
-    TimedSpan span{};
-    bool on;
-    LayerTimer(w2x_ctx *c, int layer) : ctx(c), on(c->timing) {
-        if (on) {
-            span.layer = layer;
-            span.e0 = take_event(c);
-            span.e1 = take_event(c);
-            cudaEventRecord(span.e0, c->stream);
-        }
-    }
-    ~LayerTimer() {
-        if (on) {
-            cudaEventRecord(span.e1, ctx->stream);
-            ctx->spans.push_back(span);
-        }
-    }
-};
-
 void note_kernel(w2x_ctx *ctx, int layer, const char *name) {
     if ((int)ctx->layer_kernel.size() <= layer) ctx->layer_kernel.resize((size_t)layer + 1);
     ctx->layer_kernel[(size_t)layer] = name;
@@ -229,7 +137,8 @@ int ensure_tc(w2x_ctx *ctx) {
 
 // One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).
 int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, const __half *in, __half *out, int pw, int ph,
-                    bool fused, bool profile) {
+                    bool fused, bool profile, int out_y0, int out_rows) {
+    if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     const Layer &L = m->layers[(size_t)li];
     const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
     const bool strip = ctx->strip && !fused && tc::strip_supported(L.n_in, L.n_out);
@@ -240,7 +149,8 @@ int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, cons
                                      dm->b_host[(size_t)li].data(), out, L.n_in, L.n_out, pw, ph, dm->out_scale[(size_t)li], f8,
                                      ctx->num_sms, ctx->stream,
                                      profile && ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
-                                     fused ? dm->last_w_t.data() : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr, ctx->pair));
+                                     fused ? dm->last_w_t.data() : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr, ctx->pair,
+                                     out_y0, out_rows));
     }
     note_kernel(ctx, li, f8 ? (fused ? "tcgen05_f16+f8x2+last" : strip ? "tcgen05_f16+f8x2_strip" : "tcgen05_f16+f8x2")
                             : (fused ? "tcgen05_f16x3+last" : strip ? "tcgen05_f16x3_strip" : "tcgen05_f16x3"));
@@ -251,10 +161,15 @@ int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, cons
 // ---- convertWithModelsBasic on an already padded ROI ------------------------------------------
 // src: pw x ph fp32 region (row stride src_stride floats) that already contains the n-pixel ring.
 // dst: receives the (pw-2n) x (ph-2n) interior.
+// n_tiles > 1 (tcgen05 engine with the fused last layer only): src holds n_tiles padded planes of pw x ph stacked vertically; the
+// layers run ONCE on the (n_tiles * ph)-row frame -- the seams pollute only the rings that are cropped anyway -- and tile t's
+// interior goes to dst + t * (ph - 2n) * dst_stride.
 int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const float *src, long src_stride, int pw,
-              int ph, float *dst, long dst_stride) {
+              int ph, float *dst, long dst_stride, int n_tiles = 1) {
     const int n = (int)m->layers.size();
     if (pw - 2 * n < 1 || ph - 2 * n < 1) return fail(W2X_ERR_ARG, "plane smaller than the model's receptive ring");
+    const int tile_ph = ph;
+    ph *= n_tiles;
     int maxc = 1;
     for (auto &L : m->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
     if (engine == W2X_ENGINE_FP32) {
@@ -312,10 +227,14 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         logf(ctx, "Iteration #%d...", n);
         LayerTimer t(ctx, n - 1);
         if (fuse) {
-            CU_CHECK(tc::launch_last_gather(reinterpret_cast<const float *>(cur), pw, ph, static_cast<float>(L.b[0]), n, dst,
-                                            dst_stride, ctx->stream));
+            for (int t = 0; t < n_tiles; t++) {
+                CU_CHECK(tc::launch_last_gather(reinterpret_cast<const float *>(cur) + (size_t)t * tile_ph * pw * 12, pw, tile_ph, static_cast<float>(L.b[0]), n,
+                                                dst + (long)t * (tile_ph - 2 * n) * dst_stride, dst_stride, ctx->stream));
+                if (t) ctx->launches++;
+            }
             note_kernel(ctx, n - 1, "last_gather");
         } else {
+            if (n_tiles != 1) return fail(W2X_ERR_UNSUPPORTED, "batched tiles need the fused last layer");
             CU_CHECK(tc::launch_last(cur, L.n_in, pw, ph, dm->w[(size_t)n - 1], static_cast<float>(L.b[0]), n, dst,
                                      dst_stride, ctx->stream, f8));
             note_kernel(ctx, n - 1, "last_Nx1");
@@ -396,185 +315,10 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
     return run_padded_plane(ctx, m, dm, engine, ctx->pad_buf, w, h, d_out, ostride);
 }
 
-}  // namespace
+}  // namespace eng
+}  // namespace w2x
 
-// ================================================================================================
-// Row-band session with per-layer halo exchange
-// ================================================================================================
-struct w2x_band {
-    w2x_ctx *ctx = nullptr;
-    const w2x_model *model = nullptr;
-    DevModel *dm = nullptr;
-    int width = 0, rows = 0, n = 0;
-    bool up = false, down = false;
-    int pt = 0, pb = 0;            // frame rows above / below the band: 1 (neighbour halo) or n (replicated image border)
-    int pw = 0, hf = 0;            // frame width / height
-    float *pad = nullptr;          // padded fp32 input frame
-    __half *act[2] = {nullptr, nullptr};
-    size_t act_bytes = 0;
-    int cur = 0;                   // act[cur] holds the output of the last queued step
-    int last_step = -1;
-};
-
-namespace {
-int band_check(w2x_band *b) {
-    if (!b || !b->ctx || !b->model) return fail(W2X_ERR_ARG, "NULL band session");
-    return W2X_OK;
-}
-}  // namespace
-
-extern "C" {
-
-int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows, int has_up, int has_down,
-                    w2x_band **out_band) {
-    if (check_ctx(ctx)) return W2X_ERR_ARG;
-    if (!model || !out_band || width < 1 || band_rows < 1) return fail(W2X_ERR_ARG, "w2x_band_create: bad argument");
-    *out_band = nullptr;
-    if (!model->tc_eligible || ctx->engine == W2X_ENGINE_FP32)
-        return fail(W2X_ERR_UNSUPPORTED, "w2x_band_create: the per-layer halo mode needs the tcgen05 engine and a 1->{32,64,128}..->1 model");
-    DeviceGuard g(ctx->device);
-    int rc = ensure_tc(ctx);
-    if (rc) return rc;
-    auto b = std::make_unique<w2x_band>();
-    b->ctx = ctx;
-    b->model = model;
-    rc = get_dev_model(ctx, model, &b->dm);
-    if (rc) return rc;
-    b->n = (int)model->layers.size();
-    b->width = width;
-    b->rows = band_rows;
-    b->up = has_up != 0;
-    b->down = has_down != 0;
-    b->pt = b->up ? 1 : b->n;
-    b->pb = b->down ? 1 : b->n;
-    b->pw = width + 2 * b->n;
-    b->hf = band_rows + b->pt + b->pb;
-    int maxc = 1;
-    for (auto &L : model->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
-    b->act_bytes = tc::act_bytes(maxc, b->pw, b->hf);
-    CU_CHECK(cudaMalloc(&b->pad, (size_t)b->pw * b->hf * sizeof(float)));
-    for (int i = 0; i < 2; i++) CU_CHECK(cudaMalloc(&b->act[i], b->act_bytes));
-    *out_band = b.release();
-    return W2X_OK;
-}
-
-void w2x_band_destroy(w2x_band *band) {
-    if (!band) return;
-    if (band->ctx) {
-        DeviceGuard g(band->ctx->device);
-        cudaStreamSynchronize(band->ctx->stream);
-        cudaFree(band->pad);
-        cudaFree(band->act[0]);
-        cudaFree(band->act[1]);
-    }
-    delete band;
-}
-
-int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
-    if (band_check(band)) return W2X_ERR_ARG;
-    if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load: bad input");
-    w2x_ctx *ctx = band->ctx;
-    DeviceGuard g(ctx->device);
-    const long stride = (long)(in_stride_bytes / 4);
-    const float *band0 = d_in + (band->up ? stride : 0);
-    CU_CHECK(launch_pad_replicate_xy(band0, band->width, band->rows, stride, band->n, band->pt, band->pb, band->up ? 1 : 0,
-                                     band->down ? 1 : 0, band->pad, ctx->stream));
-    ctx->launches++;
-    band->last_step = -1;
-    band->cur = 0;
-    return W2X_OK;
-}
-
-int w2x_band_step(w2x_band *band, int step) {
-    if (band_check(band)) return W2X_ERR_ARG;
-    if (step != band->last_step + 1 || step < 0 || step > band->n - 2)
-        return fail(W2X_ERR_ARG, "w2x_band_step: steps must run in order 0..%d (got %d after %d)", band->n - 2, step, band->last_step);
-    w2x_ctx *ctx = band->ctx;
-    DeviceGuard g(ctx->device);
-    const w2x_model *m = band->model;
-    DevModel *dm = band->dm;
-    const Layer &L = m->layers[(size_t)step];
-    const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
-    if (step == 0) {
-        LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8));
-        band->cur = 0;
-        note_kernel(ctx, 0, "first_1xN");
-        ctx->launches++;
-    } else {
-        int rc = launch_layer_tc(ctx, m, dm, step, band->act[band->cur], band->act[band->cur ^ 1], band->pw, band->hf, step == band->n - 2, false);
-        if (rc) return rc;
-        band->cur ^= 1;
-    }
-    band->last_step = step;
-    return W2X_OK;
-}
-
-int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up, void **send_down,
-                  void **recv_down, size_t *seg_bytes) {
-    if (band_check(band)) return W2X_ERR_ARG;
-    if (step != band->last_step || !n_segments || !send_up || !recv_up || !send_down || !recv_down || !seg_bytes)
-        return fail(W2X_ERR_ARG, "w2x_band_halo: call it for the step that was queued last");
-    const int n = band->n;
-    char *base = reinterpret_cast<char *>(band->act[band->cur]);
-    // every segment: `bytes` at  base + plane_off + row * pitch + in_row
-    struct Seg { size_t plane_off, pitch, in_row; } seg[4];
-    size_t bytes;
-    int nseg;
-    if (step == n - 2) {              // per-pixel tap partials [hf][pw][12] fp32
-        bytes = (size_t)band->pw * 12 * sizeof(float);
-        seg[0] = {0, bytes, 0};
-        nseg = 1;
-    } else {
-        const size_t C = (size_t)band->model->layers[(size_t)step].n_out, px = (size_t)band->pw * C, fr = px * band->hf;
-        if (band->ctx->precision == W2X_PRECISION_F16_F8X2) {   // frame [xh fp16][xh8][xl8]: four segments of pw*C bytes
-            bytes = px;
-            seg[0] = {0, 2 * px, 0};
-            seg[1] = {0, 2 * px, px};
-            seg[2] = {2 * fr, px, 0};
-            seg[3] = {3 * fr, px, 0};
-            nseg = 4;
-        } else {                                                 // frame [hi fp16][lo fp16]: two segments of pw*C*2 bytes
-            bytes = 2 * px;
-            seg[0] = {0, 2 * px, 0};
-            seg[1] = {2 * fr, 2 * px, 0};
-            nseg = 2;
-        }
-    }
-    *n_segments = nseg;
-    *seg_bytes = bytes;
-    for (int s = 0; s < 4; s++) {
-        const bool on = s < nseg;
-        char *pl = on ? base + seg[s].plane_off + seg[s].in_row : nullptr;
-        const size_t pitch = on ? seg[s].pitch : 0;
-        send_up[s] = on && band->up ? pl + pitch * 1 : nullptr;                                 // first owned row
-        recv_up[s] = on && band->up ? pl : nullptr;                                            // halo row above
-        send_down[s] = on && band->down ? pl + pitch * (size_t)(band->hf - 2) : nullptr;         // last owned row
-        recv_down[s] = on && band->down ? pl + pitch * (size_t)(band->hf - 1) : nullptr;         // halo row below
-    }
-    return W2X_OK;
-}
-
-int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes) {
-    if (band_check(band)) return W2X_ERR_ARG;
-    if (band->last_step != band->n - 2) return fail(W2X_ERR_ARG, "w2x_band_finish: steps 0..%d must have run", band->n - 2);
-    if (!d_out || out_stride_bytes % 4 || out_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_finish: bad output");
-    w2x_ctx *ctx = band->ctx;
-    DeviceGuard g(ctx->device);
-    const Layer &L = band->model->layers.back();
-    {
-        LayerTimer t(ctx, band->n - 1);
-        CU_CHECK(tc::launch_last_gather_xy(reinterpret_cast<const float *>(band->act[band->cur]), band->pw, band->hf,
-                                           static_cast<float>(L.b[0]), band->n, band->pt, band->pb, d_out,
-                                           (long)(out_stride_bytes / 4), ctx->stream));
-    }
-    note_kernel(ctx, band->n - 1, "last_gather");
-    ctx->launches++;
-    band->last_step = band->n - 1;
-    return W2X_OK;
-}
-
-}  // extern "C"
+using namespace w2x::eng;
 
 // ================================================================================================
 // C ABI
@@ -947,6 +691,80 @@ int w2x_ctx_layer_times(w2x_ctx *ctx, int max_layers, float *ms, int *launches, 
 const char *w2x_ctx_layer_kernel_name(const w2x_ctx *ctx, int layer) {
     if (!ctx || layer < 0 || layer >= (int)ctx->layer_kernel.size()) return "";
     return ctx->layer_kernel[(size_t)layer].c_str();
+}
+
+}  // extern "C"
+
+// ---- independent planes of one shape, one pass (the reference's block loop, src/convertRoutine.cpp:114-165) ------------------
+namespace {
+int convert_tiles_dev(w2x_ctx *ctx, const w2x_model *m, const float *d_in, float *d_out, int n_tiles, int w, int h) {
+    if (!m || !d_in || !d_out || n_tiles < 1 || w < 1 || h < 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad argument");
+    if (m->layers.front().n_in != 1 || m->layers.back().n_out != 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: model must map 1 plane to 1 plane");
+    DeviceGuard g(ctx->device);
+    const int engine = pick_engine(ctx, m);
+    if (engine < 0) return W2X_ERR_UNSUPPORTED;
+    DevModel *dm = nullptr;
+    int rc = get_dev_model(ctx, m, &dm);
+    if (rc) return rc;
+    const int n = (int)m->layers.size();
+    const int pw = w + 2 * n, ph = h + 2 * n;
+    int maxc = 1;
+    for (auto &L : m->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
+    const bool batch = engine == W2X_ENGINE_TC && ctx->fuse_last && n >= 3 && !dm->last_w_t.empty();
+    // tiles per pass: what the scratch limit allows (one frame of maxc channels, 4 bytes per element)
+    const size_t per_tile = (size_t)maxc * pw * ph * 4;
+    int group = batch ? (int)std::max<size_t>(1, std::min<size_t>((size_t)n_tiles, ctx->scratch_limit / per_tile)) : 1;
+    rc = ensure(reinterpret_cast<void **>(&ctx->pad_buf), &ctx->pad_bytes, (size_t)group * pw * ph * sizeof(float));
+    if (rc) return rc;
+    for (int t0 = 0; t0 < n_tiles; t0 += group) {
+        const int nt = std::min(group, n_tiles - t0);
+        for (int t = 0; t < nt; t++) {   // cv::copyMakeBorder per tile (src/convertRoutine.cpp:35)
+            CU_CHECK(launch_pad_replicate(d_in + (size_t)(t0 + t) * w * h, w, h, w, n, 0, 0, ctx->pad_buf + (size_t)t * pw * ph, ctx->stream));
+            ctx->launches++;
+        }
+        rc = run_basic(ctx, m, dm, engine, ctx->pad_buf, pw, pw, ph, d_out + (size_t)t0 * w * h, w, nt);
+        if (rc) return rc;
+    }
+    return W2X_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int w2x_convert_tiles_device(w2x_ctx *ctx, const w2x_model *model, const float *d_in, float *d_out, int n_tiles, int width, int height) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    return convert_tiles_dev(ctx, model, d_in, d_out, n_tiles, width, height);
+}
+
+int w2x_convert_tiles_async(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,
+                            int width, int height, size_t in_stride_bytes, size_t out_stride_bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!in_tiles || !out_tiles || n_tiles < 1 || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad argument");
+    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4) return fail(W2X_ERR_ARG, "w2x_convert_tiles: row stride smaller than a row");
+    DeviceGuard g(ctx->device);
+    const size_t tile_bytes = (size_t)width * height * sizeof(float);
+    for (int i = 0; i < 2; i++) {
+        int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], tile_bytes * (size_t)n_tiles);
+        if (rc) return rc;
+    }
+    for (int t = 0; t < n_tiles; t++) {
+        if (!in_tiles[t] || !out_tiles[t]) return fail(W2X_ERR_ARG, "w2x_convert_tiles: NULL tile %d", t);
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(ctx->io_buf[0]) + tile_bytes * (size_t)t, (size_t)width * 4, in_tiles[t], in_stride_bytes,
+                                   (size_t)width * 4, (size_t)height, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int rc = convert_tiles_dev(ctx, model, ctx->io_buf[0], ctx->io_buf[1], n_tiles, width, height);
+    if (rc) return rc;
+    for (int t = 0; t < n_tiles; t++)
+        CU_CHECK(cudaMemcpy2DAsync(out_tiles[t], out_stride_bytes, reinterpret_cast<char *>(ctx->io_buf[1]) + tile_bytes * (size_t)t, (size_t)width * 4,
+                                   (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, ctx->stream));
+    return W2X_OK;
+}
+
+int w2x_convert_tiles(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,
+                      int width, int height, size_t in_stride_bytes, size_t out_stride_bytes) {
+    int rc = w2x_convert_tiles_async(ctx, model, in_tiles, out_tiles, n_tiles, width, height, in_stride_bytes, out_stride_bytes);
+    int rc2 = ctx ? w2x_ctx_synchronize(ctx) : W2X_OK;
+    return rc ? rc : rc2;
 }
 
 }  // extern "C"

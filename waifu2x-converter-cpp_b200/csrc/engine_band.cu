@@ -1,0 +1,566 @@
+// engine_band.cu -- multi-GPU: row-band sessions with a halo exchange between layers, the peer-memory exchange itself, and
+// the one-process N-GPU driver (w2x_multi_*).
+//
+// BASELINE.json north_star: "the full-resolution plane is tiled with halo overlap across the GPUs of one box, halos
+// exchanged ... over NVLink between layers".  A plane is cut into contiguous row bands, one per GPU.  Every intermediate
+// activation of a band lives in a frame of band_rows + one halo row per neighbour side (+ the replicated n-pixel ring at
+// the image border, reference src/convertRoutine.cpp:35,96); after every layer each GPU stores its boundary row of the
+// fresh activation straight into the neighbour's halo row.  Two ways to move those rows:
+//   * w2x_band_exchange  -- inside the library: the neighbours' frames are peer-mapped (cudaDeviceEnablePeerAccess in one
+//                           process, CUDA IPC between the ranks of a torchrun job) and ONE small kernel per layer stores
+//                           the rows over NVLink, publishes a flag in the receiver's memory and waits for the neighbours'
+//                           flags.  No host round trip, no collective library, nothing between two layer launches but that
+//                           kernel.  w2x_band_run queues a whole pass; w2x_multi_* drives N GPUs from one host thread.
+//   * w2x_band_halo      -- the segments are handed to the caller (ncclSend/ncclRecv, torch.distributed P2P): the
+//                           cross-check path, bit-identical.
+// The layer kernels never store a band's halo rows (their output tensor maps exclude them), so a neighbour may deliver
+// its row as early as it likes.  Results are bit-identical to the single-GPU pass: every output pixel sees the same
+// operands in the same order.
+#include "engine_internal.h"
+
+using namespace w2x;
+using namespace w2x::eng;
+
+namespace {
+
+int band_check(w2x_band *b) {
+    if (!b || !b->ctx || !b->model) return fail(W2X_ERR_ARG, "NULL band session");
+    return W2X_OK;
+}
+
+// The rows traded after `step` (-1 = the padded input frame): up to 4 contiguous ranges per row, each `bytes` long, at
+//   base + plane_mul * (pw * C * frame_rows) + row * pitch + in_row        (evaluated in the owner's OR the neighbour's frame)
+struct RowSeg { size_t plane_mul, pitch, in_row; };
+int row_segments(const w2x_band *b, int step, RowSeg seg[4], size_t *bytes, size_t *px_out) {
+    const int n = b->n;
+    if (step == -1) {
+        *bytes = (size_t)b->pw * sizeof(float);
+        seg[0] = {0, *bytes, 0};
+        *px_out = 0;
+        return 1;
+    }
+    if (step == n - 2) {              // per-pixel tap partials [hf][pw][12] fp32
+        *bytes = (size_t)b->pw * 12 * sizeof(float);
+        seg[0] = {0, *bytes, 0};
+        *px_out = 0;
+        return 1;
+    }
+    const size_t px = (size_t)b->pw * (size_t)b->model->layers[(size_t)step].n_out;
+    *px_out = px;
+    if (b->ctx->precision == W2X_PRECISION_F16_F8X2) {   // frame [xh fp16][xh8][xl8]: four ranges of pw*C bytes
+        *bytes = px;
+        seg[0] = {0, 2 * px, 0};
+        seg[1] = {0, 2 * px, px};
+        seg[2] = {2, px, 0};
+        seg[3] = {3, px, 0};
+        return 4;
+    }
+    *bytes = 2 * px;                                       // frame [hi fp16][lo fp16]: two ranges of pw*C*2 bytes
+    seg[0] = {0, 2 * px, 0};
+    seg[1] = {2, 2 * px, 0};
+    return 2;
+}
+
+inline char *seg_at(char *base, int frame_rows, size_t px, const RowSeg &s, int row) {
+    return base + s.plane_mul * px * (size_t)frame_rows + s.pitch * (size_t)row + s.in_row;
+}
+
+constexpr uint32_t BLOB_MAGIC = 0x77327862u;   // "w2xb"
+struct BandBlob {                              // what w2x_band_export hands to the neighbour ranks
+    uint32_t magic;
+    int32_t pw, hf, n;
+    uint64_t act_bytes;
+    cudaIpcMemHandle_t pad, act0, act1, flags;
+};
+static_assert(sizeof(BandBlob) <= W2X_BAND_BLOB_BYTES, "blob does not fit W2X_BAND_BLOB_BYTES");
+
+}  // namespace
+
+extern "C" {
+
+int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows, int has_up, int has_down,
+                    w2x_band **out_band) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model || !out_band || width < 1 || band_rows < 1) return fail(W2X_ERR_ARG, "w2x_band_create: bad argument");
+    *out_band = nullptr;
+    if (!model->tc_eligible || ctx->engine == W2X_ENGINE_FP32)
+        return fail(W2X_ERR_UNSUPPORTED, "w2x_band_create: the per-layer halo mode needs the tcgen05 engine and a 1->{32,64,128}..->1 model");
+    DeviceGuard g(ctx->device);
+    int rc = ensure_tc(ctx);
+    if (rc) return rc;
+    auto b = std::make_unique<w2x_band>();
+    b->ctx = ctx;
+    b->model = model;
+    rc = get_dev_model(ctx, model, &b->dm);
+    if (rc) return rc;
+    b->n = (int)model->layers.size();
+    b->width = width;
+    b->rows = band_rows;
+    b->up = has_up != 0;
+    b->down = has_down != 0;
+    b->pt = b->up ? 1 : b->n;
+    b->pb = b->down ? 1 : b->n;
+    b->pw = width + 2 * b->n;
+    b->hf = band_rows + b->pt + b->pb;
+    int maxc = 1;
+    for (auto &L : model->layers) maxc = std::max(maxc, std::max(L.n_in, L.n_out));
+    b->act_bytes = tc::act_bytes(maxc, b->pw, b->hf);
+    auto cleanup = [&](cudaError_t e) {
+        cudaFree(b->pad);
+        cudaFree(b->act[0]);
+        cudaFree(b->act[1]);
+        cudaFree(b->flags);
+        cudaGetLastError();
+        return fail(W2X_ERR_NOMEM, "w2x_band_create: cudaMalloc failed (%s)", cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&b->pad, (size_t)b->pw * b->hf * sizeof(float))) != cudaSuccess) return cleanup(e);
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaMalloc(&b->act[i], b->act_bytes)) != cudaSuccess) return cleanup(e);
+    if ((e = cudaMalloc(&b->flags, 64)) != cudaSuccess) return cleanup(e);
+    if ((e = cudaMemset(b->flags, 0, 64)) != cudaSuccess) return cleanup(e);
+    *out_band = b.release();
+    return W2X_OK;
+}
+
+void w2x_band_destroy(w2x_band *band) {
+    if (!band) return;
+    if (band->ctx) {
+        DeviceGuard g(band->ctx->device);
+        cudaStreamSynchronize(band->ctx->stream);
+        for (auto &p : band->peer) {
+            if (!p.ipc) continue;
+            if (p.pad) cudaIpcCloseMemHandle(p.pad);
+            if (p.act[0]) cudaIpcCloseMemHandle(p.act[0]);
+            if (p.act[1]) cudaIpcCloseMemHandle(p.act[1]);
+            if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        }
+        cudaFree(band->pad);
+        cudaFree(band->act[0]);
+        cudaFree(band->act[1]);
+        cudaFree(band->flags);
+        cudaGetLastError();
+    }
+    delete band;
+}
+
+// d_in: the band's rows PLUS one real row per neighbour side (the caller fetched them); every frame row is written.
+int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load: bad input");
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const long stride = (long)(in_stride_bytes / 4);
+    const float *band0 = d_in + (band->up ? stride : 0);
+    CU_CHECK(launch_pad_replicate_xy(band0, band->width, band->rows, stride, band->n, band->pt, band->pb, band->up ? 1 : 0,
+                                     band->down ? 1 : 0, band->pad, ctx->stream));
+    ctx->launches++;
+    band->last_step = -1;
+    band->cur = 0;
+    return W2X_OK;
+}
+
+// d_in: the band's OWN rows only; the halo rows of the input frame are left to the neighbours (w2x_band_exchange(band, -1)).
+int w2x_band_load_rows(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load_rows: bad input");
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    CU_CHECK(launch_pad_replicate_xy(d_in, band->width, band->rows, (long)(in_stride_bytes / 4), band->n, band->pt, band->pb, 0, 0,
+                                     band->pad, ctx->stream, band->up ? 1 : 0, band->down ? 1 : 0));
+    ctx->launches++;
+    band->last_step = -1;
+    band->cur = 0;
+    return W2X_OK;
+}
+
+int w2x_band_step(w2x_band *band, int step) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (step != band->last_step + 1 || step < 0 || step > band->n - 2)
+        return fail(W2X_ERR_ARG, "w2x_band_step: steps must run in order 0..%d (got %d after %d)", band->n - 2, step, band->last_step);
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const w2x_model *m = band->model;
+    DevModel *dm = band->dm;
+    const Layer &L = m->layers[(size_t)step];
+    const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
+    // the halo rows belong to the neighbours: they are not part of this layer's store window
+    const int y0 = band->up ? 1 : 0, rows = band->hf - y0 - (band->down ? 1 : 0);
+    if (step == 0) {
+        LayerTimer t(ctx, 0);
+        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8, y0, rows));
+        band->cur = 0;
+        note_kernel(ctx, 0, "first_1xN");
+        ctx->launches++;
+    } else {
+        int rc = launch_layer_tc(ctx, m, dm, step, band->act[band->cur], band->act[band->cur ^ 1], band->pw, band->hf, step == band->n - 2, false, y0, rows);
+        if (rc) return rc;
+        band->cur ^= 1;
+    }
+    band->last_step = step;
+    return W2X_OK;
+}
+
+int w2x_band_halo(w2x_band *band, int step, int *n_segments, void **send_up, void **recv_up, void **send_down,
+                  void **recv_down, size_t *seg_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (step != band->last_step || step < 0 || !n_segments || !send_up || !recv_up || !send_down || !recv_down || !seg_bytes)
+        return fail(W2X_ERR_ARG, "w2x_band_halo: call it for the step that was queued last");
+    char *base = reinterpret_cast<char *>(band->act[band->cur]);
+    RowSeg seg[4];
+    size_t bytes, px;
+    const int nseg = row_segments(band, step, seg, &bytes, &px);
+    *n_segments = nseg;
+    *seg_bytes = bytes;
+    for (int s = 0; s < 4; s++) {
+        const bool on = s < nseg;
+        send_up[s] = on && band->up ? seg_at(base, band->hf, px, seg[s], 1) : nullptr;                       // first owned row
+        recv_up[s] = on && band->up ? seg_at(base, band->hf, px, seg[s], 0) : nullptr;                       // halo row above
+        send_down[s] = on && band->down ? seg_at(base, band->hf, px, seg[s], band->hf - 2) : nullptr;        // last owned row
+        recv_down[s] = on && band->down ? seg_at(base, band->hf, px, seg[s], band->hf - 1) : nullptr;        // halo row below
+    }
+    return W2X_OK;
+}
+
+int w2x_band_finish(w2x_band *band, float *d_out, size_t out_stride_bytes) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (band->last_step != band->n - 2) return fail(W2X_ERR_ARG, "w2x_band_finish: steps 0..%d must have run", band->n - 2);
+    if (!d_out || out_stride_bytes % 4 || out_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_finish: bad output");
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    const Layer &L = band->model->layers.back();
+    {
+        LayerTimer t(ctx, band->n - 1);
+        CU_CHECK(tc::launch_last_gather_xy(reinterpret_cast<const float *>(band->act[band->cur]), band->pw, band->hf,
+                                           static_cast<float>(L.b[0]), band->n, band->pt, band->pb, d_out,
+                                           (long)(out_stride_bytes / 4), ctx->stream));
+    }
+    note_kernel(ctx, band->n - 1, "last_gather");
+    ctx->launches++;
+    band->last_step = band->n - 1;
+    return W2X_OK;
+}
+
+// ---- peer wiring ---------------------------------------------------------------------------------------------------------
+int w2x_band_export(w2x_band *band, void *blob) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (!blob) return fail(W2X_ERR_ARG, "w2x_band_export: NULL blob");
+    DeviceGuard g(band->ctx->device);
+    BandBlob bl{};
+    bl.magic = BLOB_MAGIC;
+    bl.pw = band->pw;
+    bl.hf = band->hf;
+    bl.n = band->n;
+    bl.act_bytes = band->act_bytes;
+    CU_CHECK(cudaIpcGetMemHandle(&bl.pad, band->pad));
+    CU_CHECK(cudaIpcGetMemHandle(&bl.act0, band->act[0]));
+    CU_CHECK(cudaIpcGetMemHandle(&bl.act1, band->act[1]));
+    CU_CHECK(cudaIpcGetMemHandle(&bl.flags, band->flags));
+    std::memset(blob, 0, W2X_BAND_BLOB_BYTES);
+    std::memcpy(blob, &bl, sizeof bl);
+    return W2X_OK;
+}
+
+int w2x_band_connect(w2x_band *band, const void *up_blob, const void *down_blob) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if ((band->up && !up_blob) || (band->down && !down_blob)) return fail(W2X_ERR_ARG, "w2x_band_connect: a neighbour's blob is missing");
+    DeviceGuard g(band->ctx->device);
+    const void *blobs[2] = {band->up ? up_blob : nullptr, band->down ? down_blob : nullptr};
+    for (int side = 0; side < 2; side++) {
+        if (!blobs[side]) continue;
+        BandBlob bl;
+        std::memcpy(&bl, blobs[side], sizeof bl);
+        if (bl.magic != BLOB_MAGIC || bl.pw != band->pw || bl.n != band->n || bl.hf < 3)
+            return fail(W2X_ERR_ARG, "w2x_band_connect: the %s neighbour's session does not match (width / model)", side ? "down" : "up");
+        w2x_band::Peer &p = band->peer[side];
+        void *q = nullptr;
+        CU_CHECK(cudaIpcOpenMemHandle(&q, bl.pad, cudaIpcMemLazyEnablePeerAccess));
+        p.pad = static_cast<float *>(q);
+        CU_CHECK(cudaIpcOpenMemHandle(&q, bl.act0, cudaIpcMemLazyEnablePeerAccess));
+        p.act[0] = static_cast<char *>(q);
+        CU_CHECK(cudaIpcOpenMemHandle(&q, bl.act1, cudaIpcMemLazyEnablePeerAccess));
+        p.act[1] = static_cast<char *>(q);
+        CU_CHECK(cudaIpcOpenMemHandle(&q, bl.flags, cudaIpcMemLazyEnablePeerAccess));
+        p.flags = static_cast<unsigned *>(q);
+        p.hf = bl.hf;
+        p.ipc = true;
+    }
+    return W2X_OK;
+}
+
+int w2x_band_connect_local(w2x_band *band, w2x_band *up, w2x_band *down) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if ((band->up && band_check(up)) || (band->down && band_check(down))) return fail(W2X_ERR_ARG, "w2x_band_connect_local: a neighbour session is missing");
+    DeviceGuard g(band->ctx->device);
+    w2x_band *nb[2] = {band->up ? up : nullptr, band->down ? down : nullptr};
+    for (int side = 0; side < 2; side++) {
+        w2x_band *o = nb[side];
+        if (!o) continue;
+        if (o->pw != band->pw || o->n != band->n || o->ctx->precision != band->ctx->precision)
+            return fail(W2X_ERR_ARG, "w2x_band_connect_local: the %s neighbour's session does not match (width / model / precision)", side ? "down" : "up");
+        if (o->ctx->device != band->ctx->device) {
+            int can = 0;
+            CU_CHECK(cudaDeviceCanAccessPeer(&can, band->ctx->device, o->ctx->device));
+            if (!can) return fail(W2X_ERR_UNSUPPORTED, "device %d cannot map the memory of device %d (no peer access)", band->ctx->device, o->ctx->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU_CHECK(e);
+            cudaGetLastError();
+        }
+        w2x_band::Peer &p = band->peer[side];
+        p.pad = o->pad;
+        p.act[0] = reinterpret_cast<char *>(o->act[0]);
+        p.act[1] = reinterpret_cast<char *>(o->act[1]);
+        p.flags = o->flags;
+        p.hf = o->hf;
+        p.ipc = false;
+    }
+    return W2X_OK;
+}
+
+// After w2x_band_load_rows (step = -1) or w2x_band_step(step): this band's boundary rows -> the neighbours' halo rows, flag
+// handshake; the context's stream continues once the neighbours' rows are here.  One kernel.
+int w2x_band_exchange(w2x_band *band, int step) {
+    if (band_check(band)) return W2X_ERR_ARG;
+    if (step != band->last_step || step < -1 || step > band->n - 2) return fail(W2X_ERR_ARG, "w2x_band_exchange: call it for the step that was queued last");
+    if ((band->up && !band->peer[0].flags) || (band->down && !band->peer[1].flags))
+        return fail(W2X_ERR_ARG, "w2x_band_exchange: the neighbours are not connected (w2x_band_connect / w2x_band_connect_local)");
+    if (!band->up && !band->down) return W2X_OK;
+    w2x_ctx *ctx = band->ctx;
+    DeviceGuard g(ctx->device);
+    RowSeg seg[4];
+    size_t bytes, px;
+    const int nseg = row_segments(band, step, seg, &bytes, &px);
+    char *mine = step < 0 ? reinterpret_cast<char *>(band->pad) : reinterpret_cast<char *>(band->act[band->cur]);
+    HaloXArgs a{};
+    for (int s = 0; s < nseg; s++) {
+        if (band->up) {      // my first owned row -> the up neighbour's halo row below (its last frame row)
+            const w2x_band::Peer &p = band->peer[0];
+            char *theirs = step < 0 ? reinterpret_cast<char *>(p.pad) : p.act[band->cur];
+            a.src[a.n] = seg_at(mine, band->hf, px, seg[s], 1);
+            a.dst[a.n] = seg_at(theirs, p.hf, px, seg[s], p.hf - 1);
+            a.n++;
+        }
+        if (band->down) {    // my last owned row -> the down neighbour's halo row above (its frame row 0)
+            const w2x_band::Peer &p = band->peer[1];
+            char *theirs = step < 0 ? reinterpret_cast<char *>(p.pad) : p.act[band->cur];
+            a.src[a.n] = seg_at(mine, band->hf, px, seg[s], band->hf - 2);
+            a.dst[a.n] = seg_at(theirs, p.hf, px, seg[s], 0);
+            a.n++;
+        }
+    }
+    a.bytes = bytes;
+    a.counter = band->flags + 4;
+    a.value = ++band->seq;
+    // I am the DOWN neighbour of my up peer (its flag 1) and the UP neighbour of my down peer (its flag 0)
+    a.peer_flag[0] = band->up ? band->peer[0].flags + 1 : nullptr;
+    a.peer_flag[1] = band->down ? band->peer[1].flags + 0 : nullptr;
+    a.my_flag[0] = band->up ? band->flags + 0 : nullptr;
+    a.my_flag[1] = band->down ? band->flags + 1 : nullptr;
+    CU_CHECK(launch_halo_exchange(a, ctx->stream));
+    ctx->launches++;
+    return W2X_OK;
+}
+
+// One whole pass of a connected band: own rows in, own rows out; everything is queued on the context's stream.
+int w2x_band_run(w2x_band *band, const float *d_in, size_t in_stride_bytes, float *d_out, size_t out_stride_bytes) {
+    int rc = w2x_band_load_rows(band, d_in, in_stride_bytes);
+    if (rc) return rc;
+    if ((rc = w2x_band_exchange(band, -1))) return rc;
+    for (int k = 0; k <= band->n - 2; k++) {
+        if ((rc = w2x_band_step(band, k))) return rc;
+        if ((rc = w2x_band_exchange(band, k))) return rc;
+    }
+    return w2x_band_finish(band, d_out, out_stride_bytes);
+}
+
+}  // extern "C"
+
+// =========================================================================================================================
+// One process, N GPUs
+// =========================================================================================================================
+struct w2x_multi {
+    std::vector<w2x_ctx *> ctx;
+    // the band sessions of the last (model, width, height): planes of one job usually share a shape
+    uint64_t plan_uid = 0;
+    int plan_w = 0, plan_h = 0, plan_precision = -1;
+    std::vector<w2x_band *> bands;
+    std::vector<int> r0;                       // first row of every band (+ the plane height at the end)
+    std::vector<float *> d_in, d_out;          // per-GPU staging of the band's rows
+    std::vector<size_t> d_bytes;
+};
+
+namespace {
+
+void multi_drop_plan(w2x_multi *m) {
+    for (auto b : m->bands) w2x_band_destroy(b);
+    m->bands.clear();
+    m->plan_uid = 0;
+}
+
+// pinned view of a caller buffer for the duration of one call (pageable memory makes every async copy a staged, blocking one)
+struct HostPin {
+    void *p = nullptr;
+    HostPin(const void *ptr, size_t bytes) {
+        if (bytes >= ((size_t)4 << 20) && cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable) == cudaSuccess) p = const_cast<void *>(ptr);
+        else cudaGetLastError();
+    }
+    ~HostPin() {
+        if (p) cudaHostUnregister(p);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int w2x_multi_create(const int *devices, int n_devices, w2x_multi **out) {
+    if (!out || n_devices < 1 || n_devices > 64) return fail(W2X_ERR_ARG, "w2x_multi_create: bad argument");
+    *out = nullptr;
+    auto m = std::make_unique<w2x_multi>();
+    for (int i = 0; i < n_devices; i++) {
+        w2x_ctx *c = nullptr;
+        int rc = w2x_ctx_create(devices ? devices[i] : i, &c);
+        if (rc) {
+            for (auto p : m->ctx) w2x_ctx_destroy(p);
+            return rc;
+        }
+        m->ctx.push_back(c);
+    }
+    m->d_in.assign((size_t)n_devices, nullptr);
+    m->d_out.assign((size_t)n_devices, nullptr);
+    m->d_bytes.assign((size_t)n_devices, 0);
+    *out = m.release();
+    return W2X_OK;
+}
+
+void w2x_multi_destroy(w2x_multi *m) {
+    if (!m) return;
+    multi_drop_plan(m);
+    for (size_t i = 0; i < m->ctx.size(); i++) {
+        DeviceGuard g(m->ctx[i]->device);
+        cudaFree(m->d_in[i]);
+        cudaFree(m->d_out[i]);
+    }
+    for (auto c : m->ctx) w2x_ctx_destroy(c);
+    delete m;
+}
+
+int w2x_multi_device_count(const w2x_multi *m) { return m ? (int)m->ctx.size() : 0; }
+w2x_ctx *w2x_multi_ctx(w2x_multi *m, int i) { return m && i >= 0 && i < (int)m->ctx.size() ? m->ctx[(size_t)i] : nullptr; }
+
+int w2x_multi_convert_plane(w2x_multi *m, const w2x_model *model, const float *in, int width, int height, size_t in_stride_bytes,
+                            float *out, size_t out_stride_bytes, int block_splitting) {
+    if (!m || m->ctx.empty()) return fail(W2X_ERR_ARG, "w2x_multi_convert_plane: NULL handle");
+    if (!model || !in || !out || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_multi_convert_plane: bad argument");
+    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4) return fail(W2X_ERR_ARG, "w2x_multi_convert_plane: row stride smaller than a row");
+    const int n_layers = (int)model->layers.size();
+    int nd = (int)m->ctx.size();
+    // every band needs a few rows of its own; small planes (and models without a tensor-core form) stay on one GPU
+    nd = std::min(nd, height / (4 * n_layers));
+    if (nd < 2 || !model->tc_eligible || m->ctx[0]->engine == W2X_ENGINE_FP32)
+        return w2x_convert_plane(m->ctx[0], model, in, width, height, in_stride_bytes, out, out_stride_bytes, block_splitting);
+    // ---- plan: one band session per GPU, neighbours wired through peer memory ----
+    if (m->plan_uid != model->uid || m->plan_w != width || m->plan_h != height || (int)m->bands.size() != nd ||
+        m->plan_precision != m->ctx[0]->precision) {
+        multi_drop_plan(m);
+        m->r0.assign((size_t)nd + 1, 0);
+        for (int i = 0; i <= nd; i++) m->r0[(size_t)i] = (int)((long)height * i / nd);
+        for (int i = 0; i < nd; i++) {
+            m->ctx[(size_t)i]->precision = m->ctx[0]->precision;
+            w2x_band *b = nullptr;
+            int rc = w2x_band_create(m->ctx[(size_t)i], model, width, m->r0[(size_t)i + 1] - m->r0[(size_t)i], i > 0, i + 1 < nd, &b);
+            if (rc) { multi_drop_plan(m); return rc; }
+            m->bands.push_back(b);
+        }
+        for (int i = 0; i < nd; i++) {
+            int rc = w2x_band_connect_local(m->bands[(size_t)i], i > 0 ? m->bands[(size_t)i - 1] : nullptr, i + 1 < nd ? m->bands[(size_t)i + 1] : nullptr);
+            if (rc) { multi_drop_plan(m); return rc; }
+        }
+        m->plan_uid = model->uid;
+        m->plan_w = width;
+        m->plan_h = height;
+        m->plan_precision = m->ctx[0]->precision;
+    }
+    HostPin pin_in(in, in_stride_bytes * (size_t)(height - 1) + (size_t)width * 4), pin_out(out, out_stride_bytes * (size_t)(height - 1) + (size_t)width * 4);
+    // ---- queue everything: upload, the whole layer loop with its exchanges, download -- per GPU, one host thread ----
+    for (int i = 0; i < nd; i++) {
+        w2x_ctx *c = m->ctx[(size_t)i];
+        DeviceGuard g(c->device);
+        const int y = m->r0[(size_t)i], rows = m->r0[(size_t)i + 1] - y;
+        const size_t need = (size_t)rows * width * 4;
+        if (m->d_bytes[(size_t)i] < need) {
+            cudaFree(m->d_in[(size_t)i]);
+            cudaFree(m->d_out[(size_t)i]);
+            m->d_in[(size_t)i] = m->d_out[(size_t)i] = nullptr;
+            m->d_bytes[(size_t)i] = 0;
+            CU_CHECK(cudaMalloc(&m->d_in[(size_t)i], need));
+            CU_CHECK(cudaMalloc(&m->d_out[(size_t)i], need));
+            m->d_bytes[(size_t)i] = need;
+        }
+        CU_CHECK(cudaMemcpy2DAsync(m->d_in[(size_t)i], (size_t)width * 4, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes, in_stride_bytes,
+                                   (size_t)width * 4, (size_t)rows, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int i = 0; i < nd; i++) {
+        int rc = w2x_band_run(m->bands[(size_t)i], m->d_in[(size_t)i], (size_t)width * 4, m->d_out[(size_t)i], (size_t)width * 4);
+        if (rc) {
+            for (auto c : m->ctx) { DeviceGuard g(c->device); cudaStreamSynchronize(c->stream); }
+            return rc;
+        }
+    }
+    for (int i = 0; i < nd; i++) {
+        w2x_ctx *c = m->ctx[(size_t)i];
+        DeviceGuard g(c->device);
+        const int y = m->r0[(size_t)i], rows = m->r0[(size_t)i + 1] - y;
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, m->d_out[(size_t)i], (size_t)width * 4,
+                                   (size_t)width * 4, (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
+    }
+    int rc = W2X_OK;
+    for (int i = 0; i < nd; i++) {
+        w2x_ctx *c = m->ctx[(size_t)i];
+        DeviceGuard g(c->device);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess && rc == W2X_OK) rc = fail(W2X_ERR_CUDA, "CUDA error %s on device %d (%s)", cudaGetErrorName(e), c->device, cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+// Independent planes of one shape (the reference's block loop, src/convertRoutine.cpp:114-165, and BASELINE config 5):
+// tile t goes to GPU t mod N, every GPU runs its tiles as ONE batched pass; no exchange.
+int w2x_multi_convert_tiles(w2x_multi *m, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,
+                            int width, int height, size_t in_stride_bytes, size_t out_stride_bytes) {
+    if (!m || m->ctx.empty()) return fail(W2X_ERR_ARG, "w2x_multi_convert_tiles: NULL handle");
+    if (!model || !in_tiles || !out_tiles || n_tiles < 1) return fail(W2X_ERR_ARG, "w2x_multi_convert_tiles: bad argument");
+    const int nd = std::min((int)m->ctx.size(), n_tiles);
+    std::vector<std::vector<const float *>> tin((size_t)nd);
+    std::vector<std::vector<float *>> tout((size_t)nd);
+    for (int t = 0; t < n_tiles; t++) {
+        tin[(size_t)(t % nd)].push_back(in_tiles[t]);
+        tout[(size_t)(t % nd)].push_back(out_tiles[t]);
+    }
+    // queue every GPU's batch without waiting, then wait for all of them
+    int rc = W2X_OK;
+    for (int i = 0; i < nd && rc == W2X_OK; i++)
+        rc = w2x_convert_tiles_async(m->ctx[(size_t)i], model, tin[(size_t)i].data(), tout[(size_t)i].data(), (int)tin[(size_t)i].size(), width, height,
+                                     in_stride_bytes, out_stride_bytes);
+    for (int i = 0; i < nd; i++) {
+        int r2 = w2x_ctx_synchronize(m->ctx[(size_t)i]);
+        if (rc == W2X_OK) rc = r2;
+    }
+    return rc;
+}
+
+int w2x_multi_set_precision(w2x_multi *m, int precision) {
+    if (!m) return fail(W2X_ERR_ARG, "NULL handle");
+    for (auto c : m->ctx) {
+        int rc = w2x_ctx_set_precision(c, precision);
+        if (rc) return rc;
+    }
+    return W2X_OK;
+}
+
+int w2x_multi_set_log(w2x_multi *m, w2x_log_fn fn, void *user) {
+    if (!m) return fail(W2X_ERR_ARG, "NULL handle");
+    return w2x_ctx_set_log(m->ctx[0], fn, user);
+}
+
+}  // extern "C"

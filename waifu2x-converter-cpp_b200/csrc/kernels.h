@@ -11,8 +11,24 @@ namespace w2x {
 cudaError_t launch_pad_replicate(const float *in, int w, int h, long in_stride_floats, int pad, int rows_above,
                                  int rows_below, float *out, cudaStream_t s);
 // general form: horizontal pad pad_x, vertical pads pad_top / pad_bottom (row-band sessions)
+// skip_top / skip_bottom: frame rows at the top / bottom that are NOT written (a neighbour GPU stores them)
 cudaError_t launch_pad_replicate_xy(const float *in, int w, int h, long in_stride_floats, int pad_x, int pad_top,
-                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s);
+                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s,
+                                    int skip_top = 0, int skip_bottom = 0);
+// Peer-memory halo exchange (engine_band.cu): ONE kernel copies up to 8 row segments into the neighbour GPUs' frames,
+// publishes `value` in their flag words once every byte is visible system-wide, then waits until the neighbours have
+// published the same value here.  Flag values only grow, so nothing is ever reset.
+struct HaloXArgs {
+    int n;                       // segments
+    const char *src[8];
+    char *dst[8];
+    size_t bytes;                // per segment (multiple of 4)
+    unsigned *counter;           // block-completion counter in this GPU's memory (self-resetting)
+    unsigned *peer_flag[2];      // where to publish (nullptr = no neighbour on that side)
+    const unsigned *my_flag[2];  // what to wait for
+    unsigned value;
+};
+cudaError_t launch_halo_exchange(const HaloXArgs &a, cudaStream_t s);
 cudaError_t launch_crop(const float *in, int w, int h, int pad, float *out, long out_stride_floats, cudaStream_t s);
 cudaError_t launch_copy2d(const float *in, long in_stride_floats, float *out, long out_stride_floats, int w, int h,
                           cudaStream_t s);
@@ -37,7 +53,7 @@ cudaError_t init_kernels();
 // same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
 // `wgt` ([C][9]) and `bias` ((float)bias) are HOST pointers: they travel as kernel parameters.
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
-                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0);
+                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0, int out_y0 = 0, int out_rows = -1);
 // tcgen05 layer: in/out NHWC frames (pw x ph); the tensor maps are built inside.
 // `bias` is a HOST pointer to the layer's (float)bias values (they travel as kernel parameters).
 // f8 = 0: "f16x3" frames [hi][lo], wpack = TcPack::bytes, wstrip = TcPack::strip;
@@ -47,7 +63,9 @@ cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph,
 cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out,
                             int cin, int cout, int pw, int ph, float out_scale, int f8, int num_sms,
                             cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
-                            float *partial = nullptr, int pair = 0);
+                            float *partial = nullptr, int pair = 0, int out_y0 = 0, int out_rows = -1);
+// out_y0 / out_rows (both launchers): only frame rows [out_y0, out_y0 + out_rows) are stored (-1 = the whole frame); a
+// row-band session keeps its halo rows out of the window because its neighbours write them.
 bool strip_supported(int cin, int cout);
 // Fused last layer: launch_tc_layer(..., last_w = HOST pointer to [9][cout] fp32 tap-major, partial = [ph][pw][12] fp32) makes the
 // tcgen05 layer emit per-pixel tap partials instead of activations; launch_last_gather sums the 3x3

@@ -11,6 +11,9 @@
 // Roofline: CUDA-core FFMA.  32 output planes x (9 FFMA + 1 FADD) per input plane per pixel.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdint>
+
 #include "kernels.h"
 
 namespace w2x {
@@ -20,11 +23,11 @@ namespace w2x {
 // pointer addresses band row 0 and may be read at rows [-rows_above, h + rows_below).
 __global__ void pad_replicate_kernel(const float *__restrict__ in, int w, int h, long in_stride,
                                      int pad_x, int pad_top, int pad_bottom, int rows_above, int rows_below,
-                                     float *__restrict__ out) {
+                                     float *__restrict__ out, int skip_top, int skip_bottom) {
     const int W = w + 2 * pad_x, H = h + pad_top + pad_bottom;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
+    if (x >= W || y >= H - skip_bottom || y < skip_top) return;
     int sx = min(max(x - pad_x, 0), w - 1);
     int sy = min(max(y - pad_top, -rows_above), h - 1 + rows_below);
     out[(long)y * W + x] = in[(long)sy * in_stride + sx];
@@ -149,10 +152,66 @@ cudaError_t launch_pad_replicate(const float *in, int w, int h, long in_stride_f
 }
 
 cudaError_t launch_pad_replicate_xy(const float *in, int w, int h, long in_stride_floats, int pad_x, int pad_top,
-                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s) {
+                                    int pad_bottom, int rows_above, int rows_below, float *out, cudaStream_t s,
+                                    int skip_top, int skip_bottom) {
     dim3 b(32, 8);
     pad_replicate_kernel<<<grid2d(w + 2 * pad_x, h + pad_top + pad_bottom, b), b, 0, s>>>(
-        in, w, h, in_stride_floats, pad_x, pad_top, pad_bottom, rows_above, rows_below, out);
+        in, w, h, in_stride_floats, pad_x, pad_top, pad_bottom, rows_above, rows_below, out, skip_top, skip_bottom);
+    return cudaGetLastError();
+}
+
+// ---- peer-memory halo exchange (row-band sessions on neighbouring GPUs) -----------------------------------------------
+// The rows go straight into the neighbour's frame over NVLink (peer-mapped memory: cudaDeviceEnablePeerAccess inside one
+// process, CUDA IPC between processes).  Ordering is by flag words in the RECEIVER's memory; values only grow, so a flag
+// is never reset and a late reader cannot miss an update.  A protocol bug must not hang the GPU: the spin gives up with
+// __trap() after ~4 s.
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned *flag, unsigned value) {
+    if (!flag) return;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - value) < 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const HaloXArgs a) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (int sg = 0; sg < a.n; sg++) {
+        if (a.bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(a.src[sg]) | reinterpret_cast<uintptr_t>(a.dst[sg])) % 16 == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.src[sg]);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.dst[sg]);
+            for (size_t i = tid; i < a.bytes / 16; i += nthr) dst[i] = src[i];
+        } else {
+            const unsigned *src = reinterpret_cast<const unsigned *>(a.src[sg]);
+            unsigned *dst = reinterpret_cast<unsigned *>(a.dst[sg]);
+            for (size_t i = tid; i < a.bytes / 4; i += nthr) dst[i] = src[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.counter, 1u) + 1u;
+        if (done == gridDim.x) {                       // the last block: every row of this GPU is visible system-wide
+            *a.counter = 0;
+            __threadfence_system();
+            if (a.peer_flag[0]) st_release_sys(a.peer_flag[0], a.value);
+            if (a.peer_flag[1]) st_release_sys(a.peer_flag[1], a.value);
+            spin_until(a.my_flag[0], a.value);         // ... and the neighbours' rows are here
+            spin_until(a.my_flag[1], a.value);
+        }
+    }
+}
+
+cudaError_t launch_halo_exchange(const HaloXArgs &a, cudaStream_t s) {
+    if (a.n < 0 || a.n > 8 || a.bytes % 4 || !a.counter) return cudaErrorInvalidValue;
+    const int blocks = a.n == 0 ? 1 : (int)std::min<size_t>(16, (a.bytes * (size_t)a.n / 16 + 255) / 256 + 1);
+    halo_exchange_kernel<<<blocks, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

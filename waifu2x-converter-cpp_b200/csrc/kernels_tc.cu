@@ -131,7 +131,7 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8,
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
 static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h);
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w = 8, int box_h = 4);
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h, int y0, int rows);
 
 template <int CIN, bool FUSE, bool F8>
 static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const CUtensorMap *p_out_maps,
@@ -175,12 +175,14 @@ static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p,
 #define W2X_STRIP_SHAPES(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 
 static cudaError_t launch_strip(const __half *in, const void *wstrip, const float *bias, __half *out, int cin, int cout, int pw, int ph,
-                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof) {
+                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof, int out_y0, int out_rows) {
     StripParams p;
     p.wpack = reinterpret_cast<const uint8_t *>(wstrip);
     for (int i = 0; i < cout; i++) p.bias[i] = bias[i] * ACT_SCALE;
     p.Wp = pw;
     p.Hp = ph;
+    p.out_y0 = out_y0;
+    p.out_rows = out_rows;
     p.seg_rows = strip_seg_rows();
     p.ncols = (pw + STRIP_W - 1) / STRIP_W;
     p.n_units = p.ncols * ((ph + p.seg_rows - 1) / p.seg_rows);
@@ -194,7 +196,7 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 #endif
     CUtensorMap maps[4];
     if (make_act_maps(&maps[0], &maps[1], in, cin, pw, ph, f8 != 0, 32, STRIP_BOXW, 1)) return cudaErrorInvalidValue;
-    if (make_out_tensor_maps(&maps[2], &maps[3], out, cout, pw, ph, f8 != 0, 32, 1)) return cudaErrorInvalidValue;
+    if (make_out_tensor_maps(&maps[2], &maps[3], out, cout, pw, ph, f8 != 0, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
 #define X(ci, co)                                                                                       \
     if (cin == ci && cout == co)                                                                        \
         return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, s);
@@ -205,9 +207,10 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 
 cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial, int pair) {
+                            unsigned long long *prof, const float *last_w, float *partial, int pair, int out_y0, int out_rows) {
+    if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     if (wstrip && !partial && strip_supported(cin, cout))
-        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof);
+        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof, out_y0, out_rows);
     CUtensorMap tmap_in, tmap_in8;
     if (make_act_maps(&tmap_in, &tmap_in8, in, cin, pw, ph, f8 != 0, act_kc(cin), HALO, HALO)) return cudaErrorInvalidValue;
     TcParams p;
@@ -218,6 +221,8 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
     p.out = out;
     p.Wp = pw;
     p.Hp = ph;
+    p.out_y0 = out_y0;
+    p.out_rows = out_rows;
     p.tiles_x = (pw + REGION - 1) / REGION;
     p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
     p.out_scale = out_scale * ACT_SCALE;
@@ -236,7 +241,7 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
     // the epilogue's TMA stores: 8x4-pixel x 32-channel boxes of this layer's output frame (fused layers store no frame)
     CUtensorMap omaps[2];
     if (partial) { omaps[0] = tmap_in; omaps[1] = tmap_in8; }
-    else if (make_out_tensor_maps(&omaps[0], &omaps[1], out, cout, pw, ph, f8 != 0)) return cudaErrorInvalidValue;
+    else if (make_out_tensor_maps(&omaps[0], &omaps[1], out, cout, pw, ph, f8 != 0, 8, 4, out_y0, out_rows)) return cudaErrorInvalidValue;
     if (pair && cout == 128 && num_sms >= 2) {
 #define X(ci) \
     if (cin == ci) return launch_pair<ci>(&tmap_in, &tmap_in8, omaps, p, num_sms, f8 != 0, s);
@@ -252,7 +257,7 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
 
 template <int COUT>
 static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
-                                  cudaStream_t s, int f8) {
+                                  cudaStream_t s, int f8, int out_y0, int out_rows) {
     static_assert(FIRST_TILE_BYTES + 1024 <= 48 * 1024, "the first layer's staging tile stays under the default dynamic shared memory limit");
     // (under 48 KB no opt-in is required; the attribute is set anyway, once per process, as every other kernel of the engine does)
     static bool attr_done = false;
@@ -266,20 +271,21 @@ static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw
     for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
     for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
     CUtensorMap omaps[2];
-    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8)) return cudaErrorInvalidValue;
+    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
     dim3 grid((pw + 31) / 32, (ph + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
-    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, omaps[0], omaps[1], prm);
-    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, omaps[0], omaps[1], prm);
+    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s, int f8) {
+                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows) {
+    if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     switch (cout) {
-        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
-        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
-        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8);
+        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -367,21 +373,22 @@ static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t byt
 // layer's blocks store 32 x 8 pixels).
 //   f16x3: ONE map over [2][Hp][Wp][C] fp16, box {32, 8, 4, 2} (hi and lo planes in one store), SWIZZLE_64B; map8 = copy.
 //   F8:    map16 over the xh plane, box {32, 8, 4, 1}, SWIZZLE_64B; map8 over the two e4m3 planes, box {32, 8, 4, 2}, SWIZZLE_32B.
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h) {
+// Only frame rows [y0, y0 + rows) are part of the maps (row coordinate 0 = frame row y0); everything else is clipped.
+static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h, int y0, int rows) {
     PFN_encodeTiled enc = get_encode();
-    if (!enc) return -1;
+    if (!enc || rows < 1 || y0 < 0 || y0 + rows > Hp) return -1;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(f8 ? 1 : 2)};
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)rows, (cuuint64_t)(f8 ? 1 : 2)};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
         cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)(f8 ? 1 : 2)};
-        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, reinterpret_cast<char *>(base) + (size_t)y0 * Wp * C * 2, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return (int)r;
     }
     if (!f8) { *map8 = *map16; return 0; }
-    char *b8 = reinterpret_cast<char *>(base) + (size_t)2 * Hp * Wp * C;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
+    char *b8 = reinterpret_cast<char *>(base) + (size_t)2 * Hp * Wp * C + (size_t)y0 * Wp * C;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)rows, 2};
     cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
     cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 2};
     CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -77,6 +77,7 @@ struct TcParams {
     float bias[128];         // [COUT] (float)bias, by value (constant bank, see last_w)
     __half *out;             // [2][Hp][Wp][COUT]
     int Wp, Hp;
+    int out_y0, out_rows;    // only frame rows [out_y0, out_y0 + out_rows) are stored (row-band sessions keep the halo rows their neighbours write)
     int tiles_x, n_tilesets;
     float out_scale;         // 1 / wscale  (accumulator -> ACT_SCALE * conv)
     unsigned long long *prof;   // optional [gridDim.x][16] cycle counters (see PROF_* below), nullptr = off

@@ -21,7 +21,7 @@ constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16
 
 template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
-first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, const __grid_constant__ CUtensorMap tmap_out,
+first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, int out_y0, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ CUtensorMap tmap_out8, const __grid_constant__ FirstParams<COUT> prm) {
     extern __shared__ uint8_t first_smem[];
     const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
@@ -86,7 +86,7 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8 - out_y0;   // the store maps cover frame rows [out_y0, ...)
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                          ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
             if constexpr (F8)

@@ -245,7 +245,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
             const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
-            const bool inside = fy < p.Hp && fx < p.Wp;
+            const bool inside = fy < p.Hp && fx < p.Wp && fy >= p.out_y0 && fy < p.out_y0 + p.out_rows;
             float pt[9];                                   // FUSE: nine per-tap dot products of this pixel
 #pragma unroll
             for (int t = 0; t < 9; t++) pt[t] = 0.f;
@@ -280,7 +280,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
                 }
                 if constexpr (!FUSE) {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q - p.out_y0, cb);
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll

@@ -239,7 +239,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q4 * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
             const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
-            const bool inside = fy < p.Hp && fx < p.Wp;
+            const bool inside = fy < p.Hp && fx < p.Wp && fy >= p.out_y0 && fy < p.out_y0 + p.out_rows;
             float pt[9];
 #pragma unroll
             for (int t = 0; t < 9; t++) pt[t] = 0.f;
@@ -274,7 +274,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                         }
                     }
                 } else {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4 - p.out_y0, cb);
                 }
             }
             if constexpr (FUSE) {

@@ -62,6 +62,7 @@ struct StripParams {
     const uint8_t *wpack;       // [chunk][kx] stages, exact shared-memory images (model.cpp: pack_tc_layer_strip)
     float bias[64];             // (float)bias * ACT_SCALE
     int Wp, Hp;
+    int out_y0, out_rows;       // only frame rows [out_y0, out_y0 + out_rows) are stored
     int ncols, n_units, seg_rows;   // units = 128-pixel columns x segments of seg_rows rows, unit u = seg * ncols + col
     float out_scale;
     unsigned long long *prof;
@@ -301,7 +302,8 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         const float v = fmaf(act[k], p.out_scale, p.bias[cb * 32 + k]);     // = ACT_SCALE * (conv + bias)
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
-                    if (gx0 < p.Wp) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, y0 + i, cb);
+                    const int gy = y0 + i - p.out_y0;
+                    if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, gy, cb);
                 }
                 if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
             }
