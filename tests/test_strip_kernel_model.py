@@ -4,8 +4,10 @@
      block acquisition and completion -- replayed literally (same index arithmetic as the kernel) with real numbers:
      every output row must receive exactly W(ky=0)*x[y-1] + W(ky=1)*x[y] + W(ky=2)*x[y+1] (rows outside the frame are
      zero), be drained after its last contribution and before its block is reused;
-  2. the shared-memory addressing: tap column kx of a staged 130-pixel row is the descriptor start offset kx*ROWB
-     (SBO = 8*ROWB), for the fp16 (SWIZZLE_64B) and e4m3 (SWIZZLE_32B) planes;
+  2. the shared-memory addressing of RECORD frames (one 128-byte record per pixel per 32 channels, SWIZZLE_128B): tap
+     column kx of a staged 130-pixel row is the descriptor start offset kx*128 (SBO = 1024), the fp16 K steps / xh8 /
+     xl8 slices are its 32-byte quarters; and the staging tiles the epilogue and the first layer build are exactly what
+     the TMA stores read;
   3. the packed weight image (model.cpp pack_tc_layer_strip): a K-major descriptor at row offset ky*Cout of stage
      (chunk, kx) reads W[o][c*32+k][ky][kx] (scaled, split) for GEMM row ky*Cout + o.
 """
@@ -81,27 +83,54 @@ def swz(a, rowb):
     return a ^ (((a >> 7) & (rowb // 16 - 1)) << 4)
 
 
-@pytest.mark.parametrize("rowb", [64, 32])
-def test_tap_columns_are_start_offsets_into_one_staged_row(rowb):
-    """TMA writes box element (pixel px, byte b) at swz(base + px*rowb + b); a K-major descriptor with start S and
-    SBO = 8*rowb reads GEMM row m, byte b at swz(S + (m//8)*SBO + (m%8)*rowb + b).  With S = base + kx*rowb (+32 for
-    the second fp16 K step) row m must be pixel m + kx of the staged row."""
-    BOXW = 130
-    rng = np.random.default_rng(rowb)
+def test_tap_columns_and_record_quarters_are_start_offsets_into_one_staged_row():
+    """RECORD frames: TMA (SWIZZLE_128B) writes pixel px, byte b of its 128-byte record at swz(base + px*128 + b); a K-major
+    descriptor with start S and SBO = 1024 reads GEMM row m, byte b at swz(S + (m//8)*1024 + (m%8)*128 + b).  With
+    S = base + kx*128 + 32*q row m must be quarter q (fp16 K step 0 / 1, xh8, xl8) of pixel m + kx of the staged row."""
+    BOXW, rowb = 130, 128
+    rng = np.random.default_rng(7)
     row = rng.integers(0, 256, size=(BOXW, rowb), dtype=np.uint8)
-    base = 5 * 512 if rowb == 64 else 7 * 256        # plane bases are aligned to the swizzle period
+    base = 3 * 1024                                   # slots are aligned to the swizzle period
     smem = np.zeros(32 * 1024, np.uint8)
     for px in range(BOXW):
         for b in range(rowb):
             smem[swz(base + px * rowb + b, rowb)] = row[px, b]
-    sbo = 8 * rowb
     for kx in range(3):
-        for kstep in range(rowb // 32):
-            start = base + kx * rowb + 32 * kstep
+        for q in range(4):
+            start = base + kx * rowb + 32 * q
             for m in range(128):
                 for b in (0, 7, 16, 31):
-                    a = swz(start + (m // 8) * sbo + (m % 8) * rowb + b, rowb)
-                    assert smem[a] == row[m + kx, 32 * kstep + b]
+                    a = swz(start + (m // 8) * 1024 + (m % 8) * rowb + b, rowb)
+                    assert smem[a] == row[m + kx, 32 * q + b]
+
+
+def test_record_staging_tiles_are_the_tma_store_images():
+    """epilogue_store32_rec: lane = pixel, 16-byte unit u of its record at tile + lane*128 + ((u ^ (lane & 7)) << 4);
+    first_layer_kernel<REC>: row r = threadIdx.x, fp16 unit c8, e4m3 8-byte halves at units 4 + c8/2 (xh8) and 6 + c8/2 (xl8).
+    The TMA store (SWIZZLE_128B, box rows of 128 B) reads row r, byte b from swz(tile + r*128 + b)."""
+    rng = np.random.default_rng(8)
+    tile = 5 * 1024
+    smem = np.zeros(64 * 1024, np.uint8)
+    rec = rng.integers(0, 256, size=(32, 128), dtype=np.uint8)
+    for lane in range(32):
+        for u in range(8):
+            a = tile + lane * 128 + ((u ^ (lane & 7)) << 4)
+            smem[a:a + 16] = rec[lane, 16 * u:16 * u + 16]
+    for lane in range(32):
+        for b in range(128):
+            assert smem[swz(tile + lane * 128 + b, 128)] == rec[lane, b]
+    rec = rng.integers(0, 256, size=(256, 128), dtype=np.uint8)
+    smem[:] = 0
+    for r in range(256):
+        for c8 in range(4):
+            a = tile + r * 128 + ((c8 ^ (r & 7)) << 4)
+            smem[a:a + 16] = rec[r, 16 * c8:16 * c8 + 16]
+            for plane, unit0 in ((0, 4), (1, 6)):                       # xh8 bytes [64, 96), xl8 bytes [96, 128)
+                a8 = tile + r * 128 + (((unit0 + (c8 >> 1)) ^ (r & 7)) << 4) + (c8 & 1) * 8
+                smem[a8:a8 + 8] = rec[r, 64 + 32 * plane + 8 * c8:64 + 32 * plane + 8 * c8 + 8]
+    for r in range(256):
+        for b in range(128):
+            assert smem[swz(tile + r * 128 + b, 128)] == rec[r, b]
 
 
 def _f16(bits):

@@ -107,9 +107,13 @@ cudaError_t init_kernels() {
     W2X_TC_SHAPES(X)
 #undef X
 #define X(ci, co)                                                                                                                          \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
                                   StripCfg<ci, co, false>::SMEM_BYTES)) != cudaSuccess) return e;                                           \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  StripCfg<ci, co, false>::SMEM_BYTES)) != cudaSuccess) return e;                                           \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                  StripCfg<ci, co, true>::SMEM_BYTES)) != cudaSuccess) return e;                                            \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
                                   StripCfg<ci, co, true>::SMEM_BYTES)) != cudaSuccess) return e;
     X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 #undef X
@@ -131,6 +135,7 @@ static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8,
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
 static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h);
+static int make_rec_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp, int box_w, int box_h, int y0, int rows);
 static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h, int y0, int rows);
 
 template <int CIN, bool FUSE, bool F8>
@@ -165,17 +170,18 @@ static int strip_seg_rows() {   // rows per work unit (tuning knob: W2X_STRIP_RO
 }
 
 template <int CIN, int COUT, bool F8>
-static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p, int num_sms, cudaStream_t s) {
+static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p, int num_sms, bool out_rec, cudaStream_t s) {
     using C = StripCfg<CIN, COUT, F8>;
     const int grid = p.n_units < num_sms ? p.n_units : num_sms;
-    tc_conv3x3_strip_kernel<CIN, COUT, F8><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    if (out_rec) tc_conv3x3_strip_kernel<CIN, COUT, F8, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], p);
+    else tc_conv3x3_strip_kernel<CIN, COUT, F8, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], p);
     return cudaGetLastError();
 }
 
 #define W2X_STRIP_SHAPES(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 
 static cudaError_t launch_strip(const __half *in, const void *wstrip, const float *bias, __half *out, int cin, int cout, int pw, int ph,
-                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof, int out_y0, int out_rows) {
+                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof, int out_y0, int out_rows, int out_rec) {
     StripParams p;
     p.wpack = reinterpret_cast<const uint8_t *>(wstrip);
     for (int i = 0; i < cout; i++) p.bias[i] = bias[i] * ACT_SCALE;
@@ -194,12 +200,15 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 #else
     p.dbg = 0;
 #endif
-    CUtensorMap maps[4];
-    if (make_act_maps(&maps[0], &maps[1], in, cin, pw, ph, f8 != 0, 32, STRIP_BOXW, 1)) return cudaErrorInvalidValue;
-    if (make_out_tensor_maps(&maps[2], &maps[3], out, cout, pw, ph, f8 != 0, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
+    CUtensorMap maps[3];   // in (RECORD) | out | out8 (planar F8 output only)
+    if (make_rec_map(&maps[0], in, cin, pw, ph, STRIP_BOXW, 1, 0, ph)) return cudaErrorInvalidValue;
+    if (out_rec) {
+        if (make_rec_map(&maps[1], out, cout, pw, ph, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
+        maps[2] = maps[1];
+    } else if (make_out_tensor_maps(&maps[1], &maps[2], out, cout, pw, ph, f8 != 0, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
 #define X(ci, co)                                                                                       \
     if (cin == ci && cout == co)                                                                        \
-        return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, s);
+        return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, out_rec != 0, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, out_rec != 0, s);
     W2X_STRIP_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -207,10 +216,14 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 
 cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial, int pair, int out_y0, int out_rows) {
+                            unsigned long long *prof, const float *last_w, float *partial, int pair, int out_y0, int out_rows,
+                            int in_rec, int out_rec) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
-    if (wstrip && !partial && strip_supported(cin, cout))
-        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof, out_y0, out_rows);
+    if (in_rec) {          // the row-strip kernel consumes RECORD frames; every other kernel planar ones
+        if (!wstrip || partial || !strip_supported(cin, cout)) return cudaErrorInvalidValue;
+        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof, out_y0, out_rows, out_rec);
+    }
+    if (out_rec) return cudaErrorInvalidValue;
     CUtensorMap tmap_in, tmap_in8;
     if (make_act_maps(&tmap_in, &tmap_in8, in, cin, pw, ph, f8 != 0, act_kc(cin), HALO, HALO)) return cudaErrorInvalidValue;
     TcParams p;
@@ -257,13 +270,15 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
 
 template <int COUT>
 static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
-                                  cudaStream_t s, int f8, int out_y0, int out_rows) {
+                                  cudaStream_t s, int f8, int out_y0, int out_rows, int out_rec) {
     static_assert(FIRST_TILE_BYTES + 1024 <= 48 * 1024, "the first layer's staging tile stays under the default dynamic shared memory limit");
     // (under 48 KB no opt-in is required; the attribute is set anyway, once per process, as every other kernel of the engine does)
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -271,21 +286,28 @@ static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw
     for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
     for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
     CUtensorMap omaps[2];
-    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
     dim3 grid((pw + 31) / 32, (ph + 7) / 8);
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
-    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
-    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+    if (out_rec) {
+        if (make_rec_map(&omaps[0], out, COUT, pw, ph, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
+        omaps[1] = omaps[0];
+        if (f8) first_layer_kernel<COUT, true, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+        else first_layer_kernel<COUT, false, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+        return cudaGetLastError();
+    }
+    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
+    if (f8) first_layer_kernel<COUT, true, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+    else first_layer_kernel<COUT, false, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows) {
+                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows, int out_rec) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     switch (cout) {
-        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
-        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
-        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
+        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
+        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -324,9 +346,9 @@ cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bi
     return cudaGetLastError();
 }
 
-cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8) {
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8, int rec) {
     long total = (long)(w + 2) * (h + 2) * C;
-    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8);
+    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8, rec);
     return cudaGetLastError();
 }
 
@@ -393,6 +415,21 @@ static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *bas
     cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 2};
     CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// RECORD frame [Hp][Wp][C/32][128 B] (tc_epilogue.cuh) as a byte tensor {128, C/32, Wp, rows}, box {128, 1, box_w, box_h},
+// SWIZZLE_128B; only frame rows [y0, y0 + rows) are part of the map (row coordinate 0 = frame row y0).
+static int make_rec_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp, int box_w, int box_h, int y0, int rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc || rows < 1 || y0 < 0 || y0 + rows > Hp || C % 32) return -1;
+    cuuint64_t dims[4] = {128, (cuuint64_t)(C / 32), (cuuint64_t)Wp, (cuuint64_t)rows};
+    cuuint64_t strides[3] = {128, (cuuint64_t)C * 4, (cuuint64_t)Wp * C * 4};
+    cuuint32_t box[4] = {128, 1, (cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(reinterpret_cast<const char *>(base)) + (size_t)y0 * Wp * C * 4, dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 

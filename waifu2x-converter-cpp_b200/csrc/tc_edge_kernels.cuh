@@ -19,7 +19,9 @@ struct FirstParams {
 };
 constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16 KB]  or  [xh 16 KB | xh8 8 KB | xl8 8 KB]
 
-template <int COUT, bool F8>
+// REC: the output is a RECORD frame (tc_epilogue.cuh): the staged image is [256 px][128 B] per 32 channels, SWIZZLE_128B,
+// one box {128 B, 1, 32 px, 8 rows} -- a third of the planar frame's TMA row requests.
+template <int COUT, bool F8, bool REC>
 __global__ void __launch_bounds__(256, 4)
 first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, int out_y0, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ CUtensorMap tmap_out8, const __grid_constant__ FirstParams<COUT> prm) {
@@ -36,7 +38,7 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
         }
     const uint32_t r = (uint32_t)threadIdx.x;                            // pixel index inside the block = row of the staged image
-    const uint32_t sw64 = (r >> 1) & 3u, sw32 = (r >> 2) & 1u;
+    const uint32_t sw64 = (r >> 1) & 3u, sw32 = (r >> 2) & 1u, sw128 = r & 7u;
 #pragma unroll 1
     for (int cb = 0; cb < COUT / 32; cb++) {
         if (cb) {   // the previous 32 channels' boxes must have left shared memory
@@ -72,6 +74,18 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
                     lo[i] = *reinterpret_cast<uint32_t *>(&l);
                 }
             }
+            if constexpr (REC) {
+                // record row of 128 B: units 0..3 fp16, then [xh8 16+16 B | xl8 16+16 B] or the lo half
+                sts128(tile + r * 128u + (((uint32_t)c8 ^ sw128) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+                if constexpr (F8) {
+                    const uint32_t half = ((uint32_t)c8 & 1u) * 8u;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((4u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[0]), "r"(lo[1]) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((6u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[2]), "r"(lo[3]) : "memory");
+                } else {
+                    sts128(tile + r * 128u + (((4u + (uint32_t)c8) ^ sw128) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+                }
+                continue;
+            }
             // 16-byte unit c8 of this pixel's 64-byte fp16 row (SWIZZLE_64B image)
             sts128(tile + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
             if constexpr (F8) {
@@ -87,9 +101,13 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
         __syncthreads();
         if (threadIdx.x == 0) {
             const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8 - out_y0;   // the store maps cover frame rows [out_y0, ...)
-            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
-            if constexpr (F8)
+            if constexpr (REC)
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(0), "r"(cb), "r"(x0), "r"(y0) : "memory");
+            else
+                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            if constexpr (F8 && !REC)
                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                              ::"l"(reinterpret_cast<uint64_t>(&tmap_out8)), "r"(tile + 16384u), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -170,7 +188,7 @@ last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias
     dst[(long)(y - crop_top) * dst_stride + (x - crop_x)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
 }
 
-__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8) {
+__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8, int rec) {
     const int pw = w + 2, ph = h + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)pw * ph * C;
@@ -181,6 +199,19 @@ __global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w
     int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1);
     float a = in[((long)c * h + sy) * w + sx] * ACT_SCALE;
     __half hh = __float2half_rn(a);
+    if (rec) {   // RECORD frame: [pixel][C/32][128 B] = {fp16 x32 | xh8 x32 | xl8 x32} or {hi x32 | lo x32}
+        uint8_t *recp = reinterpret_cast<uint8_t *>(out) + (pix * (C / 32) + c / 32) * 128;
+        const int k = c % 32;
+        const float hf = __half2float(hh);
+        reinterpret_cast<__half *>(recp)[k] = hh;
+        if (f8) {
+            recp[64 + k] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
+            recp[96 + k] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
+        } else {
+            reinterpret_cast<__half *>(recp + 64)[k] = __float2half_rn(a - hf);
+        }
+        return;
+    }
     out[idx] = hh;
     if (f8) {
         uint8_t *b = reinterpret_cast<uint8_t *>(out);

@@ -66,3 +66,52 @@ __device__ __forceinline__ void epilogue_store32(const float (&act)[32], const C
         bulk_commit();
     }
 }
+
+// The same for RECORD frames ([Hp][Wp][C/32][128 B], one 128-byte record per pixel per 32-channel block:
+// {xh fp16 x32 | xh8 x32 | xl8 x32} or {hi fp16 x32 | lo fp16 x32}): the warp's staging tile is [32 px][128 B] in the
+// SWIZZLE_128B pattern and leaves as ONE box of 32 rows of 128 B -- a third of the TMA row requests of the planar
+// frame (the TMA unit serves ~1 row per 1.45 clk whatever its length: profiles/r02_strip_experiments.txt).
+template <bool F8>
+__device__ __forceinline__ void epilogue_store32_rec(const float (&act)[32], const CUtensorMap *tmo, int dbg, uint32_t stg, int lane, int gx0, int gy0,
+                                                     int cb) {
+    uint32_t g0[16], g1[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float v0 = act[2 * i], v1 = act[2 * i + 1];
+        __half2 h = __floats2half2_rn(v0, v1);
+        float2 hf = __half22float2(h);
+        g0[i] = *reinterpret_cast<uint32_t *>(&h);
+        if constexpr (F8) {
+            constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+            const __half2 hd = __hmul2(h, __float2half2_rn(kDown));
+            const uint32_t h8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hd), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+            if (i & 1) { g1[i >> 1] |= h8 << 16; g1[8 + (i >> 1)] |= l8 << 16; }
+            else { g1[i >> 1] = h8; g1[8 + (i >> 1)] = l8; }
+        } else {
+            __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            g1[i] = *reinterpret_cast<uint32_t *>(&l);
+        }
+    }
+    if (dbg & 2) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x ^= g0[i] ^ g1[i];
+        if (x == 0x7fc12345u) sts128(stg, make_uint4(x, x, x, x));
+        return;
+    }
+    bulk_wait_read();
+    __syncwarp();
+    const uint32_t row = stg + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {   // units 0..3: the fp16 half; units 4..7: [xh8 | xl8] or lo
+        sts128(row + (((uint32_t)u ^ sw) << 4), make_uint4(g0[4 * u], g0[4 * u + 1], g0[4 * u + 2], g0[4 * u + 3]));
+        sts128(row + (((uint32_t)(4 + u) ^ sw) << 4), make_uint4(g1[4 * u], g1[4 * u + 1], g1[4 * u + 2], g1[4 * u + 3]));
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (!(dbg & 1)) {
+        tma_store_4d(tmo, stg, 0, cb, gx0, gy0);
+        bulk_commit();
+    }
+}

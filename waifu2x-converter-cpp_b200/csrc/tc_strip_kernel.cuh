@@ -29,15 +29,16 @@
 constexpr int STRIP_W = 128;            // pixels per strip = GEMM M
 constexpr int STRIP_BOXW = STRIP_W + 2;  // staged pixels per row
 
+// Input frames are RECORD frames (tc_epilogue.cuh): one TMA box {128 B, 1 block, 130 px, 1 row} per (row, 32-channel block)
+// lands as 130 rows of 128 B in the SWIZZLE_128B pattern; the fp16 K steps, the xh8 and the xl8 slices of a pixel are the
+// 32-byte quarters of its row.  OUT_REC selects the output frame's layout (RECORD when the next layer is a strip layer).
 template <int CIN, int COUT, bool F8>
 struct StripCfg {
     static_assert((CIN == 32 || CIN == 64) && (COUT == 32 || COUT == 64), "strip kernel: narrow layers only");
     static constexpr int NCH = CIN / 32;                                     // 32-channel chunks
-    static constexpr int ROWB = 64, ROWB8 = 32;                              // bytes per pixel per chunk: fp16 / e4m3 planes
-    static constexpr int A16_PLANE = STRIP_BOXW * ROWB, A16_PAD = (A16_PLANE + 511) / 512 * 512;      // SWIZZLE_64B repeats every 512 B
-    static constexpr int A8_PLANE = STRIP_BOXW * ROWB8, A8_PAD = (A8_PLANE + 255) / 256 * 256;        // SWIZZLE_32B repeats every 256 B
-    static constexpr int A_SLOT = F8 ? A16_PAD + 2 * A8_PAD : 2 * A16_PAD;   // [xh | xh8 | xl8]  or  [hi | lo]
-    static constexpr int A_TX = F8 ? A16_PLANE + 2 * A8_PLANE : 2 * A16_PLANE;
+    static constexpr int ROWB = 128;                                         // bytes per pixel per 32-channel block (one record)
+    static constexpr int A_TX = STRIP_BOXW * ROWB;                           // bytes one TMA box delivers
+    static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;               // SWIZZLE_128B repeats every 1024 B
     static constexpr int NROWS = 3 * COUT;                                   // B rows of one stage: ky-major
     static constexpr int W_STAGE = NROWS * 128;                              // per (chunk, kx): [wh 64 B rows | wh8 | wl8 32 B rows] or [wh | wl]
     static constexpr int W_BYTES = NCH * 3 * W_STAGE;
@@ -54,7 +55,7 @@ struct StripCfg {
     static constexpr int THREADS = (4 + 4 * EPI_SETS) * 32;                  // warps: 0 A producer | 1 MMA issuer | 2 weights + TMEM | 3 idle | 4.. epilogue
     static_assert(A_SLOTS >= 3, "need at least three staged rows");
     static_assert((1 + 2 * A_SLOTS + 2 * NB) * 8 + 4 <= BAR_BYTES, "barrier area overflow");
-    static_assert(W_STAGE % 512 == 0 && A_SLOT % 512 == 0 && (NROWS * 64) % 256 == 0, "swizzle pattern alignment");
+    static_assert(W_STAGE % 1024 == 0 && A_SLOT % 1024 == 0 && (NROWS * 64) % 256 == 0, "swizzle pattern alignment");
     static_assert(NB % 2 == 0, "block ownership alternates between the epilogue sets");
 };
 
@@ -70,10 +71,10 @@ struct StripParams {
                                 // 1 = no TMA stores, 2 = no staging either, 4 = no activation loads, 8 = no MMAs
 };
 
-template <int CIN, int COUT, bool F8>
+template <int CIN, int COUT, bool F8, bool OUT_REC>
 __global__ void __launch_bounds__(StripCfg<CIN, COUT, F8>::THREADS, 1)
-tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
-                        const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out8, const StripParams p) {
+tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
+                        const __grid_constant__ CUtensorMap tmap_out8, const StripParams p) {
     using C = StripCfg<CIN, COUT, F8>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -109,10 +110,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_in);
         prefetch_tmap(&tmap_out);
-        if constexpr (F8) {
-            prefetch_tmap(&tmap_in8);
-            prefetch_tmap(&tmap_out8);
-        }
+        if constexpr (F8 && !OUT_REC) prefetch_tmap(&tmap_out8);
     }
     if (warp == 2) {
         tmem_alloc(tmem_slot, 512);
@@ -151,14 +149,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         continue;
                     }
                     mbar_arrive_expect_tx(a_full(slot), (uint32_t)C::A_TX);
-                    const uint32_t dst = a_base + slot * C::A_SLOT;
-                    tma_load_4d(dst, &tmap_in, a_full(slot), c * 32, x0, r, 0);
-                    if constexpr (F8) {
-                        tma_load_4d(dst + C::A16_PAD, &tmap_in8, a_full(slot), c * 32, x0, r, 0);                 // xh8
-                        tma_load_4d(dst + C::A16_PAD + C::A8_PAD, &tmap_in8, a_full(slot), c * 32, x0, r, 1);     // xl8
-                    } else {
-                        tma_load_4d(dst + C::A16_PAD, &tmap_in, a_full(slot), c * 32, x0, r, 1);                  // lo
-                    }
+                    tma_load_4d(a_base + slot * C::A_SLOT, &tmap_in, a_full(slot), 0, c, x0, r);
                 }
             }
         }
@@ -171,13 +162,15 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     } else if (warp == 1) {
         // ===================== MMA issuer (one converged warp, an elected lane issues) =====================================
         constexpr uint32_t LO_FIXED = 1u << 16;
-        constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB, 4u) >> 32);     // 8-pixel groups are contiguous: SBO = 512 B
-        constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB8, 6u) >> 32);
+        constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB, 2u) >> 32);     // SWIZZLE_128B, 8-pixel groups are contiguous: SBO = 1024 B
         constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(8 * 64, 4u) >> 32);
         constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
         auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
         auto lo14 = [&](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | LO_FIXED; };
         uint32_t a_it = 0, nrow = 0, n_strips = 0;
+        // The barriers of the NEXT strip are probed (mbarrier.test_wait, non-blocking) before the current strip's last MMAs
+        // are issued, so the ~90-cycle round trip of a completed-barrier wait does not drain the tensor queue between strips.
+        uint32_t a_ready = 0, new_ready = 0;
         unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
         const long long t_begin = clock64();
         mbar_wait_prof(w_full, 0u, prof_on, w_bf);
@@ -194,7 +187,8 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 const int i_top = r + 1 - ky_lo - y0;         // unit-relative output row of ky_lo (the highest row index)
                 for (; next_new <= i_top; next_new++) {      // first contribution to these rows: their blocks must be drained + zeroed
                     const uint32_t n = nrow + (uint32_t)next_new;
-                    mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
+                    if (!new_ready) mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
+                    new_ready = 0;
                 }
                 tc_fence_after();
                 // ky ascending = output row descending = block ascending (mod NB): at most two runs of adjacent blocks
@@ -205,8 +199,16 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 const uint32_t id0 = make_idesc(128, (int)(cnt0 * COUT)), id1 = make_idesc(128, (int)(cnt1 * COUT));
                 for (int c = 0; c < C::NCH; c++, a_it++) {
                     const uint32_t slot = a_it % (uint32_t)C::A_SLOTS;
-                    mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
+                    if (!a_ready) mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
                     tc_fence_after();
+                    {   // probe what the next chunk / strip will wait for
+                        const uint32_t nx = a_it + 1u;
+                        a_ready = mbar_test(a_full(nx % (uint32_t)C::A_SLOTS), (nx / (uint32_t)C::A_SLOTS) & 1u);
+                        if (c + 1 == C::NCH) {
+                            const uint32_t n = nrow + (uint32_t)next_new;      // the next output row to acquire (numbering runs on across units)
+                            new_ready = mbar_test(blk_empty(blk_of(n)), (n / NB) & 1u);
+                        }
+                    }
                     const uint32_t ab = a_base + slot * C::A_SLOT;
 #pragma unroll
                     for (int kx = 0; kx < 3; kx++) {
@@ -220,15 +222,15 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                             const uint32_t bh = lo14(sb + brow * 64u);
                             umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bh), idesc, 1u);
                             umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
+                            // the record's quarters: +0 / +2 the fp16 K steps, +4 xh8 (or lo step 0), +6 xl8 (or lo step 1)   [16-byte units]
                             if constexpr (F8) {
-                                const uint32_t a8h = lo14(ab + C::A16_PAD + kx * C::ROWB8), a8l = lo14(ab + C::A16_PAD + C::A8_PAD + kx * C::ROWB8);
                                 const uint32_t b8h = lo14(sb + C::NROWS * 64u + brow * 32u), b8l = lo14(sb + C::NROWS * 96u + brow * 32u);
-                                umma_f8(d, desc(A8_HI32, a8l), desc(B8_HI32, b8h), idesc, 1u);       // xl8 * wh8
-                                umma_f8(d, desc(A8_HI32, a8h), desc(B8_HI32, b8l), idesc, 1u);       // xh8 * wl8
+                                umma_f8(d, desc(A_HI32, ah + 6u), desc(B8_HI32, b8h), idesc, 1u);    // xl8 * wh8
+                                umma_f8(d, desc(A_HI32, ah + 4u), desc(B8_HI32, b8l), idesc, 1u);    // xh8 * wl8
                             } else {
-                                const uint32_t al = lo14(ab + C::A16_PAD + kx * C::ROWB), bl = lo14(sb + C::NROWS * 64u + brow * 64u);
-                                umma_f16(d, desc(A_HI32, al), desc(B_HI32, bh), idesc, 1u);          // xl * wh
-                                umma_f16(d, desc(A_HI32, al + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
+                                const uint32_t bl = lo14(sb + C::NROWS * 64u + brow * 64u);
+                                umma_f16(d, desc(A_HI32, ah + 4u), desc(B_HI32, bh), idesc, 1u);     // xl * wh
+                                umma_f16(d, desc(A_HI32, ah + 6u), desc(B_HI32, bh + 2u), idesc, 1u);
                                 umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bl), idesc, 1u);          // xh * wl
                                 umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bl + 2u), idesc, 1u);
                             }
@@ -303,7 +305,10 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
                     const int gy = y0 + i - p.out_y0;
-                    if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, gy, cb);
+                    if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) {
+                        if constexpr (OUT_REC) epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, gx0, gy, cb);
+                        else epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, gy, cb);
+                    }
                 }
                 if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
             }
