@@ -6,11 +6,15 @@
 Workload (BASELINE.json config 3, the one the metric is quoted on): one full scale2.0x model pass
 (7 layers, 574 272 algorithmic FLOP per output pixel) over a synthetic 4096x4096 fp32 Y plane.
 With N > 1 ranks (torchrun, one process per GPU) the plane is 4096 wide x 4096*N tall, cut into N
-row bands (weak scaling).  Default exchange (--halo per-layer, the north_star): after every layer each
-rank sends its boundary row of the fresh activation to the neighbour (torch.distributed send/recv over
-NCCL/NVLink on zero-copy views of the library's band-session buffers); --halo input trades 7 input rows
-once and recomputes the overlap.  --strong cuts ONE size x size plane into N bands instead (BASELINE
-config 4: --size 8192 --strong).
+row bands (weak scaling).  Default exchange (--halo peer, the north_star's per-layer exchange done INSIDE
+the library): every rank maps its neighbours' band-session frames (CUDA IPC, handles travel once over
+torch.distributed) and after every layer one small kernel stores its boundary row straight into the
+neighbour's halo row over NVLink and handshakes through flag words -- nothing on the data path touches
+torch or NCCL.  --halo nccl moves the same rows with torch.distributed send/recv (cross-check), --halo input
+trades 7 input rows once and recomputes the overlap.  Before timing, N > 1 runs verify the exchange against the
+one-shot mode bit for bit ("halo_check").
+The line also carries `configs`: BASELINE config 4 (ONE 8192x8192 plane over the N GPUs, strong scaling) and
+config 5 (64 tiles of 512x512, noise2, tile t on GPU t mod N) measured in the same run.
 
 metric  Mpix/s = output pixels / time of the whole pass.
 value   inputs already resident in HBM, device entry point (w2x_convert_plane_device).
@@ -243,20 +247,32 @@ def run_ours(args):
     def exchange_halos():
         bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
 
-    band = None
-    if world > 1 and args.halo == "per-layer":
-        band = w2x.Band(ctx, model, W, H, up is not None, down is not None)
-        one_up, one_dn = (1 if up is not None else 0), (1 if down is not None else 0)
+    def make_band(width, rows):
+        """This rank's band session, wired to the neighbour ranks' sessions through peer memory (CUDA IPC)."""
+        b = w2x.Band(ctx, model, width, rows, up is not None, down is not None)
+        if args.halo == "peer":
+            blobs = [None] * world
+            dist.all_gather_object(blobs, b.export())
+            b.connect(blobs[rank - 1] if up is not None else None, blobs[rank + 1] if down is not None else None)
+        return b
 
-    def step_per_layer():
-        # the same 7-row buffer is reused: only the row adjacent to the band is needed here
-        bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
-        first = d_ext[ra - one_up:]
-        bands.run_band_per_layer(band, first.data_ptr(), W * 4, d_out.data_ptr(), W * 4, rank, world, dist, torch)
+    band = None
+    if world > 1 and args.halo in ("peer", "nccl"):
+        band = make_band(W, H)
+        one_up = 1 if up is not None else 0
+
+    def step_band(b, d_rows, d_res, width):
+        if args.halo == "peer":
+            b.run(d_rows.data_ptr(), width * 4, d_res.data_ptr(), width * 4)     # load, 7 x (layer, exchange kernel), gather: all in C++
+        else:
+            # the same 7-row buffer is reused: only the row adjacent to the band is needed here
+            bands.exchange_halos(d_ext, H, rank, world, n_model, dist)
+            first = d_ext[ra - one_up:]
+            bands.run_band_per_layer(b, first.data_ptr(), width * 4, d_res.data_ptr(), width * 4, rank, world, dist, torch)
 
     def step_device():
         if band is not None:
-            return step_per_layer()
+            return step_band(band, d_band, d_out, W)
         exchange_halos()
         if world == 1:
             ctx.convert_plane_device(model, d_band.data_ptr(), W, H, W * 4, d_out.data_ptr(), W * 4, True)
@@ -268,11 +284,7 @@ def run_ours(args):
             ctx.convert_plane(model, host_in.numpy(), True, out=host_out.numpy())
         else:
             d_band.copy_(host_in, non_blocking=True)
-            if band is not None:
-                step_per_layer()
-            else:
-                exchange_halos()
-                ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
+            step_device()
             host_out.copy_(d_out, non_blocking=True)
             stream.synchronize()
 
@@ -309,7 +321,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
-    if args.check and world > 1:
+    halo_check = None
+    if world > 1:
         got = d_out.clone()
         exchange_halos()
         ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
@@ -321,11 +334,65 @@ def run_ours(args):
             print(f"[check] per-rank bit-equality of halo={args.halo} vs one-shot input-halo band mode: {flags}", file=sys.stderr, flush=True)
         if not all(flags):
             raise SystemExit("multi-GPU check failed")
+        halo_check = True
     sampler = ClockSampler(local) if rank == 0 else None
     ms_dev, _, launches, layers, clocks = timed(step_device, args.steps, with_layers=True, sampler=sampler)
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     _, ms_e2e_wall, _, _, _ = timed(step_e2e, args.steps)
+
+    # ---- the other multi-GPU configurations of BASELINE.json, measured in the same run (driver-visible) ----
+    configs = {}
+    if not args.no_configs:
+        k_cfg, w_cfg = max(3, min(args.steps, 5)), 2
+
+        def leg(fn, sync_stream=False):
+            for _ in range(w_cfg):
+                fn()
+            ms, wall, _, _, _ = timed(fn, k_cfg)
+            return (wall if sync_stream else ms) / k_cfg
+
+        # config 4: ONE 8192x8192 plane over the N GPUs (strong scaling), per-layer halo exchange through peer memory
+        S = args.cfg4_size
+        if S % world == 0 and (world == 1 or args.halo == "peer"):
+            rows4 = S // world
+            x4 = np.random.default_rng(2).random((S, S), dtype=np.float32)[rank * rows4:(rank + 1) * rows4]
+            d4_in = torch.from_numpy(np.ascontiguousarray(x4)).cuda()
+            d4_out = torch.empty_like(d4_in)
+            del x4
+            if world == 1:
+                ms4 = leg(lambda: ctx.convert_plane_device(model, d4_in.data_ptr(), S, S, S * 4, d4_out.data_ptr(), S * 4, True))
+            else:
+                band4 = make_band(S, rows4)
+                ms4 = leg(lambda: band4.run(d4_in.data_ptr(), S * 4, d4_out.data_ptr(), S * 4))
+                torch.cuda.synchronize()
+                dist.barrier()
+                band4.close()
+            configs["cfg4_strong"] = {"workload": f"ONE {S}x{S} fp32 Y plane, scale2.0x, cut into {world} row band(s) of {rows4} rows" +
+                                      ("" if world == 1 else ", 1 boundary row per neighbour after every layer through peer memory"),
+                                      "n_gpus": world, "ms_per_step": ms4, "value": S * S / (ms4 * 1e-3) / 1e6, "unit": "Mpix/s", "scaling": "strong",
+                                      "steps": k_cfg, "timing": "CUDA events, max over ranks"}
+            del d4_in, d4_out
+            torch.cuda.empty_cache()
+        # config 5: 64 tiles of 512x512, noise2 weights, tile t on GPU t mod N, every GPU runs its tiles as one batched pass
+        z5 = np.load(os.path.join(ROOT, "tests", "golden", "models", "noise2_model.npz"))
+        model5 = w2x.Model.from_arrays([z5[f"w{i}"] for i in range(int(z5["n_layers"]))], [z5[f"b{i}"] for i in range(int(z5["n_layers"]))])
+        n_tiles, T = 64, 512
+        mine = list(range(rank, n_tiles, world))
+        if mine:
+            tiles = np.random.default_rng(3).random((n_tiles, T, T), dtype=np.float32)[mine]
+            h5_in = torch.from_numpy(np.ascontiguousarray(tiles)).pin_memory()
+            h5_out = torch.empty_like(h5_in).pin_memory()
+            d5_in = h5_in.cuda()
+            d5_out = torch.empty_like(d5_in)
+            ms5 = leg(lambda: ctx.convert_tiles_device(model5, d5_in.data_ptr(), d5_out.data_ptr(), len(mine), T, T))
+            ms5_e2e = leg(lambda: ctx.convert_tiles(model5, h5_in.numpy(), out=h5_out.numpy()), sync_stream=True)
+            configs["cfg5_tiles"] = {"workload": f"{n_tiles} tiles of {T}x{T} fp32, noise2_model.json weights, tile t on GPU t mod {world}; each GPU runs its "
+                                                 f"{len(mine)} tiles as ONE stacked frame per layer launch (w2x_convert_tiles); no exchange",
+                                     "n_gpus": world, "ms_per_batch": ms5, "value": n_tiles * T * T / (ms5 * 1e-3) / 1e6, "unit": "Mpix/s",
+                                     "e2e_value": n_tiles * T * T / (ms5_e2e * 1e-3) / 1e6, "e2e_note": "host tiles (pinned) -> host tiles through w2x_convert_tiles, wall clock, max over ranks",
+                                     "steps": k_cfg}
+            del d5_in, d5_out
 
     if rank == 0:
         peaks = load_peaks()
@@ -374,12 +441,16 @@ def run_ours(args):
                           else "f16 + 2x e4m3 correction products, f32 accumulate (fp32-faithful to ~3e-5)"),
                 "data": "synthetic",
                 "config": {"workload": workload_text(W, H, world),
-                           "weights": f"{MODEL}_model.json", "engine": args.engine, "halo_exchange": ("none" if world == 1 else "7 input rows per neighbour once, NCCL send/recv" if band is None
-                                             else "1 row of every intermediate activation per neighbour after every layer, NCCL send/recv"),
+                           "weights": f"{MODEL}_model.json", "engine": args.engine,
+                           "halo_exchange": ("none" if world == 1 else "7 input rows per neighbour once, NCCL send/recv" if band is None
+                                             else "1 row of every intermediate activation per neighbour after every layer, " +
+                                             ("stored straight into the neighbour's frame by the library (peer memory over NVLink, CUDA IPC; flag handshake, one kernel per layer)"
+                                              if args.halo == "peer" else "torch.distributed send/recv (NCCL)")),
+                           "comm": (None if world == 1 else "peer-memory stores + flags (csrc/engine_band.cu w2x_band_exchange)" if args.halo == "peer" else "NCCL send/recv"),
                            "l2": "no explicit flush: each step streams ~17 GB of activations per GPU, far beyond the 126 MB L2"},
                 "e2e": {"value": mpix_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
                         "timing": "host wall clock around K calls of the host-buffer C-ABI entry (sync inside the call), max over ranks"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "halo_check": halo_check, "configs": configs}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -398,9 +469,12 @@ def main():
     ap.add_argument("--precision", default="f8", choices=["f16x3", "f8"],
                     help="tcgen05 arithmetic: fp16 + two e4m3 correction products (the library default) or three fp16 products")
     ap.add_argument("--strong", action="store_true", help="multi-GPU: cut ONE size x size plane into N row bands (strong scaling) instead of one plane per GPU")
-    ap.add_argument("--check", action="store_true", help="multi-GPU: verify the per-layer result against the one-shot band mode, bit for bit")
-    ap.add_argument("--halo", default="per-layer", choices=["input", "per-layer"],
-                    help="multi-GPU exchange: 7 input rows once (recompute), or 1 activation row after every layer (north_star)")
+    ap.add_argument("--check", action="store_true", help="(kept for compatibility: the halo check always runs for N > 1)")
+    ap.add_argument("--halo", default="peer", choices=["input", "peer", "nccl"],
+                    help="multi-GPU exchange: 1 activation row after every layer through peer memory inside the library (north_star; default), "
+                         "the same rows through torch.distributed send/recv, or 7 input rows once (recompute)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg4 (8192^2 strong) and cfg5 (64 tiles) legs")
+    ap.add_argument("--cfg4-size", type=int, default=8192)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -132,6 +132,11 @@ W2X_API int w2x_ctx_set_block_walk(w2x_ctx *ctx, int mode);
  * processed in horizontal bands with a 7-row recompute halo.  0 = default (16 GiB). */
 W2X_API int w2x_ctx_set_scratch_limit(w2x_ctx *ctx, size_t bytes);
 
+/* Page-locked host memory for planes handed to the host-buffer entry points (optional: any host pointer works, pinned
+ * ones make the copies asynchronous and link-rate).  NULL when no device / out of memory: fall back to malloc. */
+W2X_API void *w2x_host_alloc(size_t bytes);
+W2X_API void w2x_host_free(void *p);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* Replaces bool w2xc::convertWithModels(cv::Mat& in, cv::Mat& out, models, bool blockSplitting)
  * (src/convertRoutine.hpp:25-28, src/convertRoutine.cpp:21-51): out = crop_n(L_{n-1}(...L_0(

@@ -60,6 +60,12 @@ def run_band_per_layer(band, ext_in, ext_stride_bytes, d_out, out_stride_bytes, 
     if torch is None:
         import torch
     from .capi import DevBytes
+    # The NCCL sends / receives are ordered on torch's CURRENT stream; the layer kernels must be queued on the same stream or
+    # a row could be sent before its layer wrote it (and the next layer could read a halo row before it landed).
+    cur = torch.cuda.current_stream().cuda_stream
+    if cur == 0:
+        raise RuntimeError("run_band_per_layer needs a non-default torch stream (stream handle 0 means 'the context's own stream')")
+    band._ctx.set_stream(cur)
     band.load(ext_in, ext_stride_bytes)
     views = band.__dict__.setdefault("_p2p_views", {})     # zero-copy tensor views of the session's halo rows, built once
     for k in range(band.steps):

@@ -37,6 +37,7 @@ ABI_SYMBOLS = (
     "w2x_band_connect_local", "w2x_band_exchange", "w2x_band_run", "w2x_convert_tiles", "w2x_convert_tiles_async",
     "w2x_convert_tiles_device", "w2x_multi_create", "w2x_multi_destroy", "w2x_multi_device_count", "w2x_multi_ctx",
     "w2x_multi_set_precision", "w2x_multi_set_log", "w2x_multi_convert_plane", "w2x_multi_convert_tiles",
+    "w2x_host_alloc", "w2x_host_free",
 )
 BAND_BLOB_BYTES = 320
 
@@ -112,6 +113,10 @@ def lib():
     L.w2x_band_step.argtypes = [vp, ci]
     L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
     L.w2x_band_finish.argtypes = [vp, vp, cs]
+    L.w2x_host_alloc.argtypes = [cs]
+    L.w2x_host_alloc.restype = vp
+    L.w2x_host_free.argtypes = [vp]
+    L.w2x_host_free.restype = None
     L.w2x_band_load_rows.argtypes = [vp, vp, cs]
     L.w2x_band_export.argtypes = [vp, vp]
     L.w2x_band_connect.argtypes = [vp, vp, vp]
@@ -342,12 +347,13 @@ class Context:
                                              in_stride_bytes, C.c_void_p(d_out), out_stride_bytes))
 
     # n independent planes of one shape in one batched pass (the reference's block loop; BASELINE config 5)
-    def convert_tiles(self, model: Model, tiles):
+    def convert_tiles(self, model: Model, tiles, out=None):
         x = np.ascontiguousarray(tiles, np.float32)
         if x.ndim != 3:
             raise ValueError("tiles must be [n][h][w]")
         n, h, w = x.shape
-        out = np.empty_like(x)
+        if out is None:
+            out = np.empty_like(x)
         ip = (C.c_void_p * n)(*[x[i].ctypes.data for i in range(n)])
         op = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
         _check(lib().w2x_convert_tiles(self._h, model._h, ip, op, n, w, h, w * 4, w * 4))

@@ -112,11 +112,38 @@ void note_kernel(w2x_ctx *ctx, int layer, const char *name) {
 }
 
 void logf(w2x_ctx *ctx, const char *fmt, int a, int b = 0) {
-    if (!ctx->log) return;
+    if (!ctx->log || ctx->log_muted) return;
     char line[128];
     snprintf(line, sizeof line, fmt, a, b);
     ctx->log(line, ctx->log_user);
 }
+
+// The progress lines the reference prints for one convertWithModels call (src/convertRoutine.cpp:67,133-134): per block
+// "start process block (c,r) ..." + one "Iteration #k..." per layer when the plane is split, else just the iterations.
+// The fused walk and the copy pipeline process the plane in other units, so they emit the reference's sequence up front.
+void emit_reference_progress(w2x_ctx *ctx, int w, int h, int n_layers, bool split) {
+    if (!ctx->log) return;
+    int nb = 1;
+    std::vector<int> tab;
+    if (split) {
+        const Config &cfg = config();
+        nb = block_table(w, h, cfg.block_w, cfg.block_h, n_layers, nullptr, 0, nullptr, nullptr);
+        if (nb < 1) return;
+        tab.resize((size_t)nb * 8);
+        block_table(w, h, cfg.block_w, cfg.block_h, n_layers, tab.data(), nb, nullptr, nullptr);
+    }
+    for (int i = 0; i < nb; i++) {
+        if (split) logf(ctx, "start process block (%d,%d) ...", tab[(size_t)i * 8 + 1], tab[(size_t)i * 8]);
+        for (int k = 1; k <= n_layers; k++) logf(ctx, "Iteration #%d...", k);
+    }
+}
+
+struct LogMute {   // silences the per-launch lines while a caller that already emitted the reference's sequence runs the layers
+    w2x_ctx *ctx;
+    bool prev;
+    explicit LogMute(w2x_ctx *c, bool on) : ctx(c), prev(c->log_muted) { if (on) c->log_muted = true; }
+    ~LogMute() { ctx->log_muted = prev; }
+};
 
 int pick_engine(w2x_ctx *ctx, const w2x_model *m) {
     int e = ctx->engine;
@@ -324,6 +351,8 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
         }
         return W2X_OK;
     }
+    if (split && !ctx->log_muted) emit_reference_progress(ctx, w, h, n, true);     // fused walk: the reference's per-block lines, up front
+    LogMute mute(ctx, split);
     return run_padded_plane(ctx, m, dm, engine, ctx->pad_buf, w, h, d_out, ostride);
 }
 
@@ -554,7 +583,7 @@ int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int
     int nb = ctx->host_bands > 0 ? ctx->host_bands : std::min(4, height / 512);
     const bool literal_walk = block_splitting && ctx->walk == W2X_WALK_BLOCKS && w2x_requires_splitting(width, height);
     if (nb > 8) nb = 8;
-    if (nb < 2 || literal_walk || ctx->log || !model || height / nb < 2 * n_model) {   // (a log sink wants the reference's exact line sequence)
+    if (nb < 2 || literal_walk || !model || height / nb < 2 * n_model) {
         CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0], (size_t)width * 4, in, in_stride_bytes, (size_t)width * 4, (size_t)height,
                                    cudaMemcpyHostToDevice, ctx->stream));
         int rc = convert_device(ctx, model, ctx->io_buf[0], width, height, (size_t)width * 4, 0, 0, ctx->io_buf[1],
@@ -565,6 +594,9 @@ int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int
         CU_CHECK(cudaStreamSynchronize(ctx->stream));
         return W2X_OK;
     }
+    // the copy pipeline cuts the plane its own way: the reference's progress lines for this plane go out first
+    emit_reference_progress(ctx, width, height, n_model, block_splitting && w2x_requires_splitting(width, height));
+    LogMute mute(ctx, true);
     std::vector<int> r0((size_t)nb + 1);
     for (int i = 0; i <= nb; i++) r0[(size_t)i] = (int)((long)height * i / nb);
     for (int i = 0; i < nb; i++) {
@@ -579,7 +611,12 @@ int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int
         const int above = i > 0 ? n_model : 0, below = i + 1 < nb ? n_model : 0;
         int rc = convert_device(ctx, model, ctx->io_buf[0] + (size_t)y * width, width, rows, (size_t)width * 4, above, below,
                                 ctx->io_buf[1] + (size_t)y * width, (size_t)width * 4, 0);
-        if (rc) return rc;
+        if (rc) {   // uploads / downloads already queued still touch the caller's buffers and the staging: drain them first
+            cudaStreamSynchronize(ctx->copy_in);
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copy_out);
+            return rc;
+        }
         CU_CHECK(cudaEventRecord(ctx->ev_done[i], ctx->stream));
         CU_CHECK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[i], 0));
         CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, ctx->io_buf[1] + (size_t)y * width,
@@ -665,6 +702,19 @@ int w2x_filter_layer(w2x_ctx *ctx, const w2x_model *model, int layer, const floa
     }
     CU_CHECK(cudaStreamSynchronize(ctx->stream));
     return W2X_OK;
+}
+
+// Page-locked host memory for planes: copies from / to it are truly asynchronous and run at the link rate (the reference's
+// cv::Mat data is pageable; host/w2xc.hpp's Plane allocates through this).  Falls back to malloc without a device.
+void *w2x_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 1;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess) return p;
+    cudaGetLastError();
+    return nullptr;
+}
+void w2x_host_free(void *p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) cudaGetLastError();
 }
 
 int w2x_ctx_launch_count(const w2x_ctx *ctx, uint64_t *n_launches) {

@@ -124,6 +124,7 @@ int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_ro
         if ((e = cudaMalloc(&b->act[i], b->act_bytes)) != cudaSuccess) return cleanup(e);
     if ((e = cudaMalloc(&b->flags, 64)) != cudaSuccess) return cleanup(e);
     if ((e = cudaMemset(b->flags, 0, 64)) != cudaSuccess) return cleanup(e);
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cleanup(e);       // the flag words are zero before a neighbour can write them
     *out_band = b.release();
     return W2X_OK;
 }
@@ -407,6 +408,9 @@ void multi_drop_plan(w2x_multi *m) {
 struct HostPin {
     void *p = nullptr;
     HostPin(const void *ptr, size_t bytes) {
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;   // already pinned (w2x_host_alloc, cudaHostAlloc, ...)
+        cudaGetLastError();
         if (bytes >= ((size_t)4 << 20) && cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable) == cudaSuccess) p = const_cast<void *>(ptr);
         else cudaGetLastError();
     }
@@ -487,6 +491,7 @@ int w2x_multi_convert_plane(w2x_multi *m, const w2x_model *model, const float *i
         m->plan_h = height;
         m->plan_precision = m->ctx[0]->precision;
     }
+    emit_reference_progress(m->ctx[0], width, height, n_layers, block_splitting && w2x_requires_splitting(width, height));
     HostPin pin_in(in, in_stride_bytes * (size_t)(height - 1) + (size_t)width * 4), pin_out(out, out_stride_bytes * (size_t)(height - 1) + (size_t)width * 4);
     // ---- queue everything: upload, the whole layer loop with its exchanges, download -- per GPU, one host thread ----
     for (int i = 0; i < nd; i++) {

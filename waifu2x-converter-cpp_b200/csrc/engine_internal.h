@@ -51,6 +51,7 @@ struct w2x_ctx {
     size_t scratch_limit = (size_t)16 << 30;
     w2x_log_fn log = nullptr;
     void *log_user = nullptr;
+    bool log_muted = false;            // the reference's line sequence of the current call has already been emitted
     uint64_t launches = 0;
     bool timing = false;
     std::vector<w2x::eng::TimedSpan> spans;
@@ -129,6 +130,7 @@ void note_kernel(w2x_ctx *ctx, int layer, const char *name);
 int ensure_tc(w2x_ctx *ctx);
 int check_ctx(w2x_ctx *ctx);
 int pick_engine(w2x_ctx *ctx, const w2x_model *m);
+void emit_reference_progress(w2x_ctx *ctx, int w, int h, int n_layers, bool split);   // the reference's stdout lines of one convertWithModels call
 bool layer_in_rec(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, int li);   // does layer li consume a RECORD frame (= run on the strip kernel)?
 // One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).
 // Only frame rows [out_y0, out_y0 + out_rows) are stored (out_rows < 0: the whole frame).

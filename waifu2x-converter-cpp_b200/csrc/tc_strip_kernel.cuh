@@ -68,7 +68,9 @@ struct StripParams {
     float out_scale;
     unsigned long long *prof;
     int dbg;                    // always 0 in product builds; -DW2X_EPI_EXPERIMENTS + W2X_DEBUG_STRIP (timing only, results WRONG):
-                                // 1 = no TMA stores, 2 = no staging either, 4 = no activation loads, 8 = no MMAs
+                                // 1 = no TMA stores, 2 = no staging either, 4 = no activation loads, 8 = no MMAs,
+                                // 16 = the issuer neither waits for nor probes a barrier, 32 = the epilogue does not touch TMEM,
+                                // 64 = the epilogue does not zero the blocks
 };
 
 template <int CIN, int COUT, bool F8, bool OUT_REC>
@@ -187,7 +189,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 const int i_top = r + 1 - ky_lo - y0;         // unit-relative output row of ky_lo (the highest row index)
                 for (; next_new <= i_top; next_new++) {      // first contribution to these rows: their blocks must be drained + zeroed
                     const uint32_t n = nrow + (uint32_t)next_new;
-                    if (!new_ready) mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
+                    if (!new_ready && !(p.dbg & 16)) mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
                     new_ready = 0;
                 }
                 tc_fence_after();
@@ -199,9 +201,9 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 const uint32_t id0 = make_idesc(128, (int)(cnt0 * COUT)), id1 = make_idesc(128, (int)(cnt1 * COUT));
                 for (int c = 0; c < C::NCH; c++, a_it++) {
                     const uint32_t slot = a_it % (uint32_t)C::A_SLOTS;
-                    if (!a_ready) mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
+                    if (!a_ready && !(p.dbg & 16)) mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
                     tc_fence_after();
-                    {   // probe what the next chunk / strip will wait for
+                    if (!(p.dbg & 16)) {   // probe what the next chunk / strip will wait for
                         const uint32_t nx = a_it + 1u;
                         a_ready = mbar_test(a_full(nx % (uint32_t)C::A_SLOTS), (nx / (uint32_t)C::A_SLOTS) & 1u);
                         if (c + 1 == C::NCH) {
@@ -283,18 +285,24 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                 tc_fence_after();
                 const uint32_t tcol = lane_base + blk * COUT;
                 uint32_t r[32];
-                tmem_ld32(tcol, r);
+                if (p.dbg & 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) r[k] = (uint32_t)(lane + k);
+                } else tmem_ld32(tcol, r);
 #pragma unroll
                 for (int cb = 0; cb < COUT / 32; cb++) {
                     float act[32];
-                    tmem_ld_wait_dep(r);
+                    if (!(p.dbg & 32)) tmem_ld_wait_dep(r);
 #pragma unroll
                     for (int k = 0; k < 32; k++) act[k] = __uint_as_float(r[k]);
-                    if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
-                    else {   // the row is in registers: zero its block and hand it back before the last conversion
+                    if (cb + 1 < COUT / 32) {
+                        if (!(p.dbg & 32)) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
+                    } else {   // the row is in registers: zero its block and hand it back before the last conversion
+                        if (!(p.dbg & (32 | 64))) {
 #pragma unroll
-                        for (int z = 0; z < COUT / 32; z++) tmem_st32_zero(tcol + (uint32_t)z * 32u);
-                        tmem_st_wait();
+                            for (int z = 0; z < COUT / 32; z++) tmem_st32_zero(tcol + (uint32_t)z * 32u);
+                            tmem_st_wait();
+                        }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(blk_empty(blk));
