@@ -197,6 +197,70 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def write_model_json(npz_path, json_path):
+    """The committed weight fixture (tests/golden/models/*.npz) in the reference's model-file format
+    (array of {nInputPlane, nOutputPlane, kW, kH, weight[o][i][ky][kx], bias[o]}; src/modelHandler.cpp:74-115)."""
+    z = np.load(npz_path)
+    layers = []
+    for i in range(int(z["n_layers"])):
+        w, b = z[f"w{i}"], z[f"b{i}"]
+        layers.append({"nInputPlane": int(w.shape[1]), "nOutputPlane": int(w.shape[0]), "kW": 3, "kH": 3,
+                       "weight": [[[[float(np.float64(v)) for v in row] for row in k] for k in o] for o in w], "bias": [float(v) for v in b]})
+    with open(json_path, "w") as f:
+        json.dump(layers, f)
+
+
+def host_api_legs(w2x, steps, size):
+    """The API a reference maintainer links, timed from C++ / the shell:
+      e2e_cpp   w2xc::convertWithModels (host/w2xc.hpp: w2xc::Plane in / out, progress lines on stdout) on the bench plane;
+      cli_cfg2  BASELINE config 2: the drop-in CLI on a 1920x1080 RGB image, -m noise_scale (noise1 + scale2.0x), wall clock."""
+    import tempfile
+    out = {}
+    pkg = os.path.dirname(w2x.lib_path())
+    d = tempfile.mkdtemp(prefix="w2x_bench_models_")
+    for name in ("scale2.0x", "noise1"):
+        write_model_json(os.path.join(ROOT, "tests", "golden", "models", f"{name}_model.npz"), os.path.join(d, f"{name}_model.json"))
+    exe = os.path.join(pkg, "w2x-bench-host")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe, os.path.join(d, "scale2.0x_model.json"), str(size), str(size), str(steps), "2"], capture_output=True, text=True, timeout=300)
+            line = [l for l in r.stdout.splitlines() if l.startswith("BENCH_JSON ")]
+            if r.returncode == 0 and line:
+                j = json.loads(line[-1][len("BENCH_JSON "):])
+                out["e2e_cpp"] = {"value": j["mpix_per_s"], "unit": "Mpix/s", "ms_per_step": j["ms_per_step"], "api": j["api"],
+                                  "note": "C++ caller, w2xc::Plane (page-locked) in/out, the reference's progress lines printed, copies inside the call"}
+            else:
+                out["e2e_cpp"] = {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            out["e2e_cpp"] = {"error": f"{type(e).__name__}: {e}"}
+    cli = os.path.join(pkg, "w2x-converter")
+    if os.path.exists(cli):
+        try:
+            rgb = np.random.default_rng(4).integers(0, 256, size=(1080, 1920, 3), dtype=np.uint8)
+            ppm = os.path.join(d, "in.ppm")
+            with open(ppm, "wb") as f:
+                f.write(b"P6\n1920 1080\n255\n" + rgb.tobytes())
+            best, stages = None, None
+            for _ in range(3):
+                t = time.perf_counter()
+                r = subprocess.run([cli, "-i", ppm, "-o", os.path.join(d, "out.png"), "-m", "noise_scale", "--model_dir", d], capture_output=True, text=True,
+                                   timeout=300, env=dict(os.environ, W2X_CLI_TIMING="1"))
+                dt = time.perf_counter() - t
+                if r.returncode != 0:
+                    raise RuntimeError((r.stderr or r.stdout)[-300:])
+                if best is None or dt < best:
+                    best = dt
+                    tl = [l for l in r.stderr.splitlines() if "w2x_cli_timing_ms" in l]
+                    stages = json.loads(tl[-1])["w2x_cli_timing_ms"] if tl else None
+            out["cli_cfg2"] = {"workload": "1920x1080 RGB (uniform noise, PPM in, PNG out), -m noise_scale: noise1 pass on 1920x1080 Y + scale2.0x pass on 3840x2160 Y",
+                               "wall_s_per_image": best, "conv_mpix_per_s": (1920 * 1080 * 5 / 1e6) / (stages["convertWithModels"] * 1e-3) if stages else None,
+                               "stages_ms": stages, "note": "process start to exit, best of 3 (includes CUDA context creation, model JSON parsing, host colour/resize plumbing, PNG deflate)"}
+        except Exception as e:
+            out["cli_cfg2"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -435,6 +499,7 @@ def run_ours(args):
                 desc += f" (preferred baseline failed: {type(e).__name__}: {e})"
             cpu = {"value": 498 * 498 / s / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind,
                    "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} of {os.cpu_count()} host threads (the reference's plane partition cannot use more; default -j 4)"}
+        host_api = host_api_legs(w2x, max(3, min(args.steps, 10)), args.size) if (world == 1 and not args.no_configs) else {}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
                 "dtype": ("f32" if args.engine == "fp32" else "f16x3 split operands, f32 accumulate (fp32-faithful)" if args.precision == "f16x3"
@@ -450,7 +515,7 @@ def run_ours(args):
                            "l2": "no explicit flush: each step streams ~17 GB of activations per GPU, far beyond the 126 MB L2"},
                 "e2e": {"value": mpix_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
                         "timing": "host wall clock around K calls of the host-buffer C-ABI entry (sync inside the call), max over ranks"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "halo_check": halo_check, "configs": configs}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "halo_check": halo_check, "configs": configs, **host_api}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -43,6 +43,9 @@
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#ifndef CV_Assert
+#define CV_Assert(expr) assert(expr)   // opencv2/core/base.hpp
+#endif
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 
 namespace cv {

@@ -32,9 +32,12 @@ def build(force: bool = False) -> str:
     (see oracle/reference_lib.py; on the GPU box the prebuilt file is used as it is)."""
     src = os.path.join(_HERE, "w2x_oracle.c")
     ref_so = os.path.join(_HERE, "_ref", "libw2x_reference.so")
-    ref_missing = os.path.exists("/root/reference/src/modelHandler.cpp") and not os.path.exists(ref_so)
+    have_ref = os.path.exists("/root/reference/src/modelHandler.cpp")
+    ref_missing = have_ref and not os.path.exists(ref_so)
     if force or ref_missing or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "all"])
+    elif have_ref:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])      # dependency-driven: e.g. the option-A binary after a product rebuild
     return _SO
 
 

@@ -127,6 +127,21 @@ def test_cli_flag_surface_and_exit_codes(cli, tmp_path, json_models):
     assert r.returncode == 255
 
 
+@pytest.mark.parametrize("mode", ["noise", "scale", "noise_scale"])
+def test_cli_without_a_device_fails_instead_of_writing_an_unprocessed_image(cli, tmp_path, json_models, mode):
+    """No CUDA device: the conversion cannot happen and there is no CPU fallback.  The reference cannot fail silently here
+    (a failing layer ends the process: src/convertRoutine.cpp:69 std::exit(-1)); neither may the drop-in -- in particular
+    `-m noise` must not write the un-denoised input and report success."""
+    cv2.imwrite(str(tmp_path / "in.png"), _test_image(24, 20))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([cli, "-i", "in.png", "-m", mode, "--model_dir", os.path.dirname(json_models["scale2.0x"])], capture_output=True, text=True,
+                       cwd=tmp_path, env=env)
+    assert r.returncode != 0, r.stdout
+    assert "process successfully done!" not in r.stdout
+    assert [f for f in os.listdir(tmp_path) if f != "in.png"] == []
+    assert "no CUDA device" in r.stderr or "CPU fallback" in r.stderr or "Error" in r.stderr
+
+
 def _reference_pipeline(bgr, mode, level, ratio, oracle_models, ncpu):
     """src/main.cpp restated with cv2 for the plumbing and the CPU oracle for convertWithModels."""
     image = cv2.cvtColor(bgr.astype(np.float32) * np.float32(1 / 255.0), cv2.COLOR_RGB2YUV)

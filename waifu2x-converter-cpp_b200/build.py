@@ -5,6 +5,7 @@
 Outputs (git-ignored, but they travel to the GPU box with a gpurun snapshot):
     waifu2x-converter-cpp_b200/libw2x_b200.so      the C-ABI product library (include/w2x_b200.h)
     waifu2x-converter-cpp_b200/w2x-converter       the drop-in CLI (host/main.cpp), if present
+    waifu2x-converter-cpp_b200/w2x-bench-host      times w2xc::convertWithModels through host/w2xc.hpp (bench.py's e2e_cpp leg)
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libw2x_b200.so")
 CLI = os.path.join(HERE, "w2x-converter")
+BENCH_HOST = os.path.join(HERE, "w2x-bench-host")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -69,6 +71,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"CLI build failed:\n{r.stdout}\n{r.stderr}")
+    bench_cpp = os.path.join(HERE, "host", "bench_host.cpp")
+    if os.path.exists(bench_cpp) and (force or _newer(BENCH_HOST, [bench_cpp, LIB] + _headers())):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
+               bench_cpp, "-o", BENCH_HOST, "-L", HERE, "-lw2x_b200", "-pthread", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"bench host build failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         print("built", LIB)
     return LIB

@@ -37,7 +37,7 @@ ABI_SYMBOLS = (
     "w2x_band_connect_local", "w2x_band_exchange", "w2x_band_run", "w2x_convert_tiles", "w2x_convert_tiles_async",
     "w2x_convert_tiles_device", "w2x_multi_create", "w2x_multi_destroy", "w2x_multi_device_count", "w2x_multi_ctx",
     "w2x_multi_set_precision", "w2x_multi_set_log", "w2x_multi_convert_plane", "w2x_multi_convert_tiles",
-    "w2x_host_alloc", "w2x_host_free",
+    "w2x_host_alloc", "w2x_host_free", "w2x_ctx_forget_model",
 )
 BAND_BLOB_BYTES = 320
 
@@ -113,6 +113,7 @@ def lib():
     L.w2x_band_step.argtypes = [vp, ci]
     L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
     L.w2x_band_finish.argtypes = [vp, vp, cs]
+    L.w2x_ctx_forget_model.argtypes = [vp, vp]
     L.w2x_host_alloc.argtypes = [cs]
     L.w2x_host_alloc.restype = vp
     L.w2x_host_free.argtypes = [vp]
@@ -277,6 +278,7 @@ class Context:
     __del__ = close
 
     def set_engine(self, engine): _check(lib().w2x_ctx_set_engine(self._h, engine))
+    def forget_model(self, model): _check(lib().w2x_ctx_forget_model(self._h, model._h))
     def set_precision(self, precision): _check(lib().w2x_ctx_set_precision(self._h, precision))
     def get_precision(self): return lib().w2x_ctx_get_precision(self._h)
     def set_stream(self, stream_ptr): _check(lib().w2x_ctx_set_stream(self._h, C.c_void_p(stream_ptr)))

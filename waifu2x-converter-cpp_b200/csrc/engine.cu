@@ -404,18 +404,34 @@ int w2x_ctx_create(int device, w2x_ctx **out_ctx) {
     return W2X_OK;
 }
 
+static void free_dev_model(DevModel &dm) {
+    for (auto p : dm.w) cudaFree(p);
+    for (auto p : dm.b) cudaFree(p);
+    for (auto p : dm.pack) cudaFree(p);
+    for (auto p : dm.pack8) cudaFree(p);
+    for (auto p : dm.strip) cudaFree(p);
+    for (auto p : dm.strip8) cudaFree(p);
+}
+
+// Drops the context's device copies of a model (weights, packed operands); call it before w2x_model_free in a long-lived
+// context that cycles through many models.  The next conversion with the same model uploads it again.
+int w2x_ctx_forget_model(w2x_ctx *ctx, const w2x_model *model) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model) return fail(W2X_ERR_ARG, "w2x_ctx_forget_model: NULL model");
+    auto it = ctx->models.find(model->uid);
+    if (it == ctx->models.end()) return W2X_OK;
+    DeviceGuard g(ctx->device);
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    free_dev_model(it->second);
+    ctx->models.erase(it);
+    return W2X_OK;
+}
+
 void w2x_ctx_destroy(w2x_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto &kv : ctx->models) {
-        for (auto p : kv.second.w) cudaFree(p);
-        for (auto p : kv.second.b) cudaFree(p);
-        for (auto p : kv.second.pack) cudaFree(p);
-        for (auto p : kv.second.pack8) cudaFree(p);
-        for (auto p : kv.second.strip) cudaFree(p);
-        for (auto p : kv.second.strip8) cudaFree(p);
-    }
+    for (auto &kv : ctx->models) free_dev_model(kv.second);
     for (int i = 0; i < 2; i++) {
         cudaFree(ctx->buf[i]);
         cudaFree(ctx->io_buf[i]);

@@ -239,6 +239,7 @@ struct Parser {
 bool num_field(const JVal &o, const char *key, int &out) {
     const JVal *v = o.get(key);
     if (!v || v->t != JVal::Num) return false;
+    if (!(v->num > -1e9 && v->num < 1e9)) return false;   // NaN / huge values: the cast below would be undefined behaviour
     out = static_cast<int>(v->num);  // static_cast<int>(get<double>()), src/modelHandler.hpp:50-52
     return true;
 }
@@ -468,6 +469,10 @@ int w2x_model_load_json(const char *path, w2x_model **out_model) {
         return w2x::parse_model_json(path, out_model);
     } catch (const std::bad_alloc &) {
         return w2x::fail(W2X_ERR_NOMEM, "w2x_model_load_json: out of memory");
+    } catch (const std::exception &e) {          // nothing may cross the C ABI
+        return w2x::fail(W2X_ERR_PARSE, "w2x_model_load_json: %s", e.what());
+    } catch (...) {
+        return w2x::fail(W2X_ERR_PARSE, "w2x_model_load_json: unexpected failure");
     }
 }
 

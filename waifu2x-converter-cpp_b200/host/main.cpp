@@ -2,6 +2,7 @@
 // Same flags, defaults, progress messages, output naming and exit codes; the two convertWithModels calls
 // (src/main.cpp:96,148) go to libw2x_b200.so through host/w2xc.hpp, everything around them is restated from
 // src/main.cpp line by line with host/imgproc.hpp + host/imageio.hpp standing in for OpenCV.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -25,6 +26,7 @@ struct Arg {
     std::vector<std::string> allowed;
     std::string value;
     bool set = false;
+    bool hidden = false;   // accepted, but not part of the reference's flag surface: left out of --help and the usage lines
 };
 
 struct CmdLine {
@@ -46,7 +48,8 @@ struct CmdLine {
     }
     void brief(std::ostream &os) const {
         os << "Brief USAGE: \n   " << prog << " ";
-        for (auto it = args.rbegin(); it != args.rend(); ++it) os << " " << shortid(*it);
+        for (auto it = args.rbegin(); it != args.rend(); ++it)
+            if (!it->hidden) os << " " << shortid(*it);
         os << " [--] [--version] [-h]\n\nFor complete USAGE and HELP type: \n   " << prog << " --help\n\n";
     }
     [[noreturn]] void parse_error(const std::string &argid, const std::string &text) const {
@@ -56,9 +59,11 @@ struct CmdLine {
     }
     void usage() const {
         std::cout << "\nUSAGE: \n\n   " << prog << " ";
-        for (auto it = args.rbegin(); it != args.rend(); ++it) std::cout << " " << shortid(*it);
+        for (auto it = args.rbegin(); it != args.rend(); ++it)
+            if (!it->hidden) std::cout << " " << shortid(*it);
         std::cout << " [--] [--version] [-h]\n\n\nWhere: \n\n";
         for (auto it = args.rbegin(); it != args.rend(); ++it) {
+            if (it->hidden) continue;
             std::string t = it->allowed.empty() ? it->type : "";
             for (size_t i = 0; i < it->allowed.size(); i++) t += (i ? "|" : "") + it->allowed[i];
             std::cout << "   " << (it->flag.empty() ? "" : "-" + it->flag + " <" + t + ">,  ") << "--" << it->name << " <" << t << ">\n     "
@@ -128,7 +133,15 @@ int main(int argc, char **argv) {
     cmd.add("", "scale_ratio", "custom scale ratio", false, "2.0", "double");
     cmd.add("", "model_dir", "path to custom model directory (don't append last / )", false, "models", "string");
     cmd.add("j", "jobs", "number of threads launching at the same time", false, "4", "integer");
+    // the sibling of -j for this implementation (src/main.cpp:58-60 is where the reference declares -j): planes are cut into
+    // this many row bands, one per GPU, halo rows exchanged between the GPUs after every layer; W2X_GPUS does the same
+    cmd.add("", "gpus", "number of GPUs the conversion is spread over", false, "1", "integer").hidden = true;
     cmd.parse(argc, argv);
+    if (std::atoi(cmd.get("gpus").c_str()) > 1) w2xc::gpuRuntime::setNumberOfGpus(std::atoi(cmd.get("gpus").c_str()));
+    const bool timing = std::getenv("W2X_CLI_TIMING") != nullptr;   // stage times (ms) as one JSON line on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    double t_conv = 0.0;
 
     const std::string mode = cmd.get("mode"), inputFile = cmd.get("input_file"), modelDir = cmd.get("model_dir");
     const int nrLevel = std::atoi(cmd.get("noise_level").c_str());
@@ -141,6 +154,7 @@ int main(int argc, char **argv) {
         std::cerr << "Error : couldn't read image " << inputFile << " (" << ioerr << ")" << std::endl;
         std::exit(-1);
     }
+    const double t_read = now();
     w2ximg::Image3f image = w2ximg::from_u8(in8.bgr.data(), in8.width, in8.height);
     w2ximg::rgb2yuv(image);
 
@@ -153,8 +167,13 @@ int main(int argc, char **argv) {
         std::vector<std::unique_ptr<w2xc::Model>> models;
         if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) std::exit(-1);
         w2xc::Plane imageY = plane_of(image, 0), out;
-        w2xc::convertWithModels(imageY, out, models);        // return value ignored, as the reference does (:96)
-        if (!out.empty()) w2ximg::set_channel(image, 0, out.data, out.stride_bytes / 4);
+        const double t0 = now();
+        // The reference ignores the return value here (:96) because a failing layer has already ended the process inside
+        // convertWithModelsBasic (src/convertRoutine.cpp:69: std::exit(-1)).  The library never exits, so the same outcome
+        // is produced here: no device, out of memory or a CUDA error must not write the un-denoised image with exit code 0.
+        if (!w2xc::convertWithModels(imageY, out, models) || out.empty()) std::exit(-1);
+        t_conv += now() - t0;
+        w2ximg::set_channel(image, 0, out.data, out.stride_bytes / 4);
     }
 
     // ===== scaling phase ===== (:104-169)
@@ -173,10 +192,12 @@ int main(int argc, char **argv) {
             w2ximg::Image3f nearest = w2ximg::resize(image, w2, h2, w2ximg::NEAREST);    // :135
             w2xc::Plane imageY = plane_of(nearest, 0), out;
             w2ximg::Image3f bicubic = w2ximg::resize(image, w2, h2, w2ximg::CUBIC);      // :144
+            const double t0 = now();
             if (!w2xc::convertWithModels(imageY, out, models)) {
                 std::cerr << "w2xc::convertWithModels : something error has occured.\nstop." << std::endl;
                 std::exit(1);
             }
+            t_conv += now() - t0;
             w2ximg::set_channel(bicubic, 0, out.data, out.stride_bytes / 4);              // merge, :154
             image = std::move(bicubic);
         }
@@ -199,10 +220,15 @@ int main(int argc, char **argv) {
         if (mode.find("scale") != mode.npos) outputFileName = outputFileName + "(x" + std::to_string(scaleRatio) + ")";
         outputFileName += ".png";
     }
+    const double t_write0 = now();
     if (!w2xio::imwrite(outputFileName, out8.data(), image.width, image.height)) {
         std::cerr << "Error : couldn't write " << outputFileName << std::endl;
         std::exit(-1);
     }
+    if (timing)
+        std::cerr << "{\"w2x_cli_timing_ms\": {\"imread\": " << t_read - t_start << ", \"convertWithModels\": " << t_conv
+                  << ", \"colour_resize_plumbing\": " << (t_write0 - t_read) - t_conv << ", \"imwrite\": " << now() - t_write0
+                  << ", \"total\": " << now() - t_start << "}}" << std::endl;
     std::cout << "process successfully done!" << std::endl;
     return 0;
 }

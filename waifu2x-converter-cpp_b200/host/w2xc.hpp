@@ -13,6 +13,7 @@
 #define W2XC_HPP_
 
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -26,18 +27,28 @@
 
 namespace w2xc {
 
-// A CV_32FC1 matrix stand-in: fp32, row-major, possibly a strided view (like a cv::Mat ROI).
+// A CV_32FC1 matrix stand-in: fp32, row-major, possibly a strided view (like a cv::Mat ROI).  Storage is page-locked
+// (w2x_host_alloc) when a device is present, so the host<->device copies inside convertWithModels run at the link rate and
+// overlap the layers; plain calloc otherwise.
 struct Plane {
     int width = 0, height = 0;
     size_t stride_bytes = 0;
     float *data = nullptr;
-    std::shared_ptr<std::vector<float>> owner;   // empty for views
+    std::shared_ptr<void> owner;   // empty for views
 
     Plane() {}
     Plane(int w, int h) { create(w, h); }
     void create(int w, int h) {
-        owner = std::make_shared<std::vector<float>>((size_t)w * h, 0.0f);   // cv::Mat::zeros
-        width = w; height = h; stride_bytes = (size_t)w * sizeof(float); data = owner->data();
+        const size_t bytes = (size_t)w * h * sizeof(float);
+        void *p = bytes >= (size_t)(1 << 20) ? w2x_host_alloc(bytes) : nullptr;   // small planes are not worth a page-locked allocation
+        if (p) {
+            std::memset(p, 0, bytes);                                         // cv::Mat::zeros
+            owner = std::shared_ptr<void>(p, w2x_host_free);
+        } else {
+            p = std::calloc(bytes ? bytes : 1, 1);
+            owner = std::shared_ptr<void>(p, std::free);
+        }
+        width = w; height = h; stride_bytes = (size_t)w * sizeof(float); data = static_cast<float *>(p);
     }
     bool empty() const { return data == nullptr; }
     float &at(int y, int x) { return *reinterpret_cast<float *>(reinterpret_cast<char *>(data) + (size_t)y * stride_bytes + (size_t)x * 4); }
@@ -49,30 +60,53 @@ struct Plane {
     }
     Plane clone() const {                                                   // cv::Mat::copyTo / clone
         Plane p(width, height);
-        for (int y = 0; y < height; y++)
-            for (int x = 0; x < width; x++) p.at(y, x) = at(y, x);
+        for (int y = 0; y < height; y++) std::memcpy(&p.at(y, 0), &at(y, 0), (size_t)width * sizeof(float));
         return p;
     }
 };
 
-// Process-wide GPU context shared by Model::filter and convertWithModels (the reference keeps its
-// process-wide state in the modelUtility singleton as well).
+// Process-wide GPU runtime shared by Model::filter and convertWithModels (the reference keeps its process-wide state in
+// the modelUtility singleton as well).  The number of GPUs is the sibling of the reference's -j (src/main.cpp:58-60):
+// gpuRuntime::setNumberOfGpus(n) before the first conversion, or W2X_GPUS=n in the environment; planes are then cut into n
+// row bands with a per-layer halo exchange between the GPUs (bit-identical to one GPU).  W2X_DEVICE picks the first device.
 class gpuRuntime {
 public:
-    static w2x_ctx *context() {
-        static gpuRuntime rt;
-        return rt.ctx_;
+    static bool setNumberOfGpus(int n) {
+        if (n < 1 || created()) return false;
+        requested() = n;
+        return true;
     }
+    static w2x_ctx *context() { return instance().ctx_; }
+    static w2x_multi *multi() { return instance().multi_; }   // nullptr with one GPU
 private:
+    static int &requested() { static int n = 0; return n; }
+    static bool &created() { static bool c = false; return c; }
+    static gpuRuntime &instance() { static gpuRuntime rt; return rt; }
     w2x_ctx *ctx_ = nullptr;
+    w2x_multi *multi_ = nullptr;
     gpuRuntime() {
-        const char *dev = std::getenv("W2X_DEVICE");
-        if (w2x_ctx_create(dev ? std::atoi(dev) : 0, &ctx_) != W2X_OK) {
+        created() = true;
+        const char *dev = std::getenv("W2X_DEVICE"), *ng = std::getenv("W2X_GPUS");
+        const int first = dev ? std::atoi(dev) : 0;
+        int n = requested() > 0 ? requested() : (ng ? std::atoi(ng) : 1);
+        if (n > 1) {
+            std::vector<int> ids;
+            for (int i = 0; i < n; i++) ids.push_back(first + i);
+            if (w2x_multi_create(ids.data(), n, &multi_) != W2X_OK) {
+                std::cerr << "Error : " << w2x_last_error() << std::endl;
+                multi_ = nullptr;
+                return;
+            }
+            ctx_ = w2x_multi_ctx(multi_, 0);
+        } else if (w2x_ctx_create(first, &ctx_) != W2X_OK) {
             std::cerr << "Error : " << w2x_last_error() << std::endl;
             ctx_ = nullptr;
         }
     }
-    ~gpuRuntime() { w2x_ctx_destroy(ctx_); }
+    ~gpuRuntime() {
+        if (multi_) w2x_multi_destroy(multi_);
+        else w2x_ctx_destroy(ctx_);
+    }
 };
 
 class modelUtility;
@@ -139,6 +173,9 @@ public:
         }
         return true;
     }
+#ifdef W2X_WITH_OPENCV
+    bool filter(std::vector<cv::Mat> &inputPlanes, std::vector<cv::Mat> &outputPlanes);   // the reference's signature, defined below
+#endif
 };
 
 class modelUtility {
@@ -188,7 +225,12 @@ inline bool convertWithModels(Plane &inputPlane, Plane &outputPlane, std::vector
     } printer;
     (void)printer;
     w2x_ctx_set_log(ctx, &Printer::line, nullptr);   // "Iteration #k..." / "start process block (c,r) ..."
-    int rc = w2x_convert_plane(ctx, models[0]->file_.get(), inputPlane.data, inputPlane.width, inputPlane.height,
+    int rc;
+    if (w2x_multi *mg = gpuRuntime::multi())
+        rc = w2x_multi_convert_plane(mg, models[0]->file_.get(), inputPlane.data, inputPlane.width, inputPlane.height, inputPlane.stride_bytes,
+                                     outputPlane.data, outputPlane.stride_bytes, blockSplitting ? 1 : 0);
+    else
+        rc = w2x_convert_plane(ctx, models[0]->file_.get(), inputPlane.data, inputPlane.width, inputPlane.height,
                                inputPlane.stride_bytes, outputPlane.data, outputPlane.stride_bytes, blockSplitting ? 1 : 0);
     if (rc != W2X_OK) {
         std::cerr << w2x_last_error() << std::endl;
@@ -198,6 +240,8 @@ inline bool convertWithModels(Plane &inputPlane, Plane &outputPlane, std::vector
 }
 
 #ifdef W2X_WITH_OPENCV
+// The reference's own signatures (src/modelHandler.hpp:87-88, src/convertRoutine.hpp:25-28) on cv::Mat: CV_32FC1 planes are
+// viewed in place (no copy), outputs are allocated like the reference does (cv::Mat::zeros).
 inline Plane viewOf(cv::Mat &m) {
     CV_Assert(m.type() == CV_32FC1);
     Plane p; p.width = m.cols; p.height = m.rows; p.stride_bytes = m.step; p.data = m.ptr<float>();
@@ -210,6 +254,23 @@ inline bool convertWithModels(cv::Mat &inputPlane, cv::Mat &outputPlane, std::ve
     bool ok = convertWithModels(in, o, models, blockSplitting);
     outputPlane = out;
     return ok;
+}
+// bool Model::filter(std::vector<cv::Mat>& inputPlanes, std::vector<cv::Mat>& outputPlanes)  (call site: src/test.cpp:76)
+inline bool Model::filter(std::vector<cv::Mat> &inputPlanes, std::vector<cv::Mat> &outputPlanes) {
+    Model &model = *this;
+    std::vector<Plane> in, out;
+    for (auto &m : inputPlanes) {
+        if (!inputPlanes.empty() && m.step != inputPlanes[0].step) m = m.clone();   // one row stride for all planes (dense after clone)
+        in.push_back(viewOf(m));
+    }
+    if (!model.filter(in, out)) return false;
+    outputPlanes.clear();
+    for (auto &p : out) {
+        cv::Mat m = cv::Mat::zeros(cv::Size(p.width, p.height), CV_32FC1);
+        for (int y = 0; y < p.height; y++) std::memcpy(m.ptr<float>(y), &p.at(y, 0), (size_t)p.width * sizeof(float));
+        outputPlanes.push_back(m);
+    }
+    return true;
 }
 #endif
 
