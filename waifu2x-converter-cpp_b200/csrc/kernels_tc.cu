@@ -237,7 +237,7 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
     p.out_y0 = out_y0;
     p.out_rows = out_rows;
     p.tiles_x = (pw + REGION - 1) / REGION;
-    p.n_tilesets = p.tiles_x * ((ph + REGION - 1) / REGION);
+    p.n_tilesets = p.tiles_x * ((out_rows + REGION - 1) / REGION);   // tile-sets tile the store window (TMA store coordinates stay non-negative)
     p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
 #ifdef W2X_EPI_EXPERIMENTS   // timing experiments only (results are wrong): build with -DW2X_EPI_EXPERIMENTS, then W2X_DEBUG_EPI=1|2
@@ -286,7 +286,7 @@ static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw
     for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
     for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
     CUtensorMap omaps[2];
-    dim3 grid((pw + 31) / 32, (ph + 7) / 8);
+    dim3 grid((pw + 31) / 32, (out_rows + 7) / 8);   // blocks tile the store window
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
     if (out_rec) {
         if (make_rec_map(&omaps[0], out, COUT, pw, ph, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;

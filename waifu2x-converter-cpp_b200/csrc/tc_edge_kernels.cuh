@@ -28,7 +28,7 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
     extern __shared__ uint8_t first_smem[];
     const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + wy;     // threads past the frame edge compute clamped copies; TMA clips them
+    const int x = blockIdx.x * 32 + lane, y = out_y0 + blockIdx.y * 8 + wy;     // blocks tile the store window; threads past the frame edge compute clamped copies, TMA clips them
     float v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ky++)
@@ -100,7 +100,7 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8 - out_y0;   // the store maps cover frame rows [out_y0, ...)
+            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;   // window-relative: the store maps cover frame rows [out_y0, ...)
             if constexpr (REC)
                 asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                              ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(0), "r"(cb), "r"(x0), "r"(y0) : "memory");

@@ -72,7 +72,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             unsigned long long w_a = 0;
             for (int ts = blockIdx.x; ts < p.n_tilesets; ts += gridDim.x) {
                 const int ty = ts / p.tiles_x, tx = ts - ty * p.tiles_x;
-                const int x0 = tx * REGION - 1, y0 = ty * REGION - 1;   // box origin incl. ring (may be -1)
+                const int x0 = tx * REGION - 1, y0 = p.out_y0 + ty * REGION - 1;   // box origin incl. ring (may be -1); tile-sets tile the store window
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
                     const uint32_t slot = it & 1u, round = it >> 1;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
@@ -244,7 +244,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
-            const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
+            const int fy = p.out_y0 + ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
             const bool inside = fy < p.Hp && fx < p.Wp && fy >= p.out_y0 && fy < p.out_y0 + p.out_rows;
             float pt[9];                                   // FUSE: nine per-tap dot products of this pixel
 #pragma unroll
@@ -280,7 +280,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
                 }
                 if constexpr (!FUSE) {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q - p.out_y0, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);   // (row coordinates of the store maps are window-relative, never negative)
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll

@@ -43,7 +43,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     const bool is_leader = rank == 0;
     const int n_pairs_cl = (int)(gridDim.x >> 1), pair_id = (int)(blockIdx.x >> 1);
     const int n_pair_sets = (p.n_tilesets + 1) / 2;          // tile-sets are taken two at a time: (2q, 2q+1) -> (CTA 0, CTA 1)
-    const int tiles_y = (p.Hp + REGION - 1) / REGION;
+    const int tiles_y = (p.out_rows + REGION - 1) / REGION;   // tile-sets tile the store window [out_y0, out_y0 + out_rows)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
@@ -92,7 +92,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
                 int tx, ty;
                 region_of(q, tx, ty);
-                const int x0 = tx * REGION - 1, y0 = ty * REGION - 1;
+                const int x0 = tx * REGION - 1, y0 = p.out_y0 + ty * REGION - 1;
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
                     const uint32_t slot = it & 1u, round = it >> 1;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
@@ -238,7 +238,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q4 * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
-            const int fy = ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
+            const int fy = p.out_y0 + ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
             const bool inside = fy < p.Hp && fx < p.Wp && fy >= p.out_y0 && fy < p.out_y0 + p.out_rows;
             float pt[9];
 #pragma unroll
@@ -274,7 +274,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                         }
                     }
                 } else {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4 - p.out_y0, cb);
+                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4, cb);
                 }
             }
             if constexpr (FUSE) {
