@@ -343,9 +343,20 @@ def run_ours(args):
         else:
             ctx.convert_band_device(model, d_ext.data_ptr(), W, H, ra, rb, W * 4, d_out.data_ptr(), W * 4)
 
+    slab = None
+    if world > 1 and args.halo == "peer":
+        # host rows in / out: the rank's slab is cut into sub-bands (upload / layers / download overlap); its outer edges
+        # exchange a halo row per layer with the neighbour ranks' slabs; odd ranks walk bottom -> top (see w2x_slab_create)
+        slab = w2x.Slab(ctx, model, W, H, up is not None, down is not None, order=rank & 1)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, slab.export())
+        slab.connect(blobs[rank - 1] if up is not None else None, blobs[rank + 1] if down is not None else None)
+
     def step_e2e():
         if world == 1:
             ctx.convert_plane(model, host_in.numpy(), True, out=host_out.numpy())
+        elif slab is not None:
+            slab.convert(host_in.numpy(), host_out.numpy())
         else:
             d_band.copy_(host_in, non_blocking=True)
             step_device()

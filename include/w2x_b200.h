@@ -199,8 +199,13 @@ W2X_API int w2x_convert_band_device(w2x_ctx *ctx, const w2x_model *model, const 
  * partials instead of activations.  Requires the tcgen05 engine.  The layer kernels never store a band's
  * halo rows, so a neighbour's row may arrive at any time after the previous exchange. */
 typedef struct w2x_band w2x_band;
+/* What lies beyond a band's first / last row: */
+#define W2X_EDGE_BORDER 0      /* the image border: replicate (src/convertRoutine.cpp:35,96) */
+#define W2X_EDGE_NEIGHBOUR 1   /* another GPU's band: one halo row, exchanged after every layer */
+#define W2X_EDGE_OVERLAP 2     /* n_layers real input rows supplied with the band and recomputed (no exchange): the seam
+                                  between two sub-bands of ONE GPU (w2x_slab_*), input read through w2x_band_load_rows */
 W2X_API int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_rows,
-                            int has_up_neighbour, int has_down_neighbour, w2x_band **out_band);
+                            int up_edge, int down_edge, w2x_band **out_band);
 W2X_API void w2x_band_destroy(w2x_band *band);
 W2X_API int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes);
 W2X_API int w2x_band_load_rows(w2x_band *band, const float *d_in_own_rows, size_t in_stride_bytes);
@@ -218,6 +223,25 @@ W2X_API int w2x_band_connect_local(w2x_band *band, w2x_band *up, w2x_band *down)
 W2X_API int w2x_band_exchange(w2x_band *band, int step /* -1 after w2x_band_load_rows */);
 W2X_API int w2x_band_run(w2x_band *band, const float *d_in_own_rows, size_t in_stride_bytes, float *d_out,
                          size_t out_stride_bytes);
+
+/* ---- one GPU's slab of a multi-GPU plane, HOST buffers ------------------------------------------------ */
+/* What a rank of a multi-process job (or one GPU of w2x_multi_*) owns of the plane: rows in pinned host memory go in,
+ * rows come out.  The slab is cut into sub-bands so that uploads, layers and downloads overlap; seams inside the slab are
+ * W2X_EDGE_OVERLAP (recomputed, local data), its outer edges exchange a halo row per layer with the neighbour slab.
+ * order: 0 = walk the sub-bands top -> bottom, 1 = bottom -> top; neighbouring slabs must alternate (rank parity) so that
+ * both sides of a boundary are in flight at the same time.  n_sub = 0: automatic.  Blobs are 2 * W2X_BAND_BLOB_BYTES. */
+typedef struct w2x_slab w2x_slab;
+W2X_API int w2x_slab_create(w2x_ctx *ctx, const w2x_model *model, int width, int rows, int has_up_neighbour,
+                            int has_down_neighbour, int order, int n_sub, w2x_slab **out_slab);
+W2X_API void w2x_slab_destroy(w2x_slab *slab);
+W2X_API int w2x_slab_export(w2x_slab *slab, void *blob /* 2 * W2X_BAND_BLOB_BYTES */);
+W2X_API int w2x_slab_connect(w2x_slab *slab, const void *up_blob, const void *down_blob);
+W2X_API int w2x_slab_connect_local(w2x_slab *slab, w2x_slab *up, w2x_slab *down);
+W2X_API int w2x_slab_convert(w2x_slab *slab, const float *in_rows, size_t in_stride_bytes, float *out_rows,
+                             size_t out_stride_bytes);
+W2X_API int w2x_slab_convert_async(w2x_slab *slab, const float *in_rows, size_t in_stride_bytes, float *out_rows,
+                                   size_t out_stride_bytes);
+W2X_API int w2x_slab_synchronize(w2x_slab *slab);
 
 /* ---- independent planes of one shape in one pass ---------------------------------------------- */
 /* The reference's block loop (src/convertRoutine.cpp:114-165) and BASELINE config 5 (64 x 512x512 tiles):

@@ -55,8 +55,34 @@ for precision in (1, 0):
         c.close()
     print(f"band sessions + peer exchange, precision {precision}, devices {devs}: bit-identical to one GPU", flush=True)
 
+# ---- w2x_slab_*: host rows in / out, copy pipeline over sub-bands, outer edges exchanged with the neighbour slabs ----
+W2, H2 = 190, 420
+x2 = oracle.seeded_plane(W2, H2, 9, "uniform")
+ref = w2x.Context(0, engine=w2x.ENGINE_TC)
+whole2 = ref.convert_plane(models["noise1"], x2)
+ref.close()
+cuts = [H2 * b // nb for b in range(nb + 1)]
+ctxs = [w2x.Context(d, engine=w2x.ENGINE_TC) for d in devs]
+slabs = [w2x.Slab(ctxs[b], models["noise1"], W2, cuts[b + 1] - cuts[b], b > 0, b < nb - 1, order=b & 1, n_sub=2 + (b == 1)) for b in range(nb)]
+for b in range(nb):
+    slabs[b].connect_local(slabs[b - 1] if b > 0 else None, slabs[b + 1] if b < nb - 1 else None)
+h_in = torch.from_numpy(x2).pin_memory().numpy()
+h_out = torch.zeros((H2, W2)).pin_memory().numpy()
+for rep in range(3):
+    h_out[:] = 0
+    for b in range(nb):
+        slabs[b].convert_async(h_in[cuts[b]:cuts[b + 1]], h_out[cuts[b]:cuts[b + 1]])
+    for sl in slabs:
+        sl.synchronize()
+    assert np.array_equal(h_out, whole2), (rep, float(np.abs(h_out - whole2).max()))
+for sl in slabs:
+    sl.close()
+for c in ctxs:
+    c.close()
+print(f"slabs (sub-band copy pipeline, alternating order) on devices {devs}: bit-identical to one GPU", flush=True)
+
 # ---- w2x_multi_*: the one-process driver ----
-x = oracle.seeded_plane(260, 300, 5, "uniform")
+x = oracle.seeded_plane(260, 1700, 5, "uniform")             # tall enough for sub-bands inside every slab
 single = w2x.Context(0)
 want = single.convert_plane(models["noise1"], x)
 tiles = np.stack([oracle.seeded_plane(64, 48, 200 + t, "uniform") for t in range(7)])

@@ -37,7 +37,8 @@ ABI_SYMBOLS = (
     "w2x_band_connect_local", "w2x_band_exchange", "w2x_band_run", "w2x_convert_tiles", "w2x_convert_tiles_async",
     "w2x_convert_tiles_device", "w2x_multi_create", "w2x_multi_destroy", "w2x_multi_device_count", "w2x_multi_ctx",
     "w2x_multi_set_precision", "w2x_multi_set_log", "w2x_multi_convert_plane", "w2x_multi_convert_tiles",
-    "w2x_host_alloc", "w2x_host_free", "w2x_ctx_forget_model",
+    "w2x_host_alloc", "w2x_host_free", "w2x_ctx_forget_model", "w2x_slab_create", "w2x_slab_destroy", "w2x_slab_export",
+    "w2x_slab_connect", "w2x_slab_connect_local", "w2x_slab_convert", "w2x_slab_convert_async", "w2x_slab_synchronize",
 )
 BAND_BLOB_BYTES = 320
 
@@ -114,6 +115,15 @@ def lib():
     L.w2x_band_halo.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(cs)]
     L.w2x_band_finish.argtypes = [vp, vp, cs]
     L.w2x_ctx_forget_model.argtypes = [vp, vp]
+    L.w2x_slab_create.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, C.POINTER(vp)]
+    L.w2x_slab_destroy.argtypes = [vp]
+    L.w2x_slab_destroy.restype = None
+    L.w2x_slab_export.argtypes = [vp, vp]
+    L.w2x_slab_connect.argtypes = [vp, vp, vp]
+    L.w2x_slab_connect_local.argtypes = [vp, vp, vp]
+    L.w2x_slab_convert.argtypes = [vp, vp, cs, vp, cs]
+    L.w2x_slab_convert_async.argtypes = [vp, vp, cs, vp, cs]
+    L.w2x_slab_synchronize.argtypes = [vp]
     L.w2x_host_alloc.argtypes = [cs]
     L.w2x_host_alloc.restype = vp
     L.w2x_host_free.argtypes = [vp]
@@ -432,6 +442,42 @@ class Band:
         su, ru, sd, rd = ((C.c_void_p * 4)() for _ in range(4))
         _check(lib().w2x_band_halo(self._h, k, C.byref(n), su, ru, sd, rd, C.byref(nb)))
         return [(su[i], ru[i], sd[i], rd[i], nb.value) for i in range(n.value)]
+
+
+class Slab:
+    """w2x_slab_*: one rank's rows of a multi-GPU plane with HOST buffers; upload / layers / download pipelined over sub-bands."""
+
+    def __init__(self, ctx: Context, model: Model, width, rows, has_up, has_down, order=0, n_sub=0):
+        h = C.c_void_p()
+        _check(lib().w2x_slab_create(ctx._h, model._h, width, rows, int(has_up), int(has_down), int(order), int(n_sub), C.byref(h)))
+        self._h, self._ctx, self._model = h, ctx, model
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.w2x_slab_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(2 * BAND_BLOB_BYTES)
+        _check(lib().w2x_slab_export(self._h, buf))
+        return buf.raw
+
+    def connect(self, up_blob, down_blob): _check(lib().w2x_slab_connect(self._h, up_blob, down_blob))
+
+    def connect_local(self, up, down):
+        _check(lib().w2x_slab_connect_local(self._h, up._h if up is not None else None, down._h if down is not None else None))
+
+    def convert(self, rows_in, rows_out):
+        """numpy [rows][width] fp32 (pinned for full overlap) -> rows_out"""
+        _check(lib().w2x_slab_convert(self._h, C.c_void_p(rows_in.ctypes.data), rows_in.strides[0], C.c_void_p(rows_out.ctypes.data), rows_out.strides[0]))
+        return rows_out
+
+    def convert_async(self, rows_in, rows_out):
+        _check(lib().w2x_slab_convert_async(self._h, C.c_void_p(rows_in.ctypes.data), rows_in.strides[0], C.c_void_p(rows_out.ctypes.data), rows_out.strides[0]))
+
+    def synchronize(self): _check(lib().w2x_slab_synchronize(self._h))
 
 
 # ---- one process, N GPUs ------------------------------------------------------------------------

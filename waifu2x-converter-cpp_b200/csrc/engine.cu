@@ -169,7 +169,10 @@ bool layer_in_rec(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, in
     if (li < 1 || li > n - 2 || !ctx->strip) return false;
     const Layer &L = m->layers[(size_t)li];
     const bool fused = ctx->fuse_last && n >= 3 && !dm->last_w_t.empty() && li == n - 2;
-    return !fused && tc::strip_supported(L.n_in, L.n_out) && dm->strip[(size_t)li] != nullptr;
+    if (fused || !tc::strip_supported(L.n_in, L.n_out) || dm->strip[(size_t)li] == nullptr) return false;
+    // its producer must be able to EMIT a RECORD frame: the first layer or another strip layer (the 16x16-tile kernels
+    // write planar frames only); otherwise this layer stays on the tile kernel
+    return li == 1 || layer_in_rec(ctx, m, dm, li - 1);
 }
 
 // One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).

@@ -101,8 +101,11 @@ int w2x_band_create(w2x_ctx *ctx, const w2x_model *model, int width, int band_ro
     b->n = (int)model->layers.size();
     b->width = width;
     b->rows = band_rows;
-    b->up = has_up != 0;
-    b->down = has_down != 0;
+    if (has_up < 0 || has_up > 2 || has_down < 0 || has_down > 2) return fail(W2X_ERR_ARG, "w2x_band_create: edge kind must be 0 (image border), 1 (neighbour GPU) or 2 (overlap rows)");
+    b->up = has_up == W2X_EDGE_NEIGHBOUR;
+    b->down = has_down == W2X_EDGE_NEIGHBOUR;
+    b->ov_up = has_up == W2X_EDGE_OVERLAP;
+    b->ov_down = has_down == W2X_EDGE_OVERLAP;
     b->pt = b->up ? 1 : b->n;
     b->pb = b->down ? 1 : b->n;
     b->pw = width + 2 * b->n;
@@ -156,6 +159,7 @@ int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
     if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load: bad input");
     w2x_ctx *ctx = band->ctx;
     DeviceGuard g(ctx->device);
+    if (band->ov_up || band->ov_down) return fail(W2X_ERR_ARG, "w2x_band_load: overlap edges take their rows through w2x_band_load_rows");
     const long stride = (long)(in_stride_bytes / 4);
     const float *band0 = d_in + (band->up ? stride : 0);
     CU_CHECK(launch_pad_replicate_xy(band0, band->width, band->rows, stride, band->n, band->pt, band->pb, band->up ? 1 : 0,
@@ -166,14 +170,16 @@ int w2x_band_load(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
     return W2X_OK;
 }
 
-// d_in: the band's OWN rows only; the halo rows of the input frame are left to the neighbours (w2x_band_exchange(band, -1)).
+// d_in: the band's OWN rows; the halo rows of the input frame are left to the neighbours (w2x_band_exchange(band, -1)).  On an
+// overlap edge (W2X_EDGE_OVERLAP) the n input rows beyond the band must be readable at d_in - n rows / d_in + rows.
 int w2x_band_load_rows(w2x_band *band, const float *d_in, size_t in_stride_bytes) {
     if (band_check(band)) return W2X_ERR_ARG;
     if (!d_in || in_stride_bytes % 4 || in_stride_bytes < (size_t)band->width * 4) return fail(W2X_ERR_ARG, "w2x_band_load_rows: bad input");
     w2x_ctx *ctx = band->ctx;
     DeviceGuard g(ctx->device);
-    CU_CHECK(launch_pad_replicate_xy(d_in, band->width, band->rows, (long)(in_stride_bytes / 4), band->n, band->pt, band->pb, 0, 0,
-                                     band->pad, ctx->stream, band->up ? 1 : 0, band->down ? 1 : 0));
+    CU_CHECK(launch_pad_replicate_xy(d_in, band->width, band->rows, (long)(in_stride_bytes / 4), band->n, band->pt, band->pb,
+                                     band->ov_up ? band->n : 0, band->ov_down ? band->n : 0, band->pad, ctx->stream, band->up ? 1 : 0,
+                                     band->down ? 1 : 0));
     ctx->launches++;
     band->last_step = -1;
     band->cur = 0;
@@ -383,24 +389,179 @@ int w2x_band_run(w2x_band *band, const float *d_in, size_t in_stride_bytes, floa
 }  // extern "C"
 
 // =========================================================================================================================
+// One GPU's slab of a multi-GPU plane with HOST buffers: upload, layers and download pipelined over sub-bands
+// =========================================================================================================================
+// A slab is what one rank (or one GPU of w2x_multi_*) owns of the plane.  It is cut into K sub-bands that run one after the
+// other: the upload of sub-band t+1 and the download of t-1 overlap the layers of t (copy engines + SMs).  Seams INSIDE the
+// slab are overlap edges (n real input rows, recomputed -- the data is local anyway); the slab's outer edges keep the
+// per-layer halo exchange with the neighbour GPU.  Two neighbouring slabs must work on their common boundary at the same
+// time, so even slabs walk top -> bottom and odd ones bottom -> top (`order`).
+struct w2x_slab {
+    w2x_ctx *ctx = nullptr;
+    const w2x_model *model = nullptr;
+    int width = 0, rows = 0, order = 0;
+    bool up = false, down = false;
+    std::vector<w2x_band *> sub;
+    std::vector<int> r0;                         // sub-band s owns slab rows [r0[s], r0[s+1])
+    float *d_in = nullptr, *d_out = nullptr;     // [rows][width]
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_drained = nullptr;            // the previous pass's downloads have left d_out
+};
+
+extern "C" {
+
+void w2x_slab_destroy(w2x_slab *s) {
+    if (!s) return;
+    for (auto b : s->sub) w2x_band_destroy(b);
+    if (s->ctx) {
+        DeviceGuard g(s->ctx->device);
+        cudaFree(s->d_in);
+        cudaFree(s->d_out);
+        for (auto e : s->ev_in) cudaEventDestroy(e);
+        for (auto e : s->ev_done) cudaEventDestroy(e);
+        if (s->ev_drained) cudaEventDestroy(s->ev_drained);
+        cudaGetLastError();
+    }
+    delete s;
+}
+
+int w2x_slab_create(w2x_ctx *ctx, const w2x_model *model, int width, int rows, int has_up, int has_down, int order, int n_sub, w2x_slab **out) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!model || !out || width < 1 || rows < 1) return fail(W2X_ERR_ARG, "w2x_slab_create: bad argument");
+    *out = nullptr;
+    const int n = (int)model->layers.size();
+    if (n_sub <= 0) n_sub = std::min(4, rows / 512);            // like w2x_convert_plane's copy pipeline
+    n_sub = std::max(1, std::min(n_sub, std::min(8, rows / (4 * n))));
+    auto s = std::unique_ptr<w2x_slab, void (*)(w2x_slab *)>(new w2x_slab(), w2x_slab_destroy);
+    s->ctx = ctx;
+    s->model = model;
+    s->width = width;
+    s->rows = rows;
+    s->order = order ? 1 : 0;
+    s->up = has_up != 0;
+    s->down = has_down != 0;
+    for (int i = 0; i <= n_sub; i++) s->r0.push_back((int)((long)rows * i / n_sub));
+    DeviceGuard g(ctx->device);
+    for (int i = 0; i < n_sub; i++) {
+        w2x_band *b = nullptr;
+        const int ue = i == 0 ? (s->up ? W2X_EDGE_NEIGHBOUR : W2X_EDGE_BORDER) : W2X_EDGE_OVERLAP;
+        const int de = i == n_sub - 1 ? (s->down ? W2X_EDGE_NEIGHBOUR : W2X_EDGE_BORDER) : W2X_EDGE_OVERLAP;
+        int rc = w2x_band_create(ctx, model, width, s->r0[(size_t)i + 1] - s->r0[(size_t)i], ue, de, &b);
+        if (rc) return rc;
+        s->sub.push_back(b);
+    }
+    CU_CHECK(cudaMalloc(&s->d_in, (size_t)rows * width * 4));
+    CU_CHECK(cudaMalloc(&s->d_out, (size_t)rows * width * 4));
+    for (int i = 0; i < n_sub; i++) {
+        cudaEvent_t e;
+        CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->ev_in.push_back(e);
+        CU_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->ev_done.push_back(e);
+    }
+    CU_CHECK(cudaEventCreateWithFlags(&s->ev_drained, cudaEventDisableTiming));
+    *out = s.release();
+    return W2X_OK;
+}
+
+// blob = [top sub-band's session | bottom sub-band's session]
+int w2x_slab_export(w2x_slab *s, void *blob) {
+    if (!s || !blob) return fail(W2X_ERR_ARG, "w2x_slab_export: NULL argument");
+    int rc = w2x_band_export(s->sub.front(), blob);
+    if (rc) return rc;
+    return w2x_band_export(s->sub.back(), static_cast<char *>(blob) + W2X_BAND_BLOB_BYTES);
+}
+
+int w2x_slab_connect(w2x_slab *s, const void *up_blob, const void *down_blob) {
+    if (!s) return fail(W2X_ERR_ARG, "w2x_slab_connect: NULL slab");
+    if ((s->up && !up_blob) || (s->down && !down_blob)) return fail(W2X_ERR_ARG, "w2x_slab_connect: a neighbour's blob is missing");
+    const void *ub = s->up ? static_cast<const char *>(up_blob) + W2X_BAND_BLOB_BYTES : nullptr;   // the up slab's BOTTOM session
+    const void *db = s->down ? down_blob : nullptr;                                                  // the down slab's TOP session
+    if (s->sub.size() == 1) return w2x_band_connect(s->sub[0], ub, db);
+    int rc = w2x_band_connect(s->sub.front(), ub, nullptr);
+    if (rc) return rc;
+    return w2x_band_connect(s->sub.back(), nullptr, db);
+}
+
+int w2x_slab_connect_local(w2x_slab *s, w2x_slab *up, w2x_slab *down) {
+    if (!s) return fail(W2X_ERR_ARG, "w2x_slab_connect_local: NULL slab");
+    if ((s->up && !up) || (s->down && !down)) return fail(W2X_ERR_ARG, "w2x_slab_connect_local: a neighbour slab is missing");
+    w2x_band *ub = s->up ? up->sub.back() : nullptr, *db = s->down ? down->sub.front() : nullptr;
+    if (s->sub.size() == 1) return w2x_band_connect_local(s->sub[0], ub, db);
+    int rc = w2x_band_connect_local(s->sub.front(), ub, nullptr);
+    if (rc) return rc;
+    return w2x_band_connect_local(s->sub.back(), nullptr, db);
+}
+
+// Queues one whole pass: host rows in -> host rows out (pinned host memory keeps every copy asynchronous).
+int w2x_slab_convert_async(w2x_slab *s, const float *in, size_t in_stride_bytes, float *out, size_t out_stride_bytes) {
+    if (!s || !in || !out) return fail(W2X_ERR_ARG, "w2x_slab_convert: NULL argument");
+    if (in_stride_bytes < (size_t)s->width * 4 || out_stride_bytes < (size_t)s->width * 4) return fail(W2X_ERR_ARG, "w2x_slab_convert: row stride smaller than a row");
+    w2x_ctx *ctx = s->ctx;
+    DeviceGuard g(ctx->device);
+    const int K = (int)s->sub.size();
+    const size_t rowb = (size_t)s->width * 4;
+    auto at = [&](int t) { return s->order ? K - 1 - t : t; };      // t-th sub-band in processing order
+    CU_CHECK(cudaStreamWaitEvent(ctx->copy_in, s->ev_done[(size_t)at(K - 1)], 0));   // the previous pass has finished reading d_in
+    CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_drained, 0));                    // ... and its downloads have left d_out
+    for (int t = 0; t < K; t++) {
+        const int i = at(t), y = s->r0[(size_t)i], rows = s->r0[(size_t)i + 1] - y;
+        CU_CHECK(cudaMemcpy2DAsync(s->d_in + (size_t)y * s->width, rowb, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes, in_stride_bytes, rowb,
+                                   (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU_CHECK(cudaEventRecord(s->ev_in[(size_t)i], ctx->copy_in));
+    }
+    for (int t = 0; t < K; t++) {
+        const int i = at(t), y = s->r0[(size_t)i], rows = s->r0[(size_t)i + 1] - y;
+        for (int j = std::max(0, i - 1); j <= std::min(K - 1, i + 1); j++) CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_in[(size_t)j], 0));   // own rows + the overlap rows
+        int rc = w2x_band_run(s->sub[(size_t)i], s->d_in + (size_t)y * s->width, rowb, s->d_out + (size_t)y * s->width, rowb);
+        if (rc) {
+            cudaStreamSynchronize(ctx->copy_in);
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copy_out);
+            return rc;
+        }
+        CU_CHECK(cudaEventRecord(s->ev_done[(size_t)i], ctx->stream));
+        CU_CHECK(cudaStreamWaitEvent(ctx->copy_out, s->ev_done[(size_t)i], 0));
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, s->d_out + (size_t)y * s->width, rowb, rowb,
+                                   (size_t)rows, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CU_CHECK(cudaEventRecord(s->ev_drained, ctx->copy_out));
+    return W2X_OK;
+}
+
+int w2x_slab_synchronize(w2x_slab *s) {
+    if (!s) return fail(W2X_ERR_ARG, "NULL slab");
+    DeviceGuard g(s->ctx->device);
+    CU_CHECK(cudaStreamSynchronize(s->ctx->copy_out));
+    CU_CHECK(cudaStreamSynchronize(s->ctx->stream));
+    return W2X_OK;
+}
+
+int w2x_slab_convert(w2x_slab *s, const float *in, size_t in_stride_bytes, float *out, size_t out_stride_bytes) {
+    int rc = w2x_slab_convert_async(s, in, in_stride_bytes, out, out_stride_bytes);
+    int rc2 = s ? w2x_slab_synchronize(s) : W2X_OK;
+    return rc ? rc : rc2;
+}
+
+}  // extern "C"
+
+// =========================================================================================================================
 // One process, N GPUs
 // =========================================================================================================================
 struct w2x_multi {
     std::vector<w2x_ctx *> ctx;
-    // the band sessions of the last (model, width, height): planes of one job usually share a shape
+    // the slabs of the last (model, width, height): planes of one job usually share a shape
     uint64_t plan_uid = 0;
     int plan_w = 0, plan_h = 0, plan_precision = -1;
-    std::vector<w2x_band *> bands;
-    std::vector<int> r0;                       // first row of every band (+ the plane height at the end)
-    std::vector<float *> d_in, d_out;          // per-GPU staging of the band's rows
-    std::vector<size_t> d_bytes;
+    std::vector<w2x_slab *> slabs;
+    std::vector<int> r0;                       // first row of every slab (+ the plane height at the end)
 };
 
 namespace {
 
 void multi_drop_plan(w2x_multi *m) {
-    for (auto b : m->bands) w2x_band_destroy(b);
-    m->bands.clear();
+    for (auto b : m->slabs) w2x_slab_destroy(b);
+    m->slabs.clear();
     m->plan_uid = 0;
 }
 
@@ -436,9 +597,6 @@ int w2x_multi_create(const int *devices, int n_devices, w2x_multi **out) {
         }
         m->ctx.push_back(c);
     }
-    m->d_in.assign((size_t)n_devices, nullptr);
-    m->d_out.assign((size_t)n_devices, nullptr);
-    m->d_bytes.assign((size_t)n_devices, 0);
     *out = m.release();
     return W2X_OK;
 }
@@ -446,11 +604,6 @@ int w2x_multi_create(const int *devices, int n_devices, w2x_multi **out) {
 void w2x_multi_destroy(w2x_multi *m) {
     if (!m) return;
     multi_drop_plan(m);
-    for (size_t i = 0; i < m->ctx.size(); i++) {
-        DeviceGuard g(m->ctx[i]->device);
-        cudaFree(m->d_in[i]);
-        cudaFree(m->d_out[i]);
-    }
     for (auto c : m->ctx) w2x_ctx_destroy(c);
     delete m;
 }
@@ -469,21 +622,21 @@ int w2x_multi_convert_plane(w2x_multi *m, const w2x_model *model, const float *i
     nd = std::min(nd, height / (4 * n_layers));
     if (nd < 2 || !model->tc_eligible || m->ctx[0]->engine == W2X_ENGINE_FP32)
         return w2x_convert_plane(m->ctx[0], model, in, width, height, in_stride_bytes, out, out_stride_bytes, block_splitting);
-    // ---- plan: one band session per GPU, neighbours wired through peer memory ----
-    if (m->plan_uid != model->uid || m->plan_w != width || m->plan_h != height || (int)m->bands.size() != nd ||
+    // ---- plan: one slab per GPU (sub-bands for the copy pipeline), neighbours wired through peer memory ----
+    if (m->plan_uid != model->uid || m->plan_w != width || m->plan_h != height || (int)m->slabs.size() != nd ||
         m->plan_precision != m->ctx[0]->precision) {
         multi_drop_plan(m);
         m->r0.assign((size_t)nd + 1, 0);
         for (int i = 0; i <= nd; i++) m->r0[(size_t)i] = (int)((long)height * i / nd);
         for (int i = 0; i < nd; i++) {
             m->ctx[(size_t)i]->precision = m->ctx[0]->precision;
-            w2x_band *b = nullptr;
-            int rc = w2x_band_create(m->ctx[(size_t)i], model, width, m->r0[(size_t)i + 1] - m->r0[(size_t)i], i > 0, i + 1 < nd, &b);
+            w2x_slab *sl = nullptr;
+            int rc = w2x_slab_create(m->ctx[(size_t)i], model, width, m->r0[(size_t)i + 1] - m->r0[(size_t)i], i > 0, i + 1 < nd, i & 1, 0, &sl);
             if (rc) { multi_drop_plan(m); return rc; }
-            m->bands.push_back(b);
+            m->slabs.push_back(sl);
         }
         for (int i = 0; i < nd; i++) {
-            int rc = w2x_band_connect_local(m->bands[(size_t)i], i > 0 ? m->bands[(size_t)i - 1] : nullptr, i + 1 < nd ? m->bands[(size_t)i + 1] : nullptr);
+            int rc = w2x_slab_connect_local(m->slabs[(size_t)i], i > 0 ? m->slabs[(size_t)i - 1] : nullptr, i + 1 < nd ? m->slabs[(size_t)i + 1] : nullptr);
             if (rc) { multi_drop_plan(m); return rc; }
         }
         m->plan_uid = model->uid;
@@ -493,44 +646,14 @@ int w2x_multi_convert_plane(w2x_multi *m, const w2x_model *model, const float *i
     }
     emit_reference_progress(m->ctx[0], width, height, n_layers, block_splitting && w2x_requires_splitting(width, height));
     HostPin pin_in(in, in_stride_bytes * (size_t)(height - 1) + (size_t)width * 4), pin_out(out, out_stride_bytes * (size_t)(height - 1) + (size_t)width * 4);
-    // ---- queue everything: upload, the whole layer loop with its exchanges, download -- per GPU, one host thread ----
-    for (int i = 0; i < nd; i++) {
-        w2x_ctx *c = m->ctx[(size_t)i];
-        DeviceGuard g(c->device);
-        const int y = m->r0[(size_t)i], rows = m->r0[(size_t)i + 1] - y;
-        const size_t need = (size_t)rows * width * 4;
-        if (m->d_bytes[(size_t)i] < need) {
-            cudaFree(m->d_in[(size_t)i]);
-            cudaFree(m->d_out[(size_t)i]);
-            m->d_in[(size_t)i] = m->d_out[(size_t)i] = nullptr;
-            m->d_bytes[(size_t)i] = 0;
-            CU_CHECK(cudaMalloc(&m->d_in[(size_t)i], need));
-            CU_CHECK(cudaMalloc(&m->d_out[(size_t)i], need));
-            m->d_bytes[(size_t)i] = need;
-        }
-        CU_CHECK(cudaMemcpy2DAsync(m->d_in[(size_t)i], (size_t)width * 4, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes, in_stride_bytes,
-                                   (size_t)width * 4, (size_t)rows, cudaMemcpyHostToDevice, c->stream));
-    }
-    for (int i = 0; i < nd; i++) {
-        int rc = w2x_band_run(m->bands[(size_t)i], m->d_in[(size_t)i], (size_t)width * 4, m->d_out[(size_t)i], (size_t)width * 4);
-        if (rc) {
-            for (auto c : m->ctx) { DeviceGuard g(c->device); cudaStreamSynchronize(c->stream); }
-            return rc;
-        }
-    }
-    for (int i = 0; i < nd; i++) {
-        w2x_ctx *c = m->ctx[(size_t)i];
-        DeviceGuard g(c->device);
-        const int y = m->r0[(size_t)i], rows = m->r0[(size_t)i + 1] - y;
-        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, m->d_out[(size_t)i], (size_t)width * 4,
-                                   (size_t)width * 4, (size_t)rows, cudaMemcpyDeviceToHost, c->stream));
-    }
+    // ---- queue everything (uploads, the layer loops with their exchanges, downloads) for every GPU from this one thread ----
     int rc = W2X_OK;
+    for (int i = 0; i < nd && rc == W2X_OK; i++)
+        rc = w2x_slab_convert_async(m->slabs[(size_t)i], reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + (size_t)m->r0[(size_t)i] * in_stride_bytes),
+                                    in_stride_bytes, reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (size_t)m->r0[(size_t)i] * out_stride_bytes), out_stride_bytes);
     for (int i = 0; i < nd; i++) {
-        w2x_ctx *c = m->ctx[(size_t)i];
-        DeviceGuard g(c->device);
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess && rc == W2X_OK) rc = fail(W2X_ERR_CUDA, "CUDA error %s on device %d (%s)", cudaGetErrorName(e), c->device, cudaGetErrorString(e));
+        int r2 = w2x_slab_synchronize(m->slabs[(size_t)i]);
+        if (rc == W2X_OK) rc = r2;
     }
     return rc;
 }

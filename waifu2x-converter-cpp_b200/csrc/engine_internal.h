@@ -79,8 +79,9 @@ struct w2x_band {
     const w2x_model *model = nullptr;
     w2x::eng::DevModel *dm = nullptr;
     int width = 0, rows = 0, n = 0;
-    bool up = false, down = false;
-    int pt = 0, pb = 0;            // frame rows above / below the band: 1 (neighbour halo) or n (replicated image border)
+    bool up = false, down = false; // a neighbour GPU owns the rows above / below: one halo row, exchanged after every layer
+    bool ov_up = false, ov_down = false;   // the n rows above / below are REAL input rows supplied with the band (recomputed overlap, no exchange)
+    int pt = 0, pb = 0;            // frame rows above / below the band: 1 (neighbour halo) or n (image border: replicated; overlap: real rows)
     int pw = 0, hf = 0;            // frame width / height
     float *pad = nullptr;          // padded fp32 input frame
     __half *act[2] = {nullptr, nullptr};
