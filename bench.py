@@ -415,6 +415,15 @@ def run_ours(args):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     _, ms_e2e_wall, _, _, _ = timed(step_e2e, args.steps)
+    step_device()
+    torch.cuda.synchronize()
+    e2e_same = bool(torch.equal(host_out, d_out.cpu()))          # the host-buffer path returns the device-resident path's bits
+    if world > 1:
+        fl = [None] * world
+        dist.all_gather_object(fl, e2e_same)
+        e2e_same = all(fl)
+    if not e2e_same:
+        raise SystemExit("e2e result differs from the device-resident result")
 
     # ---- the other multi-GPU configurations of BASELINE.json, measured in the same run (driver-visible) ----
     configs = {}
@@ -526,7 +535,7 @@ def run_ours(args):
                            "l2": "no explicit flush: each step streams ~17 GB of activations per GPU, far beyond the 126 MB L2"},
                 "e2e": {"value": mpix_e2e, "unit": "Mpix/s", "h2d_bytes_per_step": W * H * 4 * world, "d2h_bytes_per_step": W * H * 4 * world,
                         "timing": "host wall clock around K calls of the host-buffer C-ABI entry (sync inside the call), max over ranks"},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "halo_check": halo_check, "configs": configs, **host_api}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "halo_check": halo_check, "e2e_check": e2e_same, "configs": configs, **host_api}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
