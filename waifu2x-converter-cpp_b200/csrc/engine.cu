@@ -810,6 +810,43 @@ int convert_tiles_dev(w2x_ctx *ctx, const w2x_model *m, const float *d_in, float
 }
 }  // namespace
 
+namespace w2x {
+namespace eng {
+// phase 1: uploads + the batched pass (results stay in the context's staging buffer); phase 2: downloads.  Split so that a
+// multi-GPU driver can queue phase 1 everywhere before a download into pageable memory blocks its thread.
+int tiles_enqueue_compute(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, int n_tiles, int width, int height, size_t in_stride_bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!in_tiles || n_tiles < 1 || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad argument");
+    if (in_stride_bytes < (size_t)width * 4) return fail(W2X_ERR_ARG, "w2x_convert_tiles: row stride smaller than a row");
+    DeviceGuard g(ctx->device);
+    const size_t tile_bytes = (size_t)width * height * sizeof(float);
+    for (int i = 0; i < 2; i++) {
+        int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], tile_bytes * (size_t)n_tiles);
+        if (rc) return rc;
+    }
+    for (int t = 0; t < n_tiles; t++) {
+        if (!in_tiles[t]) return fail(W2X_ERR_ARG, "w2x_convert_tiles: NULL tile %d", t);
+        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(ctx->io_buf[0]) + tile_bytes * (size_t)t, (size_t)width * 4, in_tiles[t], in_stride_bytes,
+                                   (size_t)width * 4, (size_t)height, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return convert_tiles_dev(ctx, model, ctx->io_buf[0], ctx->io_buf[1], n_tiles, width, height);
+}
+
+int tiles_enqueue_download(w2x_ctx *ctx, float *const *out_tiles, int n_tiles, int width, int height, size_t out_stride_bytes) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    if (!out_tiles || out_stride_bytes < (size_t)width * 4) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad output argument");
+    DeviceGuard g(ctx->device);
+    const size_t tile_bytes = (size_t)width * height * sizeof(float);
+    for (int t = 0; t < n_tiles; t++) {
+        if (!out_tiles[t]) return fail(W2X_ERR_ARG, "w2x_convert_tiles: NULL tile %d", t);
+        CU_CHECK(cudaMemcpy2DAsync(out_tiles[t], out_stride_bytes, reinterpret_cast<char *>(ctx->io_buf[1]) + tile_bytes * (size_t)t, (size_t)width * 4,
+                                   (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return W2X_OK;
+}
+}  // namespace eng
+}  // namespace w2x
+
 extern "C" {
 
 int w2x_convert_tiles_device(w2x_ctx *ctx, const w2x_model *model, const float *d_in, float *d_out, int n_tiles, int width, int height) {
@@ -819,26 +856,9 @@ int w2x_convert_tiles_device(w2x_ctx *ctx, const w2x_model *model, const float *
 
 int w2x_convert_tiles_async(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,
                             int width, int height, size_t in_stride_bytes, size_t out_stride_bytes) {
-    if (check_ctx(ctx)) return W2X_ERR_ARG;
-    if (!in_tiles || !out_tiles || n_tiles < 1 || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad argument");
-    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4) return fail(W2X_ERR_ARG, "w2x_convert_tiles: row stride smaller than a row");
-    DeviceGuard g(ctx->device);
-    const size_t tile_bytes = (size_t)width * height * sizeof(float);
-    for (int i = 0; i < 2; i++) {
-        int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], tile_bytes * (size_t)n_tiles);
-        if (rc) return rc;
-    }
-    for (int t = 0; t < n_tiles; t++) {
-        if (!in_tiles[t] || !out_tiles[t]) return fail(W2X_ERR_ARG, "w2x_convert_tiles: NULL tile %d", t);
-        CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(ctx->io_buf[0]) + tile_bytes * (size_t)t, (size_t)width * 4, in_tiles[t], in_stride_bytes,
-                                   (size_t)width * 4, (size_t)height, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    int rc = convert_tiles_dev(ctx, model, ctx->io_buf[0], ctx->io_buf[1], n_tiles, width, height);
+    int rc = tiles_enqueue_compute(ctx, model, in_tiles, n_tiles, width, height, in_stride_bytes);
     if (rc) return rc;
-    for (int t = 0; t < n_tiles; t++)
-        CU_CHECK(cudaMemcpy2DAsync(out_tiles[t], out_stride_bytes, reinterpret_cast<char *>(ctx->io_buf[1]) + tile_bytes * (size_t)t, (size_t)width * 4,
-                                   (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, ctx->stream));
-    return W2X_OK;
+    return tiles_enqueue_download(ctx, out_tiles, n_tiles, width, height, out_stride_bytes);
 }
 
 int w2x_convert_tiles(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,

@@ -493,10 +493,11 @@ int w2x_slab_connect_local(w2x_slab *s, w2x_slab *up, w2x_slab *down) {
     return w2x_band_connect_local(s->sub.back(), nullptr, db);
 }
 
-// Queues one whole pass: host rows in -> host rows out (pinned host memory keeps every copy asynchronous).
-int w2x_slab_convert_async(w2x_slab *s, const float *in, size_t in_stride_bytes, float *out, size_t out_stride_bytes) {
-    if (!s || !in || !out) return fail(W2X_ERR_ARG, "w2x_slab_convert: NULL argument");
-    if (in_stride_bytes < (size_t)s->width * 4 || out_stride_bytes < (size_t)s->width * 4) return fail(W2X_ERR_ARG, "w2x_slab_convert: row stride smaller than a row");
+}  // extern "C"
+
+namespace {
+// Phase 1 of a pass: uploads and the layer loops of every sub-band (nothing here can block the host on another GPU's progress).
+int slab_enqueue_compute(w2x_slab *s, const float *in, size_t in_stride_bytes) {
     w2x_ctx *ctx = s->ctx;
     DeviceGuard g(ctx->device);
     const int K = (int)s->sub.size();
@@ -511,22 +512,47 @@ int w2x_slab_convert_async(w2x_slab *s, const float *in, size_t in_stride_bytes,
         CU_CHECK(cudaEventRecord(s->ev_in[(size_t)i], ctx->copy_in));
     }
     for (int t = 0; t < K; t++) {
-        const int i = at(t), y = s->r0[(size_t)i], rows = s->r0[(size_t)i + 1] - y;
+        const int i = at(t), y = s->r0[(size_t)i];
         for (int j = std::max(0, i - 1); j <= std::min(K - 1, i + 1); j++) CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_in[(size_t)j], 0));   // own rows + the overlap rows
         int rc = w2x_band_run(s->sub[(size_t)i], s->d_in + (size_t)y * s->width, rowb, s->d_out + (size_t)y * s->width, rowb);
         if (rc) {
             cudaStreamSynchronize(ctx->copy_in);
             cudaStreamSynchronize(ctx->stream);
-            cudaStreamSynchronize(ctx->copy_out);
             return rc;
         }
         CU_CHECK(cudaEventRecord(s->ev_done[(size_t)i], ctx->stream));
+    }
+    return W2X_OK;
+}
+
+// Phase 2: every sub-band's rows go home as soon as its layers are done.  (A download into PAGEABLE memory blocks the host
+// until the data is there -- which is why a multi-GPU driver must have queued phase 1 on every GPU first: this GPU's layers
+// wait for its neighbours' halo rows.)
+int slab_enqueue_download(w2x_slab *s, float *out, size_t out_stride_bytes) {
+    w2x_ctx *ctx = s->ctx;
+    DeviceGuard g(ctx->device);
+    const int K = (int)s->sub.size();
+    const size_t rowb = (size_t)s->width * 4;
+    for (int t = 0; t < K; t++) {
+        const int i = s->order ? K - 1 - t : t, y = s->r0[(size_t)i], rows = s->r0[(size_t)i + 1] - y;
         CU_CHECK(cudaStreamWaitEvent(ctx->copy_out, s->ev_done[(size_t)i], 0));
         CU_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(out) + (size_t)y * out_stride_bytes, out_stride_bytes, s->d_out + (size_t)y * s->width, rowb, rowb,
                                    (size_t)rows, cudaMemcpyDeviceToHost, ctx->copy_out));
     }
     CU_CHECK(cudaEventRecord(s->ev_drained, ctx->copy_out));
     return W2X_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// Queues one whole pass: host rows in -> host rows out (pinned host memory keeps every copy asynchronous).
+int w2x_slab_convert_async(w2x_slab *s, const float *in, size_t in_stride_bytes, float *out, size_t out_stride_bytes) {
+    if (!s || !in || !out) return fail(W2X_ERR_ARG, "w2x_slab_convert: NULL argument");
+    if (in_stride_bytes < (size_t)s->width * 4 || out_stride_bytes < (size_t)s->width * 4) return fail(W2X_ERR_ARG, "w2x_slab_convert: row stride smaller than a row");
+    int rc = slab_enqueue_compute(s, in, in_stride_bytes);
+    if (rc) return rc;
+    return slab_enqueue_download(s, out, out_stride_bytes);
 }
 
 int w2x_slab_synchronize(w2x_slab *s) {
@@ -648,9 +674,10 @@ int w2x_multi_convert_plane(w2x_multi *m, const w2x_model *model, const float *i
     HostPin pin_in(in, in_stride_bytes * (size_t)(height - 1) + (size_t)width * 4), pin_out(out, out_stride_bytes * (size_t)(height - 1) + (size_t)width * 4);
     // ---- queue everything (uploads, the layer loops with their exchanges, downloads) for every GPU from this one thread ----
     int rc = W2X_OK;
+    for (int i = 0; i < nd && rc == W2X_OK; i++)      // phase 1 on EVERY GPU before any download can block this thread
+        rc = slab_enqueue_compute(m->slabs[(size_t)i], reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + (size_t)m->r0[(size_t)i] * in_stride_bytes), in_stride_bytes);
     for (int i = 0; i < nd && rc == W2X_OK; i++)
-        rc = w2x_slab_convert_async(m->slabs[(size_t)i], reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + (size_t)m->r0[(size_t)i] * in_stride_bytes),
-                                    in_stride_bytes, reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (size_t)m->r0[(size_t)i] * out_stride_bytes), out_stride_bytes);
+        rc = slab_enqueue_download(m->slabs[(size_t)i], reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (size_t)m->r0[(size_t)i] * out_stride_bytes), out_stride_bytes);
     for (int i = 0; i < nd; i++) {
         int r2 = w2x_slab_synchronize(m->slabs[(size_t)i]);
         if (rc == W2X_OK) rc = r2;
@@ -674,8 +701,9 @@ int w2x_multi_convert_tiles(w2x_multi *m, const w2x_model *model, const float *c
     // queue every GPU's batch without waiting, then wait for all of them
     int rc = W2X_OK;
     for (int i = 0; i < nd && rc == W2X_OK; i++)
-        rc = w2x_convert_tiles_async(m->ctx[(size_t)i], model, tin[(size_t)i].data(), tout[(size_t)i].data(), (int)tin[(size_t)i].size(), width, height,
-                                     in_stride_bytes, out_stride_bytes);
+        rc = tiles_enqueue_compute(m->ctx[(size_t)i], model, tin[(size_t)i].data(), (int)tin[(size_t)i].size(), width, height, in_stride_bytes);
+    for (int i = 0; i < nd && rc == W2X_OK; i++)
+        rc = tiles_enqueue_download(m->ctx[(size_t)i], tout[(size_t)i].data(), (int)tout[(size_t)i].size(), width, height, out_stride_bytes);
     for (int i = 0; i < nd; i++) {
         int r2 = w2x_ctx_synchronize(m->ctx[(size_t)i]);
         if (rc == W2X_OK) rc = r2;

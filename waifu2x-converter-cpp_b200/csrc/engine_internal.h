@@ -141,6 +141,9 @@ int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, cons
 int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, int h, size_t in_stride_bytes, int rows_above,
                    int rows_below, float *d_out, size_t out_stride_bytes, int block_splitting);
 
+int tiles_enqueue_compute(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, int n_tiles, int width, int height, size_t in_stride_bytes);
+int tiles_enqueue_download(w2x_ctx *ctx, float *const *out_tiles, int n_tiles, int width, int height, size_t out_stride_bytes);
+
 struct LayerTimer {   // brackets one layer launch with events when timing is on
     w2x_ctx *ctx;
     TimedSpan span{};
