@@ -210,6 +210,28 @@ def write_model_json(npz_path, json_path):
         json.dump(layers, f)
 
 
+def pin_to_gpu_numa_node(torch, local):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the page-locked host buffers it allocates (first touch) sit
+    behind the same PCIe root as the GPU: with one rank per GPU and no affinity, half of the host<->device traffic of an 8-GPU
+    box crosses the socket interconnect."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        dev = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def host_api_legs(w2x, steps, size):
     """The API a reference maintainer links, timed from C++ / the shell:
       e2e_cpp   w2xc::convertWithModels (host/w2xc.hpp: w2xc::Plane in / out, progress lines on stdout) on the bench plane;
@@ -275,6 +297,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    pin_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W = H = args.size
@@ -364,11 +387,12 @@ def run_ours(args):
             stream.synchronize()
 
     def timed(fn, steps, with_layers=False, sampler=None):
+        if sampler:
+            sampler.start()          # BEFORE the barrier: forking nvidia-smi takes rank 0 tens of milliseconds, and with a per-layer
+                                     # exchange every other rank would spend them waiting for rank 0 inside its timed region
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
         if with_layers:
             ctx.set_timing(True)
             ctx.layer_times(reset=True)
