@@ -320,6 +320,7 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
     if (m->layers.front().n_in != 1 || m->layers.back().n_out != 1)
         return fail(W2X_ERR_ARG, "w2x_convert_plane: model must map 1 plane to 1 plane");
     DeviceGuard g(ctx->device);
+    NvtxRange nvtx("w2x convertWithModels");
     const int engine = pick_engine(ctx, m);
     if (engine < 0) return W2X_ERR_UNSUPPORTED;
     DevModel *dm = nullptr;

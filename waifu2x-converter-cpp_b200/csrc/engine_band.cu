@@ -369,6 +369,7 @@ int w2x_band_exchange(w2x_band *band, int step) {
     a.peer_flag[1] = band->down ? band->peer[1].flags + 0 : nullptr;
     a.my_flag[0] = band->up ? band->flags + 0 : nullptr;
     a.my_flag[1] = band->down ? band->flags + 1 : nullptr;
+    NvtxRange nvtx("w2x halo exchange");
     CU_CHECK(launch_halo_exchange(a, ctx->stream));
     ctx->launches++;
     return W2X_OK;

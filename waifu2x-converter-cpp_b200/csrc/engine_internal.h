@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost a few nanoseconds when no tool is attached
 
 #include <algorithm>
 #include <cstdlib>
@@ -144,11 +145,19 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
 int tiles_enqueue_compute(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, int n_tiles, int width, int height, size_t in_stride_bytes);
 int tiles_enqueue_download(w2x_ctx *ctx, float *const *out_tiles, int n_tiles, int width, int height, size_t out_stride_bytes);
 
-struct LayerTimer {   // brackets one layer launch with events when timing is on
+struct NvtxRange {    // a named range on the calling thread's timeline (nsys / ncu --nvtx), e.g. "w2x L3", "w2x halo exchange"
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+struct LayerTimer {   // brackets one layer launch with an NVTX range, and with events when timing is on
     w2x_ctx *ctx;
     TimedSpan span{};
     bool on;
     LayerTimer(w2x_ctx *c, int layer) : ctx(c), on(c->timing) {
+        char name[24];
+        snprintf(name, sizeof name, "w2x L%d", layer);
+        nvtxRangePushA(name);
         if (on) {
             span.layer = layer;
             span.e0 = take_event(c);
@@ -161,6 +170,7 @@ struct LayerTimer {   // brackets one layer launch with events when timing is on
             cudaEventRecord(span.e1, ctx->stream);
             ctx->spans.push_back(span);
         }
+        nvtxRangePop();
     }
 };
 
