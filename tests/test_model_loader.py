@@ -92,7 +92,7 @@ def _swizzle(off, row_bytes):
 
 
 def test_tc_operand_pack_layout_and_split(w2x, oracle_models):
-    """[chunk][tap][32-ch block][hi|lo][n_out x 32] fp16, K-major rows of 64 B, 16-byte units XOR-swizzled
+    """[32-ch block][tap][hi|lo][n_out x 32] fp16, K-major rows of 64 B, 16-byte units XOR-swizzled
     (SWIZZLE_64B); hi+lo == w*scale to ~22 bits."""
     m = w2x.Model.from_arrays(oracle_models["scale2.0x"].weights, oracle_models["scale2.0x"].biases)
     assert m.debug_tc_pack(0)[0] is None and m.debug_tc_pack(6)[0] is None      # 1->32 and 128->1 are not MMA layers
@@ -100,7 +100,7 @@ def test_tc_operand_pack_layout_and_split(w2x, oracle_models):
         data, nch, kbl, ws = m.debug_tc_pack(li)
         w = oracle_models["scale2.0x"].weights[li]
         co, ci = w.shape[:2]
-        kc_a = 32 if ci <= 64 else 64      # channels per staged activation box (tc::act_kc)
+        kc_a = 32                          # channels per staged activation box (one block of 128-byte records)
         assert nch == ci // kc_a and kbl == kc_a // 32 and ws == 2.0 ** np.floor(np.log2(1024.0 / np.abs(w).max()))
         data = data.view(np.float16).reshape(nch, 9, kbl, 2, co * 32)
         ws_w = (w * np.float32(ws)).astype(np.float32)

@@ -162,27 +162,23 @@ int ensure_tc(w2x_ctx *ctx) {
     return W2X_OK;
 }
 
-// Frame layout between layers (kernels.h): layer li CONSUMES a RECORD frame iff it runs on the row-strip kernel -- a property
-// of the layer's shape and position only, never of the frame size, so every tiling of a plane picks the same kernels.
-bool layer_in_rec(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, int li) {
+// Does layer li run on the row-strip kernel?  A property of the layer's shape and position only, never of the frame size,
+// so every tiling of a plane picks the same kernels.
+bool layer_is_strip(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, int li) {
     const int n = (int)m->layers.size();
     if (li < 1 || li > n - 2 || !ctx->strip) return false;
     const Layer &L = m->layers[(size_t)li];
     const bool fused = ctx->fuse_last && n >= 3 && !dm->last_w_t.empty() && li == n - 2;
-    if (fused || !tc::strip_supported(L.n_in, L.n_out) || dm->strip[(size_t)li] == nullptr) return false;
-    // its producer must be able to EMIT a RECORD frame: the first layer or another strip layer (the 16x16-tile kernels
-    // write planar frames only); otherwise this layer stays on the tile kernel
-    return li == 1 || layer_in_rec(ctx, m, dm, li - 1);
+    return !fused && tc::strip_supported(L.n_in, L.n_out) && dm->strip[(size_t)li] != nullptr;
 }
 
 // One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).
 int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, const __half *in, __half *out, int pw, int ph,
-                    bool fused, bool profile, int out_y0, int out_rows, bool planar_out) {
+                    bool fused, bool profile, int out_y0, int out_rows) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     const Layer &L = m->layers[(size_t)li];
     const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
-    const bool strip = !fused && layer_in_rec(ctx, m, dm, li);
-    const bool out_rec = !fused && !planar_out && layer_in_rec(ctx, m, dm, li + 1);       // the consumer decides the output frame's layout
+    const bool strip = !fused && layer_is_strip(ctx, m, dm, li);
     {
         LayerTimer t(ctx, li);
         CU_CHECK(tc::launch_tc_layer(in, f8 ? (const void *)dm->pack8[(size_t)li] : (const void *)dm->pack[(size_t)li],
@@ -191,7 +187,7 @@ int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, cons
                                      ctx->num_sms, ctx->stream,
                                      profile && ctx->prof_buf ? ctx->prof_buf + (size_t)li * tc::PROF_MAX_CTAS * tc::PROF_WORDS : nullptr,
                                      fused ? dm->last_w_t.data() : nullptr, fused ? reinterpret_cast<float *>(out) : nullptr, ctx->pair,
-                                     out_y0, out_rows, strip ? 1 : 0, out_rec ? 1 : 0));
+                                     out_y0, out_rows));
     }
     note_kernel(ctx, li, f8 ? (fused ? "tcgen05_f16+f8x2+last" : strip ? "tcgen05_f16+f8x2_strip" : "tcgen05_f16+f8x2")
                             : (fused ? "tcgen05_f16x3+last" : strip ? "tcgen05_f16x3_strip" : "tcgen05_f16x3"));
@@ -252,8 +248,7 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         const Layer &L = m->layers[0];
         logf(ctx, "Iteration #%d...", 1);
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, L.w.data(), dm->b_host[0].data(), L.n_out, cur, ctx->stream, f8, 0, -1,
-                                  layer_in_rec(ctx, m, dm, 1) ? 1 : 0));
+        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, L.w.data(), dm->b_host[0].data(), L.n_out, cur, ctx->stream, f8));
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
@@ -672,8 +667,8 @@ int w2x_filter_layer_device(w2x_ctx *ctx, const w2x_model *model, int layer, con
         if (rc) return rc;
         __half *fin = static_cast<__half *>(ctx->buf[0]), *fout = static_cast<__half *>(ctx->buf[1]);
         const int f8 = ctx->precision == W2X_PRECISION_F16_F8X2 ? 1 : 0;
-        CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream, f8, layer_in_rec(ctx, model, dm, layer) ? 1 : 0));
-        rc = launch_layer_tc(ctx, model, dm, layer, fin, fout, pw, ph, false, false, 0, -1, true);   // planar output: nhwc_to_planar reads it
+        CU_CHECK(tc::launch_planar_to_nhwc(d_in, L.n_in, width, height, fin, ctx->stream, f8));
+        rc = launch_layer_tc(ctx, model, dm, layer, fin, fout, pw, ph, false, false);
         if (rc) return rc;
         CU_CHECK(tc::launch_nhwc_to_planar(fout, L.n_out, width, height, d_out, ctx->stream, f8));
         ctx->launches += 2;

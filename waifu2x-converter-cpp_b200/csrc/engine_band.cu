@@ -47,23 +47,9 @@ int row_segments(const w2x_band *b, int step, RowSeg seg[4], size_t *bytes, size
     }
     const size_t px = (size_t)b->pw * (size_t)b->model->layers[(size_t)step].n_out;
     *px_out = px;
-    if (layer_in_rec(b->ctx, b->model, b->dm, step + 1)) {   // RECORD frame: a row is one contiguous range of 4 bytes per element
-        *bytes = 4 * px;
-        seg[0] = {0, 4 * px, 0};
-        return 1;
-    }
-    if (b->ctx->precision == W2X_PRECISION_F16_F8X2) {   // frame [xh fp16][xh8][xl8]: four ranges of pw*C bytes
-        *bytes = px;
-        seg[0] = {0, 2 * px, 0};
-        seg[1] = {0, 2 * px, px};
-        seg[2] = {2, px, 0};
-        seg[3] = {3, px, 0};
-        return 4;
-    }
-    *bytes = 2 * px;                                       // frame [hi fp16][lo fp16]: two ranges of pw*C*2 bytes
-    seg[0] = {0, 2 * px, 0};
-    seg[1] = {2, 2 * px, 0};
-    return 2;
+    *bytes = 4 * px;                  // RECORD frame: a row is one contiguous range of 4 bytes per element
+    seg[0] = {0, 4 * px, 0};
+    return 1;
 }
 
 inline char *seg_at(char *base, int frame_rows, size_t px, const RowSeg &s, int row) {
@@ -200,8 +186,7 @@ int w2x_band_step(w2x_band *band, int step) {
     const int y0 = band->up ? 1 : 0, rows = band->hf - y0 - (band->down ? 1 : 0);
     if (step == 0) {
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8, y0, rows,
-                                  layer_in_rec(ctx, m, dm, 1) ? 1 : 0));
+        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8, y0, rows));
         band->cur = 0;
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;

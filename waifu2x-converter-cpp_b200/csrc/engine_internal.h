@@ -133,11 +133,11 @@ int ensure_tc(w2x_ctx *ctx);
 int check_ctx(w2x_ctx *ctx);
 int pick_engine(w2x_ctx *ctx, const w2x_model *m);
 void emit_reference_progress(w2x_ctx *ctx, int w, int h, int n_layers, bool split);   // the reference's stdout lines of one convertWithModels call
-bool layer_in_rec(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, int li);   // does layer li consume a RECORD frame (= run on the strip kernel)?
+bool layer_is_strip(const w2x_ctx *ctx, const w2x_model *m, const DevModel *dm, int li);   // does layer li run on the row-strip kernel?
 // One tcgen05 layer `li` on frames of pw x ph: in -> out (or, fused with the last layer, -> per-pixel tap partials in `out`).
 // Only frame rows [out_y0, out_y0 + out_rows) are stored (out_rows < 0: the whole frame).
 int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, const __half *in, __half *out, int pw, int ph,
-                    bool fused, bool profile, int out_y0 = 0, int out_rows = -1, bool planar_out = false);
+                    bool fused, bool profile, int out_y0 = 0, int out_rows = -1);
 // convertWithModels on device buffers (rows_above / rows_below: real neighbour rows available around the band)
 int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, int h, size_t in_stride_bytes, int rows_above,
                    int rows_below, float *d_out, size_t out_stride_bytes, int block_splitting);

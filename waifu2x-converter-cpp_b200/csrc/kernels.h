@@ -41,8 +41,8 @@ constexpr int REGION = 16;          // a tile-set covers REGION x REGION output 
 constexpr int HALO = REGION + 2;    // staged input footprint per side
 constexpr float ACT_SCALE = 16.0f;  // activations are stored as fp16 hi/lo of (value * ACT_SCALE)
 
-// Activation tensor between layers: [2 (hi,lo)][Hp][Wp][C] fp16.
-inline size_t act_bytes(int C, int Wp, int Hp) { return (size_t)2 * Hp * Wp * C * 2; }
+// Activation frame between layers: 4 bytes per element (RECORD frame, see launch_tc_layer).
+inline size_t act_bytes(int C, int Wp, int Hp) { return (size_t)Hp * Wp * C * 4; }
 
 bool layer_supported(int cin, int cout);
 size_t layer_smem_bytes(int cin, int cout);
@@ -53,8 +53,7 @@ cudaError_t init_kernels();
 // same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
 // `wgt` ([C][9]) and `bias` ((float)bias) are HOST pointers: they travel as kernel parameters.
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
-                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0, int out_y0 = 0, int out_rows = -1,
-                         int out_rec = 0);
+                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0, int out_y0 = 0, int out_rows = -1);
 // tcgen05 layer: in/out NHWC frames (pw x ph); the tensor maps are built inside.
 // `bias` is a HOST pointer to the layer's (float)bias values (they travel as kernel parameters).
 // f8 = 0: "f16x3" frames [hi][lo], wpack = TcPack::bytes, wstrip = TcPack::strip;
@@ -64,11 +63,10 @@ cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph,
 cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out,
                             int cin, int cout, int pw, int ph, float out_scale, int f8, int num_sms,
                             cudaStream_t s, unsigned long long *prof = nullptr, const float *last_w = nullptr,
-                            float *partial = nullptr, int pair = 0, int out_y0 = 0, int out_rows = -1, int in_rec = 0,
-                            int out_rec = 0);
-// Frame layouts.  PLANAR: [xh fp16 | xh8 | xl8] (or [hi | lo]) planes of [Hp][Wp][C].  RECORD (in_rec / out_rec = 1): the same
-// bytes as one 128-byte record per pixel per 32-channel block, [Hp][Wp][C/32][128 B] -- what the row-strip kernel consumes
-// (in_rec = 1 selects it) and what its producers (first layer, strip layers, planar_to_nhwc) can emit (out_rec = 1).
+                            float *partial = nullptr, int pair = 0, int out_y0 = 0, int out_rows = -1);
+// Frames: every activation between layers is a RECORD frame [Hp][Wp][C/32][128 B] -- one 128-byte record per pixel per
+// 32-channel block = {xh fp16 x32 | xh8 e4m3 x32 | xl8 e4m3 x32} (f8) or {hi fp16 x32 | lo fp16 x32} (f16x3): 4 bytes per
+// element, one TMA box row per record (SWIZZLE_128B).
 // out_y0 / out_rows (both launchers): only frame rows [out_y0, out_y0 + out_rows) are stored (-1 = the whole frame); a
 // row-band session keeps its halo rows out of the window because its neighbours write them.
 bool strip_supported(int cin, int cout);
@@ -88,7 +86,7 @@ constexpr int PROF_MAX_CTAS = 256;
 cudaError_t launch_last(const __half *in, int cin, int pw, int ph, const float *wgt /*[C][9]*/, float bias,
                         int crop, float *dst, long dst_stride_floats, cudaStream_t s, int f8 = 0);
 // planar fp32 [C][h][w] -> NHWC hi/lo frame (h+2) x (w+2), replicate ring of 1 (for w2x_filter_layer)
-cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8 = 0, int rec = 0);
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8 = 0);
 // NHWC hi/lo frame (h+2) x (w+2) -> planar fp32 [C][h][w] (interior)
 cudaError_t launch_nhwc_to_planar(const __half *in, int C, int w, int h, float *out, cudaStream_t s, int f8 = 0);
 

@@ -107,13 +107,9 @@ cudaError_t init_kernels() {
     W2X_TC_SHAPES(X)
 #undef X
 #define X(ci, co)                                                                                                                          \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,                    \
                                   StripCfg<ci, co, false>::SMEM_BYTES)) != cudaSuccess) return e;                                           \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                  StripCfg<ci, co, false>::SMEM_BYTES)) != cudaSuccess) return e;                                           \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                  StripCfg<ci, co, true>::SMEM_BYTES)) != cudaSuccess) return e;                                            \
-    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+    if ((e = cudaFuncSetAttribute(tc_conv3x3_strip_kernel<ci, co, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
                                   StripCfg<ci, co, true>::SMEM_BYTES)) != cudaSuccess) return e;
     X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 #undef X
@@ -121,40 +117,37 @@ cudaError_t init_kernels() {
 }
 
 template <int CIN, int COUT, bool FUSE, bool F8>
-static cudaError_t launch_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *p_out_maps, const TcParams &p, int grid, cudaStream_t s) {
-    tc_conv3x3_kernel<CIN, COUT, FUSE, F8><<<grid, NUM_THREADS, Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, p_out_maps[0], p_out_maps[1], p);
+static cudaError_t launch_k(const CUtensorMap *tmap, const CUtensorMap *omap, const TcParams &p, int grid, cudaStream_t s) {
+    tc_conv3x3_kernel<CIN, COUT, FUSE, F8><<<grid, NUM_THREADS, Cfg<CIN, COUT, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *omap, p);
     return cudaGetLastError();
 }
 
 template <int CIN, int COUT>
-static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *omaps, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+static cudaError_t launch_one(const CUtensorMap *tmap, const CUtensorMap *omap, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
     int grid = p.n_tilesets < num_sms ? p.n_tilesets : num_sms;
-    if (f8) return p.partial ? launch_k<CIN, COUT, true, true>(tmap, tmap8, omaps, p, grid, s) : launch_k<CIN, COUT, false, true>(tmap, tmap8, omaps, p, grid, s);
-    return p.partial ? launch_k<CIN, COUT, true, false>(tmap, tmap8, omaps, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, tmap8, omaps, p, grid, s);
+    if (f8) return p.partial ? launch_k<CIN, COUT, true, true>(tmap, omap, p, grid, s) : launch_k<CIN, COUT, false, true>(tmap, omap, p, grid, s);
+    return p.partial ? launch_k<CIN, COUT, true, false>(tmap, omap, p, grid, s) : launch_k<CIN, COUT, false, false>(tmap, omap, p, grid, s);
 }
 
 static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t bytes);
-static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h);
 static int make_rec_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp, int box_w, int box_h, int y0, int rows);
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h, int y0, int rows);
 
 template <int CIN, bool FUSE, bool F8>
-static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *tmapw, const CUtensorMap *p_out_maps,
-                                 const TcParams &p, int grid, cudaStream_t s) {
-    tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8><<<grid, NUM_THREADS, PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmap8, *tmapw, p_out_maps[0], p_out_maps[1], p);
+static cudaError_t launch_pair_k(const CUtensorMap *tmap, const CUtensorMap *tmapw, const CUtensorMap *omap, const TcParams &p, int grid, cudaStream_t s) {
+    tc_conv3x3_pair_kernel<CIN, 128, FUSE, F8><<<grid, NUM_THREADS, PairCfg<CIN, 128, FUSE, F8>::SMEM_BYTES, s>>>(*tmap, *tmapw, *omap, p);
     return cudaGetLastError();
 }
 
 template <int CIN>
-static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *tmap8, const CUtensorMap *omaps, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
+static cudaError_t launch_pair(const CUtensorMap *tmap, const CUtensorMap *omap, const TcParams &p, int num_sms, bool f8, cudaStream_t s) {
     using C0 = Cfg<CIN, 128, false, false>;
-    const size_t bytes = (size_t)C0::NCHUNK * 9 * C0::KBLOCKS * 2 * C0::B_BLOCK;   // both flavours stream the same number of bytes per tile-set
+    const size_t bytes = (size_t)C0::NCHUNK * 9 * 2 * C0::B_BLOCK;   // both flavours stream the same number of bytes per tile-set
     CUtensorMap tmapw;
     if (make_weight_stream_map(&tmapw, p.wpack, bytes)) return cudaErrorInvalidValue;
     const int n_pair_sets = (p.n_tilesets + 1) / 2;
     int grid = 2 * (n_pair_sets < num_sms / 2 ? n_pair_sets : num_sms / 2);
-    if (f8) return p.partial ? launch_pair_k<CIN, true, true>(tmap, tmap8, &tmapw, omaps, p, grid, s) : launch_pair_k<CIN, false, true>(tmap, tmap8, &tmapw, omaps, p, grid, s);
-    return p.partial ? launch_pair_k<CIN, true, false>(tmap, tmap8, &tmapw, omaps, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, tmap8, &tmapw, omaps, p, grid, s);
+    if (f8) return p.partial ? launch_pair_k<CIN, true, true>(tmap, &tmapw, omap, p, grid, s) : launch_pair_k<CIN, false, true>(tmap, &tmapw, omap, p, grid, s);
+    return p.partial ? launch_pair_k<CIN, true, false>(tmap, &tmapw, omap, p, grid, s) : launch_pair_k<CIN, false, false>(tmap, &tmapw, omap, p, grid, s);
 }
 
 // ---- row-strip kernel (narrow layers) ----
@@ -170,18 +163,17 @@ static int strip_seg_rows() {   // rows per work unit (tuning knob: W2X_STRIP_RO
 }
 
 template <int CIN, int COUT, bool F8>
-static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p, int num_sms, bool out_rec, cudaStream_t s) {
+static cudaError_t launch_strip_k(const CUtensorMap *maps, const StripParams &p, int num_sms, cudaStream_t s) {
     using C = StripCfg<CIN, COUT, F8>;
     const int grid = p.n_units < num_sms ? p.n_units : num_sms;
-    if (out_rec) tc_conv3x3_strip_kernel<CIN, COUT, F8, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], p);
-    else tc_conv3x3_strip_kernel<CIN, COUT, F8, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], p);
+    tc_conv3x3_strip_kernel<CIN, COUT, F8><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(maps[0], maps[1], p);
     return cudaGetLastError();
 }
 
 #define W2X_STRIP_SHAPES(X) X(32, 32) X(32, 64) X(64, 32) X(64, 64)
 
 static cudaError_t launch_strip(const __half *in, const void *wstrip, const float *bias, __half *out, int cin, int cout, int pw, int ph,
-                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof, int out_y0, int out_rows, int out_rec) {
+                                float out_scale, int f8, int num_sms, cudaStream_t s, unsigned long long *prof, int out_y0, int out_rows) {
     StripParams p;
     p.wpack = reinterpret_cast<const uint8_t *>(wstrip);
     for (int i = 0; i < cout; i++) p.bias[i] = bias[i] * ACT_SCALE;
@@ -200,15 +192,12 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 #else
     p.dbg = 0;
 #endif
-    CUtensorMap maps[3];   // in (RECORD) | out | out8 (planar F8 output only)
+    CUtensorMap maps[2];   // in | out
     if (make_rec_map(&maps[0], in, cin, pw, ph, STRIP_BOXW, 1, 0, ph)) return cudaErrorInvalidValue;
-    if (out_rec) {
-        if (make_rec_map(&maps[1], out, cout, pw, ph, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
-        maps[2] = maps[1];
-    } else if (make_out_tensor_maps(&maps[1], &maps[2], out, cout, pw, ph, f8 != 0, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
+    if (make_rec_map(&maps[1], out, cout, pw, ph, 32, 1, out_y0, out_rows)) return cudaErrorInvalidValue;
 #define X(ci, co)                                                                                       \
     if (cin == ci && cout == co)                                                                        \
-        return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, out_rec != 0, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, out_rec != 0, s);
+        return f8 ? launch_strip_k<ci, co, true>(maps, p, num_sms, s) : launch_strip_k<ci, co, false>(maps, p, num_sms, s);
     W2X_STRIP_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -216,16 +205,12 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
 
 cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wstrip, const float *bias, __half *out, int cin,
                             int cout, int pw, int ph, float out_scale, int f8, int num_sms, cudaStream_t s,
-                            unsigned long long *prof, const float *last_w, float *partial, int pair, int out_y0, int out_rows,
-                            int in_rec, int out_rec) {
+                            unsigned long long *prof, const float *last_w, float *partial, int pair, int out_y0, int out_rows) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
-    if (in_rec) {          // the row-strip kernel consumes RECORD frames; every other kernel planar ones
-        if (!wstrip || partial || !strip_supported(cin, cout)) return cudaErrorInvalidValue;
-        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof, out_y0, out_rows, out_rec);
-    }
-    if (out_rec) return cudaErrorInvalidValue;
-    CUtensorMap tmap_in, tmap_in8;
-    if (make_act_maps(&tmap_in, &tmap_in8, in, cin, pw, ph, f8 != 0, act_kc(cin), HALO, HALO)) return cudaErrorInvalidValue;
+    if (wstrip && !partial && strip_supported(cin, cout))
+        return launch_strip(in, wstrip, bias, out, cin, cout, pw, ph, out_scale, f8, num_sms, s, prof, out_y0, out_rows);
+    CUtensorMap tmap_in;
+    if (make_rec_map(&tmap_in, in, cin, pw, ph, HALO, HALO, 0, ph)) return cudaErrorInvalidValue;
     TcParams p;
     p.wpack = reinterpret_cast<const uint16_t *>(wpack);
     // ACT_SCALE (a power of two) is folded into the epilogue's affine step: leaky(16 v) = 16 leaky(v) exactly, so the
@@ -251,18 +236,18 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
         if (!last_w) return cudaErrorInvalidValue;
         for (int i = 0; i < 9 * cout; i++) p.last_w[i] = last_w[i] * (1.0f / ACT_SCALE);      // HOST pointer: [9][cout]
     }
-    // the epilogue's TMA stores: 8x4-pixel x 32-channel boxes of this layer's output frame (fused layers store no frame)
-    CUtensorMap omaps[2];
-    if (partial) { omaps[0] = tmap_in; omaps[1] = tmap_in8; }
-    else if (make_out_tensor_maps(&omaps[0], &omaps[1], out, cout, pw, ph, f8 != 0, 8, 4, out_y0, out_rows)) return cudaErrorInvalidValue;
+    // the epilogue's TMA stores: 8x4-pixel boxes of records of this layer's output frame (fused layers store no frame)
+    CUtensorMap omap;
+    if (partial) omap = tmap_in;
+    else if (make_rec_map(&omap, out, cout, pw, ph, 8, 4, out_y0, out_rows)) return cudaErrorInvalidValue;
     if (pair && cout == 128 && num_sms >= 2) {
 #define X(ci) \
-    if (cin == ci) return launch_pair<ci>(&tmap_in, &tmap_in8, omaps, p, num_sms, f8 != 0, s);
+    if (cin == ci) return launch_pair<ci>(&tmap_in, &omap, p, num_sms, f8 != 0, s);
         W2X_PAIR_CINS(X)
 #undef X
     }
 #define X(ci, co) \
-    if (cin == ci && cout == co) return launch_one<ci, co>(&tmap_in, &tmap_in8, omaps, p, num_sms, f8 != 0, s);
+    if (cin == ci && cout == co) return launch_one<ci, co>(&tmap_in, &omap, p, num_sms, f8 != 0, s);
     W2X_TC_SHAPES(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -270,44 +255,35 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
 
 template <int COUT>
 static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
-                                  cudaStream_t s, int f8, int out_y0, int out_rows, int out_rec) {
+                                  cudaStream_t s, int f8, int out_y0, int out_rows) {
     static_assert(FIRST_TILE_BYTES + 1024 <= 48 * 1024, "the first layer's staging tile stays under the default dynamic shared memory limit");
     // (under 48 KB no opt-in is required; the attribute is set anyway, once per process, as every other kernel of the engine does)
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
     FirstParams<COUT> prm;
     for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
     for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
-    CUtensorMap omaps[2];
+    CUtensorMap omap;
     dim3 grid((pw + 31) / 32, (out_rows + 7) / 8);   // blocks tile the store window
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
-    if (out_rec) {
-        if (make_rec_map(&omaps[0], out, COUT, pw, ph, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
-        omaps[1] = omaps[0];
-        if (f8) first_layer_kernel<COUT, true, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
-        else first_layer_kernel<COUT, false, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
-        return cudaGetLastError();
-    }
-    if (make_out_tensor_maps(&omaps[0], &omaps[1], out, COUT, pw, ph, f8 != 0, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
-    if (f8) first_layer_kernel<COUT, true, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
-    else first_layer_kernel<COUT, false, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omaps[0], omaps[1], prm);
+    if (make_rec_map(&omap, out, COUT, pw, ph, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
+    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omap, prm);
+    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omap, prm);
     return cudaGetLastError();
 }
 
 cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows, int out_rec) {
+                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     switch (cout) {
-        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
-        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
-        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows, out_rec);
+        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -346,9 +322,9 @@ cudaError_t launch_last_gather_xy(const float *partial, int pw, int ph, float bi
     return cudaGetLastError();
 }
 
-cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8, int rec) {
+cudaError_t launch_planar_to_nhwc(const float *in, int C, int w, int h, __half *out, cudaStream_t s, int f8) {
     long total = (long)(w + 2) * (h + 2) * C;
-    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8, rec);
+    planar_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, C, w, h, out, f8);
     return cudaGetLastError();
 }
 
@@ -391,33 +367,6 @@ static int make_weight_stream_map(CUtensorMap *map, const void *base, size_t byt
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-// Output frame as the epilogue stores it: boxes of 32 channels x 8 px x 4 rows (one epilogue warp's pixels; the first
-// layer's blocks store 32 x 8 pixels).
-//   f16x3: ONE map over [2][Hp][Wp][C] fp16, box {32, 8, 4, 2} (hi and lo planes in one store), SWIZZLE_64B; map8 = copy.
-//   F8:    map16 over the xh plane, box {32, 8, 4, 1}, SWIZZLE_64B; map8 over the two e4m3 planes, box {32, 8, 4, 2}, SWIZZLE_32B.
-// Only frame rows [y0, y0 + rows) are part of the maps (row coordinate 0 = frame row y0); everything else is clipped.
-static int make_out_tensor_maps(CUtensorMap *map16, CUtensorMap *map8, void *base, int C, int Wp, int Hp, bool f8, int box_w, int box_h, int y0, int rows) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc || rows < 1 || y0 < 0 || y0 + rows > Hp) return -1;
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)rows, (cuuint64_t)(f8 ? 1 : 2)};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-        cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)(f8 ? 1 : 2)};
-        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, reinterpret_cast<char *>(base) + (size_t)y0 * Wp * C * 2, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return (int)r;
-    }
-    if (!f8) { *map8 = *map16; return 0; }
-    char *b8 = reinterpret_cast<char *>(base) + (size_t)2 * Hp * Wp * C + (size_t)y0 * Wp * C;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)rows, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
-    cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 2};
-    CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, b8, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)r;
-}
-
 // RECORD frame [Hp][Wp][C/32][128 B] (tc_epilogue.cuh) as a byte tensor {128, C/32, Wp, rows}, box {128, 1, box_w, box_h},
 // SWIZZLE_128B; only frame rows [y0, y0 + rows) are part of the map (row coordinate 0 = frame row y0).
 static int make_rec_map(CUtensorMap *map, const void *base, int C, int Wp, int Hp, int box_w, int box_h, int y0, int rows) {
@@ -430,34 +379,6 @@ static int make_rec_map(CUtensorMap *map, const void *base, int C, int Wp, int H
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(reinterpret_cast<const char *>(base)) + (size_t)y0 * Wp * C * 4, dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : (int)r;
-}
-
-// Input frame as the layer kernels stage it: boxes of box_c channels x box_w pixels x box_h rows of ONE plane.
-//   f16x3: map16 over [2][Hp][Wp][C] fp16 (plane index = 4th coordinate); map8 = copy.
-//   F8:    frames are [xh fp16 [Hp][Wp][C]] [xh8 [Hp][Wp][C]] [xl8 [Hp][Wp][C]] (bytes 2 + 1 + 1 per element):
-//          map16 over the xh plane, map8 over the two e4m3 planes.
-// Swizzle = the box's inner extent in bytes (64 B / 128 B for fp16, 32 B / 64 B for e4m3).
-static int make_act_maps(CUtensorMap *map16, CUtensorMap *map8, const void *base, int C, int Wp, int Hp, bool f8, int box_c, int box_w, int box_h) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) return -1;
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(f8 ? 1 : 2)};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-        CUresult r = enc(map16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return (int)r;
-    }
-    if (!f8) { *map8 = *map16; return 0; }
-    const char *b8 = reinterpret_cast<const char *>(base) + (size_t)2 * Hp * Wp * C;
-    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, 2};
-    cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)Wp * C, (cuuint64_t)Hp * Wp * C};
-    CUresult r = enc(map8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<char *>(b8), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 

@@ -323,8 +323,8 @@ static inline size_t swizzled_offset(size_t logical, int row_bytes) {
 
 static void pack_tc_layer(const Layer &L, TcPack &P) {
     // Blocks of 32 input channels (two K=16 MMA steps), rows of 64 B, SWIZZLE_64B, in the kernel's consumption
-    // order: [activation chunk c (64 ch, or 32 when Cin = 32)][tap][32-ch block inside the chunk][hi | lo].
-    const int kc_a = L.n_in <= 64 ? 32 : 64;   // = tc::act_kc(n_in): channels per staged activation box
+    // order: [32-channel block c (= one staged box of records)][tap][hi | lo].
+    const int kc_a = 32;                       // channels per staged activation box (one record block)
     P.kc = 32;
     P.n_chunk = L.n_in / kc_a;
     P.kblocks = kc_a / 32;
@@ -363,7 +363,7 @@ static void pack_tc_layer(const Layer &L, TcPack &P) {
 static inline size_t swizzle32(size_t logical) { return logical ^ (((logical >> 7) & 1) << 4); }
 
 static void pack_tc_layer_f8(const Layer &L, TcPack &P) {
-    const int kc_a = L.n_in <= 64 ? 32 : 64;   // = tc::act_kc(n_in): channels per staged activation box
+    const int kc_a = 32;                       // channels per staged activation box (one record block)
     const size_t blk16 = (size_t)L.n_out * 64, blk8 = (size_t)L.n_out * 32, stage = blk16 + 2 * blk8;
     P.bytes8.assign((size_t)P.n_chunk * 9 * P.kblocks * stage, 0);
     const float up = std::ldexp(1.0f, F8_C), down = std::ldexp(1.0f, -F8_A);

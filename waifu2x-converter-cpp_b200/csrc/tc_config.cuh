@@ -6,54 +6,48 @@
 // ================================================================================================
 // Per-layer configuration
 // ================================================================================================
-// Channels per staged activation box: 32 for layers up to 64 inputs (two small boxes per tile-set instead of one 83 KB
-// one leave room for the store staging and a deep weight ring), 64 for the 128-input layers.
-__host__ __device__ constexpr int act_kc(int cin) { return cin <= 64 ? 32 : 64; }
-
+// Activations are RECORD frames (kernels.h): [Hp][Wp][C/32][128 B], one 128-byte record per pixel per 32-channel block =
+// {xh fp16 x32 | xh8 e4m3 x32 | xl8 e4m3 x32} (F8) or {hi fp16 x32 | lo fp16 x32}.  One staged box = the 18x18-pixel halo
+// region of ONE 32-channel block: 324 rows of 128 B, SWIZZLE_128B; the fp16 K steps / xh8 / xl8 (or lo) slices of a pixel
+// are the 32-byte quarters of its row (+0, +2, +4, +6 sixteen-byte units in the descriptor start address).
+//
 // F8 = false: three kind::f16 products xh*wh + xl*wh + xh*wl ("f16x3").
 // F8 = true : xh*wh in kind::f16, the two correction products in kind::f8f6f4 on e4m3 copies
 //             xl8*wh8 + xh8*wl8 (K = 32 per MMA at twice the rate: 2.0 instead of 3.0 pass-equivalents).
-//             Activation frames then hold [xh fp16][xh8][xl8] planes (same 4 bytes per element).
 constexpr int F8_A = 10, F8_C = 1;   // xl8 = e4m3((x16 - xh) * 2^F8_A), xh8 = e4m3(xh * 2^-F8_C); must match w2x_internal.h
 
 template <int CIN, int COUT, bool FUSE = false, bool F8 = false>
 struct Cfg {
-    // ---- A operand (activations): one TMA box per (tile-set, 64-channel chunk, hi|lo) ----
-    static constexpr int KC = act_kc(CIN);              // channels per activation chunk
+    // ---- A operand (activations): one TMA box per (tile-set, 32-channel block) ----
+    static constexpr int KC = 32;                       // channels per activation chunk
     static constexpr int NCHUNK = CIN / KC;
-    static constexpr int ROWB = KC * 2;                 // bytes per pixel per chunk (= swizzle span)
-    static constexpr uint32_t A_LAYOUT = ROWB == 128 ? 2u : 4u;                // SWIZZLE_128B : SWIZZLE_64B
-    static constexpr int A_PLANE = HALO * HALO * ROWB;                       // bytes one TMA box delivers
-    static constexpr int A_PLANE_PAD = (A_PLANE + 1023) / 1024 * 1024;
-    static constexpr int ROWB8 = KC;                                         // e4m3 planes: one byte per channel
-    static constexpr uint32_t A8_LAYOUT = ROWB8 == 64 ? 4u : 6u;               // SWIZZLE_64B : SWIZZLE_32B
-    static constexpr int A8_PLANE = HALO * HALO * ROWB8;
-    static constexpr int A8_PLANE_PAD = (A8_PLANE + 1023) / 1024 * 1024;
-    static constexpr int A_SLOT = F8 ? A_PLANE_PAD + 2 * A8_PLANE_PAD : 2 * A_PLANE_PAD;   // xh + (xh8, xl8)  |  hi + lo
-    static constexpr int A_TX = F8 ? A_PLANE + 2 * A8_PLANE : 2 * A_PLANE;   // bytes the TMA loads of one slot deliver
+    static constexpr int ROWB = 128;                    // bytes per pixel per chunk (one record = the swizzle span)
+    static constexpr uint32_t A_LAYOUT = 2u;            // SWIZZLE_128B
+    static constexpr int A_TX = HALO * HALO * ROWB;     // bytes the TMA load of one slot delivers
+    static constexpr int A_SLOT = (A_TX + 1023) / 1024 * 1024;
     static constexpr int A_SLOTS = 2;
     // ---- B operand (weights): stages of 32 input channels (two K=16 steps), SWIZZLE_64B rows of 64 B ----
     static constexpr int KB = 32;
-    static constexpr int KBLOCKS = KC / KB;             // weight stages per (chunk, tap, part)
+    static constexpr int KBLOCKS = 1;                   // weight stages per (chunk, tap, part)
     static constexpr int B_ROWB = KB * 2;
     static constexpr uint32_t B_LAYOUT = 4u;
     // Cout <= 64: hi and lo weights form ONE stage of 2*Cout rows, so xh*[wh;wl] is a single N = 2*Cout MMA
     // (accumulators D1 | D2 side by side, summed in the epilogue) -- two MMAs per K step instead of three.
     static constexpr bool STACK = COUT <= 64 && !F8;
-    static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, kblock, hi|lo) block
+    static constexpr int B_BLOCK = COUT * B_ROWB;                            // one (chunk, tap, hi|lo) block
     // F8: per 32-channel block ONE stage [wh fp16 (Cout x 64 B) | wh8 | wl8 (e4m3, Cout x 32 B each)]: four MMAs per
     // issuer per barrier round trip.
-    static constexpr bool MERGE = F8 && (COUT <= 64 || FUSE);   // (a stored 128-in/128-out layer has no room for 16 KB stages beside its two 83 KB activation slots)
+    static constexpr bool MERGE = F8;
     static constexpr int B_STAGE = (STACK || MERGE) ? 2 * B_BLOCK : B_BLOCK;
-    static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * KBLOCKS * ((STACK || MERGE) ? 1 : 2);
+    static constexpr int STAGES_PER_TILESET = NCHUNK * 9 * ((STACK || MERGE) ? 1 : 2);
     // ---- accumulators ----
     static constexpr int TILE_COLS = STACK ? 2 * COUT : COUT;                // TMEM columns per M-tile
     static constexpr int ACC_COLS = 4 * TILE_COLS;                           // 2 sets x 2 M-tiles
     static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
-    // ---- shared memory map: [A slots][B stages][barriers + bias (1 KB)][last-layer weights][store staging] ----
+    // ---- shared memory map: [A slots][B stages][barriers (1 KB)][store staging] ----
     static constexpr int BAR_BYTES = 1024;
     static constexpr int W6_BYTES = 0;                                       // (the fused last layer's weights travel as kernel parameters)
-    static constexpr int STG_WARP = 4096;                                    // [fp16 plane 2 KB | lo plane 2 KB, or xh8 1 KB | xl8 1 KB] of 32 px x 32 ch
+    static constexpr int STG_WARP = 4096;                                    // one record tile: 32 px x 128 B
     static constexpr int STG_BYTES = FUSE ? 0 : 8 * STG_WARP;               // epilogue store staging per epilogue warp
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int NB_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W6_BYTES - STG_BYTES - A_SLOTS * A_SLOT) / B_STAGE;
@@ -65,8 +59,8 @@ struct Cfg {
     static_assert(NB >= 3, "need at least three weight stages");
     static_assert((8 + 2 * NB) * 8 + 4 <= 512 && COUT * 4 <= 512, "barrier/bias area overflow");
     static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
-    static_assert(B_STAGE % 512 == 0, "weight stage must keep the 512-byte SWIZZLE_64B pattern alignment");
-    static_assert(CIN % KC == 0 && KC % KB == 0 && COUT % 16 == 0 && COUT <= 128, "shape");
+    static_assert(B_STAGE % 1024 == 0 && A_SLOT % 1024 == 0, "swizzle pattern alignment");
+    static_assert(CIN % KC == 0 && COUT % 16 == 0 && COUT <= 128, "shape");
 };
 
 // warps: 0 A producer | 1, 7 MMA issuers (M-tile 0, 1) | 2 B producer + TMEM owner | 3-6 epilogue of M-tile 0 | 8-11 epilogue of M-tile 1
@@ -108,11 +102,13 @@ template <int CIN, int COUT, bool FUSE, bool F8>
 struct PairCfg : Cfg<CIN, COUT, FUSE, F8> {
     using Base = Cfg<CIN, COUT, FUSE, F8>;
     static_assert(COUT == 128, "the CTA-pair kernel is built for the 128-wide layers");
+    static constexpr int A_SLOTS = FUSE ? 3 : 2;                          // (a fused layer has no store staging: room for a third box)
     static constexpr int B_HALF = Base::B_BLOCK;                         // bytes of one weight stage held by ONE CTA: its 64 rows of BOTH blocks
                                                                          // of a 32-channel step ([hi | lo] or [wh | wh8 | wl8])
-    static constexpr int NBP_FIT = (Base::SMEM_MAX - 1024 - Base::BAR_BYTES - Base::W6_BYTES - Base::STG_BYTES - Base::A_SLOTS * Base::A_SLOT) / B_HALF;
+    static constexpr int NBP_FIT = (Base::SMEM_MAX - 1024 - Base::BAR_BYTES - Base::W6_BYTES - Base::STG_BYTES - A_SLOTS * Base::A_SLOT) / B_HALF;
     static constexpr int NBP = NBP_FIT > 12 ? 12 : NBP_FIT;
-    static constexpr int SMEM_BYTES = 1024 + Base::A_SLOTS * Base::A_SLOT + NBP * B_HALF + Base::BAR_BYTES + Base::W6_BYTES + Base::STG_BYTES;
-    static_assert((8 + 2 * NBP) * 8 + 4 <= 512, "barrier area overflow");
+    static constexpr int SMEM_BYTES = 1024 + A_SLOTS * Base::A_SLOT + NBP * B_HALF + Base::BAR_BYTES + Base::W6_BYTES + Base::STG_BYTES;
+    static_assert((2 * A_SLOTS + 4 + 2 * NBP) * 8 + 4 <= 512, "barrier area overflow");
     static_assert(B_HALF % 2048 == 0, "weight halves are moved as 2 KB TMA boxes");
+    static_assert(NBP >= 6, "weight ring too shallow");
 };

@@ -19,12 +19,12 @@ struct FirstParams {
 };
 constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16 KB]  or  [xh 16 KB | xh8 8 KB | xl8 8 KB]
 
-// REC: the output is a RECORD frame (tc_epilogue.cuh): the staged image is [256 px][128 B] per 32 channels, SWIZZLE_128B,
-// one box {128 B, 1, 32 px, 8 rows} -- a third of the planar frame's TMA row requests.
-template <int COUT, bool F8, bool REC>
+// The output is a RECORD frame (tc_epilogue.cuh): the staged image is [256 px][128 B] per 32 channels, SWIZZLE_128B, one box
+// {128 B, 1, 32 px, 8 rows} per 32 channels.
+template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
 first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, int out_y0, const __grid_constant__ CUtensorMap tmap_out,
-                   const __grid_constant__ CUtensorMap tmap_out8, const __grid_constant__ FirstParams<COUT> prm) {
+                   const __grid_constant__ FirstParams<COUT> prm) {
     extern __shared__ uint8_t first_smem[];
     const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
     const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
@@ -38,10 +38,10 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
         }
     const uint32_t r = (uint32_t)threadIdx.x;                            // pixel index inside the block = row of the staged image
-    const uint32_t sw64 = (r >> 1) & 3u, sw32 = (r >> 2) & 1u, sw128 = r & 7u;
+    const uint32_t sw128 = r & 7u;
 #pragma unroll 1
     for (int cb = 0; cb < COUT / 32; cb++) {
-        if (cb) {   // the previous 32 channels' boxes must have left shared memory
+        if (cb) {   // the previous 32 channels' box must have left shared memory
             if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncthreads();
         }
@@ -74,42 +74,22 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
                     lo[i] = *reinterpret_cast<uint32_t *>(&l);
                 }
             }
-            if constexpr (REC) {
-                // record row of 128 B: units 0..3 fp16, then [xh8 16+16 B | xl8 16+16 B] or the lo half
-                sts128(tile + r * 128u + (((uint32_t)c8 ^ sw128) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-                if constexpr (F8) {
-                    const uint32_t half = ((uint32_t)c8 & 1u) * 8u;
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((4u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[0]), "r"(lo[1]) : "memory");
-                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((6u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[2]), "r"(lo[3]) : "memory");
-                } else {
-                    sts128(tile + r * 128u + (((4u + (uint32_t)c8) ^ sw128) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-                }
-                continue;
-            }
-            // 16-byte unit c8 of this pixel's 64-byte fp16 row (SWIZZLE_64B image)
-            sts128(tile + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            // record row of 128 B: units 0..3 fp16, then [xh8 16+16 B | xl8 16+16 B] or the lo half
+            sts128(tile + r * 128u + (((uint32_t)c8 ^ sw128) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
             if constexpr (F8) {
-                // 8 bytes of the pixel's 32-byte e4m3 rows (SWIZZLE_32B images): unit c8/2, half c8%2
-                const uint32_t off = r * 32u + ((((uint32_t)c8 >> 1) ^ sw32) << 4) + ((uint32_t)c8 & 1u) * 8u;
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 16384u + off), "r"(lo[0]), "r"(lo[1]) : "memory");
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + 24576u + off), "r"(lo[2]), "r"(lo[3]) : "memory");
+                const uint32_t half = ((uint32_t)c8 & 1u) * 8u;
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((4u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[0]), "r"(lo[1]) : "memory");
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(tile + r * 128u + (((6u + ((uint32_t)c8 >> 1)) ^ sw128) << 4) + half), "r"(lo[2]), "r"(lo[3]) : "memory");
             } else {
-                sts128(tile + 16384u + r * 64u + (((uint32_t)c8 ^ sw64) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+                sts128(tile + r * 128u + (((4u + (uint32_t)c8) ^ sw128) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
             }
         }
         fence_proxy_async();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;   // window-relative: the store maps cover frame rows [out_y0, ...)
-            if constexpr (REC)
-                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(0), "r"(cb), "r"(x0), "r"(y0) : "memory");
-            else
-                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
-            if constexpr (F8 && !REC)
-                asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                             ::"l"(reinterpret_cast<uint64_t>(&tmap_out8)), "r"(tile + 16384u), "r"(cb * 32), "r"(x0), "r"(y0), "r"(0) : "memory");
+            const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;   // window-relative: the store map covers frame rows [out_y0, ...)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_out)), "r"(tile), "r"(0), "r"(cb), "r"(x0), "r"(y0) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
@@ -127,8 +107,8 @@ last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__
     __syncthreads();
     const int x = crop + blockIdx.x * 32 + (threadIdx.x & 31), y = crop + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= pw - crop || y >= ph - crop) return;
-    const size_t plane_elems = (size_t)ph * pw * CIN;
     const float inv = 1.0f / ACT_SCALE;
+    const uint8_t *frame = reinterpret_cast<const uint8_t *>(in);      // RECORD frame: [ph][pw][CIN/32][128 B]
     float acc = 0.f;
     for (int c8 = 0; c8 < CIN / 8; c8++) {
         float t[8];
@@ -139,14 +119,14 @@ last_layer_kernel(const __half *__restrict__ in, int pw, int ph, const float *__
 #pragma unroll
             for (int kx = 0; kx < 3; kx++) {
                 // frame reads outside [0,pw)x[0,ph) cannot happen: crop >= 1 keeps the 3x3 window inside
-                const size_t pixo = ((size_t)(y + ky - 1) * pw + (x + kx - 1)) * CIN + c8 * 8;
-                const __half *ph_ = in + pixo;
-                uint4 uh = __ldg(reinterpret_cast<const uint4 *>(ph_));
+                const uint8_t *rec = frame + (((size_t)(y + ky - 1) * pw + (x + kx - 1)) * (CIN / 32) + c8 / 4) * 128;
+                const int k0 = (c8 & 3) * 8;                                 // first of this thread's 8 channels inside the record
+                uint4 uh = __ldg(reinterpret_cast<const uint4 *>(rec + 2 * k0));
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&uh);
                 uint4 ul = make_uint4(0, 0, 0, 0);
                 uint2 ul8 = make_uint2(0, 0);
-                if constexpr (F8) ul8 = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint8_t *>(in) + 3 * plane_elems + pixo));
-                else ul = __ldg(reinterpret_cast<const uint4 *>(ph_ + plane_elems));
+                if constexpr (F8) ul8 = __ldg(reinterpret_cast<const uint2 *>(rec + 96 + k0));          // xl8
+                else ul = __ldg(reinterpret_cast<const uint4 *>(rec + 64 + 2 * k0));                    // lo
                 const __half2 *l2 = reinterpret_cast<const __half2 *>(&ul);
                 const __nv_fp8x2_storage_t *l8 = reinterpret_cast<const __nv_fp8x2_storage_t *>(&ul8);
 #pragma unroll
@@ -188,7 +168,7 @@ last_gather_kernel(const float *__restrict__ partial, int pw, int ph, float bias
     dst[(long)(y - crop_top) * dst_stride + (x - crop_x)] = fminf(r, 0.f) * 0.1f + fmaxf(r, 0.f);
 }
 
-__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8, int rec) {
+__global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w, int h, __half *__restrict__ out, int f8) {
     const int pw = w + 2, ph = h + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)pw * ph * C;
@@ -199,44 +179,33 @@ __global__ void planar_to_nhwc_kernel(const float *__restrict__ in, int C, int w
     int sx = min(max(x - 1, 0), w - 1), sy = min(max(y - 1, 0), h - 1);
     float a = in[((long)c * h + sy) * w + sx] * ACT_SCALE;
     __half hh = __float2half_rn(a);
-    if (rec) {   // RECORD frame: [pixel][C/32][128 B] = {fp16 x32 | xh8 x32 | xl8 x32} or {hi x32 | lo x32}
-        uint8_t *recp = reinterpret_cast<uint8_t *>(out) + (pix * (C / 32) + c / 32) * 128;
-        const int k = c % 32;
-        const float hf = __half2float(hh);
-        reinterpret_cast<__half *>(recp)[k] = hh;
-        if (f8) {
-            recp[64 + k] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
-            recp[96 + k] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
-        } else {
-            reinterpret_cast<__half *>(recp + 64)[k] = __float2half_rn(a - hf);
-        }
-        return;
-    }
-    out[idx] = hh;
+    // RECORD frame: [pixel][C/32][128 B] = {fp16 x32 | xh8 x32 | xl8 x32} or {hi x32 | lo x32}
+    uint8_t *recp = reinterpret_cast<uint8_t *>(out) + (pix * (C / 32) + c / 32) * 128;
+    const int k = c % 32;
+    const float hf = __half2float(hh);
+    reinterpret_cast<__half *>(recp)[k] = hh;
     if (f8) {
-        uint8_t *b = reinterpret_cast<uint8_t *>(out);
-        const float hf = __half2float(hh);
-        b[2 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
-        b[3 * total + idx] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
+        recp[64 + k] = (uint8_t)__nv_cvt_float_to_fp8(hf * (1.0f / (float)(1 << F8_C)), __NV_SATFINITE, __NV_E4M3);
+        recp[96 + k] = (uint8_t)__nv_cvt_float_to_fp8((a - hf) * (float)(1 << F8_A), __NV_SATFINITE, __NV_E4M3);
     } else {
-        out[idx + total] = __float2half_rn(a - __half2float(hh));
+        reinterpret_cast<__half *>(recp + 64)[k] = __float2half_rn(a - hf);
     }
 }
 
 __global__ void nhwc_to_planar_kernel(const __half *__restrict__ in, int C, int w, int h, float *__restrict__ out, int f8) {
-    const int pw = w + 2, ph = h + 2;
+    const int pw = w + 2;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     long total = (long)w * h * C;
     if (idx >= total) return;
     int x = (int)(idx % w);
     long r = idx / w;
     int y = (int)(r % h), c = (int)(r / h);
-    long src = ((long)(y + 1) * pw + (x + 1)) * C + c;
-    long plane = (long)pw * ph * C;
+    const uint8_t *recp = reinterpret_cast<const uint8_t *>(in) + ((((long)(y + 1) * pw + (x + 1)) * (C / 32)) + c / 32) * 128;
+    const int k = c % 32;
     float lo;
     if (f8) {
-        __half_raw r = __nv_cvt_fp8_to_halfraw(reinterpret_cast<const uint8_t *>(in)[3 * plane + src], __NV_E4M3);
-        lo = __half2float(*reinterpret_cast<__half *>(&r)) * (1.0f / (float)(1 << F8_A));
-    } else lo = __half2float(in[src + plane]);
-    out[idx] = (__half2float(in[src]) + lo) * (1.0f / ACT_SCALE);
+        __half_raw hr = __nv_cvt_fp8_to_halfraw(recp[96 + k], __NV_E4M3);
+        lo = __half2float(*reinterpret_cast<__half *>(&hr)) * (1.0f / (float)(1 << F8_A));
+    } else lo = __half2float(reinterpret_cast<const __half *>(recp + 64)[k]);
+    out[idx] = (__half2float(reinterpret_cast<const __half *>(recp)[k]) + lo) * (1.0f / ACT_SCALE);
 }

@@ -8,11 +8,10 @@
 // ================================================================================================
 template <int CIN, int COUT, bool FUSE, bool F8>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
-                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out8, const TcParams p) {
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
     using C = Cfg<CIN, COUT, FUSE, F8>;
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment: swizzle patterns repeat every 1024 B (SWIZZLE_128B) / 512 B (SWIZZLE_64B)
+    // 1024-byte alignment: the SWIZZLE_128B pattern repeats every 1024 B
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + C::A_SLOTS * C::A_SLOT;
@@ -49,11 +48,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     }
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_in);
-        if constexpr (F8) prefetch_tmap(&tmap_in8);
-        if constexpr (!FUSE) {
-            prefetch_tmap(&tmap_out);
-            if constexpr (F8) prefetch_tmap(&tmap_out8);
-        }
+        if constexpr (!FUSE) prefetch_tmap(&tmap_out);
     }
     if (warp == 2) {
         tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -65,7 +60,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);   // uniform for the compiler as well
 
     if (warp == 0) {
-        // ===================== A producer: one halo'd box per (tile-set, chunk, hi|lo) ==============
+        // ===================== A producer: one halo'd box of records per (tile-set, 32-channel block) ==============
         // (whole warp walks the loop; the arrive and the TMA instructions elect one lane)
         {
             uint32_t it = 0;
@@ -77,14 +72,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     const uint32_t slot = it & 1u, round = it >> 1;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
                     mbar_arrive_expect_tx(a_full(slot), (uint32_t)C::A_TX);
-                    const uint32_t dst = a_base + slot * C::A_SLOT;
-                    tma_load_4d(dst, &tmap_in, a_full(slot), c * C::KC, x0, y0, 0);
-                    if constexpr (F8) {
-                        tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in8, a_full(slot), c * C::KC, x0, y0, 0);                     // xh8
-                        tma_load_4d(dst + C::A_PLANE_PAD + C::A8_PLANE_PAD, &tmap_in8, a_full(slot), c * C::KC, x0, y0, 1);   // xl8
-                    } else {
-                        tma_load_4d(dst + C::A_PLANE_PAD, &tmap_in, a_full(slot), c * C::KC, x0, y0, 1);
-                    }
+                    tma_load_4d(a_base + slot * C::A_SLOT, &tmap_in, a_full(slot), 0, c, x0, y0);
                 }
             }
             if (prof_on && lane == 0) prof[PROF_APROD_WAIT] += w_a;
@@ -118,8 +106,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
         constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::A_LAYOUT) >> 32);
         constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::B_LAYOUT) >> 32);
         constexpr uint32_t LO_FIXED = 1u << 16;                      // LBO field = 1
-        // e4m3 operands (F8): activation planes with ROWB8-byte rows, weight blocks with 32-byte rows (SWIZZLE_32B)
-        constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(HALO * C::ROWB8, C::A8_LAYOUT) >> 32);
+        // e4m3 weight blocks: 32-byte rows (SWIZZLE_32B); the e4m3 activation slices are quarters of the same 128-byte records
         constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
         auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
         uint32_t a_it = 0, stage = 0, phase = 0, n = 0;
@@ -156,39 +143,23 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                 const uint32_t slot = a_it & 1u;
                 mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
                 tc_fence_after();
-                // descriptor low words (address >> 4) of this issuer's window into the hi / lo activation planes
+                // descriptor low word (address >> 4) of this issuer's window into the staged records; a record's quarters:
+                // +0 / +2 the fp16 K steps, +4 xh8 (f16x3: lo step 0), +6 xl8 (f16x3: lo step 1)   [16-byte units]
                 const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
-                const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
-                // F8: windows into the xh8 / xl8 planes of this slot
-                const uint32_t a8h0 = ((((a_base + slot * C::A_SLOT + C::A_PLANE_PAD) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB8 >> 4);
-                const uint32_t a8l0 = a8h0 + (C::A8_PLANE_PAD >> 4);
                 uint32_t tap_off = 0;                 // ((ky*HALO + kx) * ROWB) >> 4
-                uint32_t tap_off8 = 0;                // ((ky*HALO + kx) * ROWB8) >> 4
                 for (int t = 0; t < 9; t++) {
                     const uint32_t first = (c | t) != 0 ? 1u : 0u;
-#pragma unroll
-                    for (int kb = 0; kb < C::KBLOCKS; kb++) {
-                        const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;   // 32 channels = 64 B = 4 units
-                        const uint32_t acc0 = kb ? 1u : first;
+                    {
+                        const uint32_t ah = ah0 + tap_off, al = ah + 4u;
+                        const uint32_t acc0 = first;
                         uint32_t b0;
                         if constexpr (C::MERGE) {
                             // one stage = [wh fp16 | wh8 | wl8]: main product (two K=16 steps) + both e4m3 corrections (K=32 each)
                             acquire_b(b0);
                             umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
                             umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
-                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u);
-                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u);
-                            release_b();
-                        } else if constexpr (F8) {
-                            // ---- stage 1: wh (fp16): the main product xh*wh, two K=16 steps ----
-                            acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
-                            release_b();
-                            // ---- stage 2: [wh8 | wl8] (e4m3): corrections xl8*wh8 and xh8*wl8, one K=32 step each ----
-                            acquire_b(b0);
-                            umma_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0), idesc_c, 1u);
-                            umma_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (COUT * 32u >> 4)), idesc_c, 1u);
+                            umma_f8(dj, desc(A_HI32, ah + 6u), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u);    // xl8 * wh8
+                            umma_f8(dj, desc(A_HI32, ah + 4u), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u);    // xh8 * wl8
                             release_b();
                         } else if constexpr (C::STACK) {
                             // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
@@ -215,7 +186,6 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     }
                     // next tap: kx+1, or the next halo row
                     tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
-                    tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
                 }
                 umma_commit_one(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
             }
@@ -280,7 +250,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                     act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
                 }
                 if constexpr (!FUSE) {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);   // (row coordinates of the store maps are window-relative, never negative)
+                    epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);   // (row coordinates of the store map are window-relative, never negative)
                 } else {
                     // last layer folded in: accumulate the nine tap dot products over these 32 channels
 #pragma unroll

@@ -16,22 +16,22 @@
 //   * both CTAs' epilogue warps arrive (remotely) on the leader's accumulator-empty barriers.
 template <int CIN, int COUT, bool FUSE, bool F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_in8,
-                       const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
-                       const __grid_constant__ CUtensorMap tmap_out8, const TcParams p) {
+tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                       const __grid_constant__ CUtensorMap tmap_out, const TcParams p) {
     using C = PairCfg<CIN, COUT, FUSE, F8>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base;
-    const uint32_t b_base = a_base + C::A_SLOTS * C::A_SLOT;
+    constexpr int NAS = C::A_SLOTS;
+    const uint32_t b_base = a_base + NAS * C::A_SLOT;
     const uint32_t bar_base = b_base + C::NBP * C::B_HALF;
     auto a_full = [&](int i) { return bar_base + 8u * (uint32_t)i; };
-    auto a_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 + i); };
-    auto acc_full = [&](int i) { return bar_base + 8u * (uint32_t)(4 + i); };
-    auto acc_empty = [&](int i) { return bar_base + 8u * (uint32_t)(6 + i); };
-    auto b_full = [&](int i) { return bar_base + 8u * (uint32_t)(8 + i); };
-    auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(8 + C::NBP + i); };
-    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(8 + 2 * C::NBP);
+    auto a_empty = [&](int i) { return bar_base + 8u * (uint32_t)(NAS + i); };
+    auto acc_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * NAS + i); };
+    auto acc_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * NAS + 2 + i); };
+    auto b_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * NAS + 4 + i); };
+    auto b_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * NAS + 4 + C::NBP + i); };
+    const uint32_t tmem_slot = bar_base + 8u * (uint32_t)(2 * NAS + 4 + 2 * C::NBP);
     uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     // warp index through a shuffle: ptxas then knows it is warp-uniform, and with it the role branch, the M-tile index and
@@ -46,9 +46,11 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     const int tiles_y = (p.out_rows + REGION - 1) / REGION;   // tile-sets tile the store window [out_y0, out_y0 + out_rows)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < NAS; i++) {
             mbar_init(a_full(i), 1);        // leader's: its A producer's arrive.expect_tx covers the bytes of BOTH CTAs
             mbar_init(a_empty(i), 2);       // one multicast tcgen05.commit per issuer
+        }
+        for (int i = 0; i < 2; i++) {
             mbar_init(acc_full(i), 2);
             mbar_init(acc_empty(i), 16);    // leader's: 8 local + 8 remote epilogue warps
         }
@@ -62,11 +64,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_in);
         prefetch_tmap(&tmap_w);
-        if constexpr (F8) prefetch_tmap(&tmap_in8);
-        if constexpr (!FUSE) {
-            prefetch_tmap(&tmap_out);
-            if constexpr (F8) prefetch_tmap(&tmap_out8);
-        }
+        if constexpr (!FUSE) prefetch_tmap(&tmap_out);
     }
     cluster_sync_all();                     // both CTAs' barriers exist before anything can signal them
     if (warp == 2) {
@@ -94,18 +92,10 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                 region_of(q, tx, ty);
                 const int x0 = tx * REGION - 1, y0 = p.out_y0 + ty * REGION - 1;
                 for (int c = 0; c < C::NCHUNK; c++, it++) {
-                    const uint32_t slot = it & 1u, round = it >> 1;
+                    const uint32_t slot = it % (uint32_t)NAS, round = it / (uint32_t)NAS;
                     mbar_wait_prof(a_empty(slot), (round & 1u) ^ 1u, prof_on, w_a);
                     if (is_leader) mbar_arrive_expect_tx(a_full(slot), 2u * (uint32_t)C::A_TX);
-                    const uint32_t bar = mapa_rank(a_full(slot), 0);
-                    const uint32_t dst = a_base + slot * C::A_SLOT;
-                    tma_load_4d_2cta(dst, &tmap_in, bar, c * C::KC, x0, y0, 0);
-                    if constexpr (F8) {
-                        tma_load_4d_2cta(dst + C::A_PLANE_PAD, &tmap_in8, bar, c * C::KC, x0, y0, 0);
-                        tma_load_4d_2cta(dst + C::A_PLANE_PAD + C::A8_PLANE_PAD, &tmap_in8, bar, c * C::KC, x0, y0, 1);
-                    } else {
-                        tma_load_4d_2cta(dst + C::A_PLANE_PAD, &tmap_in, bar, c * C::KC, x0, y0, 1);
-                    }
+                    tma_load_4d_2cta(a_base + slot * C::A_SLOT, &tmap_in, mapa_rank(a_full(slot), 0), 0, c, x0, y0);   // 324 records of this 32-channel block
                 }
             }
             if (prof_on && lane == 0) prof[PROF_APROD_WAIT] += w_a;
@@ -117,7 +107,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
         {
             uint32_t stage = 0, phase = 0;
             unsigned long long w_b = 0;
-            constexpr int N_STEPS = C::NCHUNK * 9 * C::KBLOCKS;                // one stage per (chunk, tap, 32-channel block)
+            constexpr int N_STEPS = C::NCHUNK * 9;                             // one stage per (32-channel block, tap)
             for (int q = pair_id; q < n_pair_sets; q += n_pairs_cl) {
                 for (int blk = 0; blk < N_STEPS; blk++) {
                     mbar_wait_prof(b_empty(stage), phase ^ 1u, prof_on, w_b);
@@ -151,7 +141,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
             constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(A_SBO, C::A_LAYOUT) >> 32);
             constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(B_SBO, C::B_LAYOUT) >> 32);
             constexpr uint32_t LO_FIXED = 1u << 16;
-            constexpr uint32_t A8_HI32 = (uint32_t)(make_desc_const(HALO * C::ROWB8, C::A8_LAYOUT) >> 32);
             constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
             auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
             uint32_t a_it = 0, stage = 0, phase = 0, n = 0, b_ready = 0;
@@ -175,27 +164,25 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                 tc_fence_after();
                 const uint32_t dj = tmem_base + (set * 2u + jt) * C::TILE_COLS;
                 for (int c = 0; c < C::NCHUNK; c++, a_it++) {
-                    const uint32_t slot = a_it & 1u;
-                    mbar_wait_prof(a_full(slot), (a_it >> 1) & 1u, prof_on, w_af);
+                    const uint32_t slot = a_it % (uint32_t)NAS;
+                    mbar_wait_prof(a_full(slot), (a_it / (uint32_t)NAS) & 1u, prof_on, w_af);
                     tc_fence_after();
+                    // this issuer's window into the staged records; a record's quarters: +0 / +2 the fp16 K steps, +4 xh8 (f16x3: lo
+                    // step 0), +6 xl8 (f16x3: lo step 1)   [16-byte units]
                     const uint32_t ah0 = ((((a_base + slot * C::A_SLOT) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB >> 4);
-                    const uint32_t al0 = ah0 + (C::A_PLANE_PAD >> 4);
-                    const uint32_t a8h0 = ((((a_base + slot * C::A_SLOT + C::A_PLANE_PAD) >> 4) & 0x3FFFu) | LO_FIXED) + jt * (8u * C::ROWB8 >> 4);
-                    const uint32_t a8l0 = a8h0 + (C::A8_PLANE_PAD >> 4);
-                    uint32_t tap_off = 0, tap_off8 = 0;
+                    uint32_t tap_off = 0;
                     for (int t = 0; t < 9; t++) {
                         const uint32_t first = (c | t) != 0 ? 1u : 0u;
-#pragma unroll
-                        for (int kb = 0; kb < C::KBLOCKS; kb++) {
-                            const uint32_t ah = ah0 + tap_off + 4u * kb, al = al0 + tap_off + 4u * kb;
-                            const uint32_t acc0 = kb ? 1u : first;
+                        {
+                            const uint32_t ah = ah0 + tap_off, al = ah + 4u;
+                            const uint32_t acc0 = first;
                             uint32_t b0;
                             acquire_b(b0);                  // one stage per 32-channel step: this CTA's rows of both blocks
                             if constexpr (F8) {
                                 umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
                                 umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
-                                umma2_f8(dj, desc(A8_HI32, a8l0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u);
-                                umma2_f8(dj, desc(A8_HI32, a8h0 + tap_off8 + 2u * kb), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u);
+                                umma2_f8(dj, desc(A_HI32, ah + 6u), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u);    // xl8 * wh8
+                                umma2_f8(dj, desc(A_HI32, ah + 4u), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u);    // xh8 * wl8
                             } else {
                                 umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
                                 umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
@@ -207,7 +194,6 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                             release_b();
                         }
                         tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
-                        tap_off8 += (t % 3 == 2) ? ((HALO - 2) * C::ROWB8 >> 4) : (C::ROWB8 >> 4);
                     }
                     umma2_commit_one(a_empty(slot));
                 }
@@ -274,7 +260,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                         }
                     }
                 } else {
-                    epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4, cb);
+                    epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q4, cb);
                 }
             }
             if constexpr (FUSE) {

@@ -31,7 +31,7 @@ constexpr int STRIP_BOXW = STRIP_W + 2;  // staged pixels per row
 
 // Input frames are RECORD frames (tc_epilogue.cuh): one TMA box {128 B, 1 block, 130 px, 1 row} per (row, 32-channel block)
 // lands as 130 rows of 128 B in the SWIZZLE_128B pattern; the fp16 K steps, the xh8 and the xl8 slices of a pixel are the
-// 32-byte quarters of its row.  OUT_REC selects the output frame's layout (RECORD when the next layer is a strip layer).
+// 32-byte quarters of its row.  The output frame is a RECORD frame as well.
 template <int CIN, int COUT, bool F8>
 struct StripCfg {
     static_assert((CIN == 32 || CIN == 64) && (COUT == 32 || COUT == 64), "strip kernel: narrow layers only");
@@ -73,10 +73,9 @@ struct StripParams {
                                 // 64 = the epilogue does not zero the blocks
 };
 
-template <int CIN, int COUT, bool F8, bool OUT_REC>
+template <int CIN, int COUT, bool F8>
 __global__ void __launch_bounds__(StripCfg<CIN, COUT, F8>::THREADS, 1)
-tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out,
-                        const __grid_constant__ CUtensorMap tmap_out8, const StripParams p) {
+tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_out, const StripParams p) {
     using C = StripCfg<CIN, COUT, F8>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -112,7 +111,6 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_in);
         prefetch_tmap(&tmap_out);
-        if constexpr (F8 && !OUT_REC) prefetch_tmap(&tmap_out8);
     }
     if (warp == 2) {
         tmem_alloc(tmem_slot, 512);
@@ -313,10 +311,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
                     const int gy = y0 + i - p.out_y0;
-                    if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) {
-                        if constexpr (OUT_REC) epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, gx0, gy, cb);
-                        else epilogue_store32<COUT, F8>(act, &tmap_out, &tmap_out8, p.dbg, stg, lane, gx0, gy, cb);
-                    }
+                    if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, gx0, gy, cb);
                 }
                 if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
             }
