@@ -201,8 +201,10 @@ int launch_layer_tc(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int li, cons
 // n_tiles > 1 (tcgen05 engine with the fused last layer only): src holds n_tiles padded planes of pw x ph stacked vertically; the
 // layers run ONCE on the (n_tiles * ph)-row frame -- the seams pollute only the rings that are cropped anyway -- and tile t's
 // interior goes to dst + t * (ph - 2n) * dst_stride.
+// direct (tcgen05 engine, one plane): the first layer reads the UNPADDED plane it describes and folds the replicate padding into
+// its loads; src / src_stride are then unused.
 int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const float *src, long src_stride, int pw,
-              int ph, float *dst, long dst_stride, int n_tiles = 1) {
+              int ph, float *dst, long dst_stride, int n_tiles = 1, const tc::FirstSource *direct = nullptr) {
     const int n = (int)m->layers.size();
     if (pw - 2 * n < 1 || ph - 2 * n < 1) return fail(W2X_ERR_ARG, "plane smaller than the model's receptive ring");
     const int tile_ph = ph;
@@ -248,7 +250,8 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
         const Layer &L = m->layers[0];
         logf(ctx, "Iteration #%d...", 1);
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(src, src_stride, pw, ph, L.w.data(), dm->b_host[0].data(), L.n_out, cur, ctx->stream, f8));
+        const tc::FirstSource padded{src, src_stride, pw, ph, 0, 0, 0, 0};
+        CU_CHECK(tc::launch_first(direct ? *direct : padded, pw, ph, L.w.data(), dm->b_host[0].data(), L.n_out, cur, ctx->stream, f8));
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;
     }
@@ -283,8 +286,10 @@ int run_basic(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const 
 
 // Whole plane (or row band) already available as a padded plane: cut it into horizontal bands that
 // respect the scratch limit, each band re-reads n rows of context above and below.
+// direct_in != nullptr (tcgen05 engine): no padded plane exists; the first layer reads d_in (rows_above / rows_below real rows
+// beyond the plane) with the padding folded into its loads.
 int run_padded_plane(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine, const float *padp, int w, int h,
-                     float *dst, long dst_stride) {
+                     float *dst, long dst_stride, const float *direct_in = nullptr, long in_stride = 0, int rows_above = 0, int rows_below = 0) {
     const int n = (int)m->layers.size();
     const int pw = w + 2 * n;
     int maxc = 1;
@@ -295,8 +300,13 @@ int run_padded_plane(w2x_ctx *ctx, const w2x_model *m, DevModel *dm, int engine,
     int band = (int)std::min<long>(h, max_rows);
     for (int y0 = 0; y0 < h; y0 += band) {
         const int bh = std::min(band, h - y0);
-        int rc = run_basic(ctx, m, dm, engine, padp + (long)y0 * pw, pw, pw, bh + 2 * n, dst + (long)y0 * dst_stride,
-                           dst_stride);
+        int rc;
+        if (direct_in) {
+            const tc::FirstSource fs{direct_in + (long)y0 * in_stride, in_stride, w, bh, n, n, std::min(n, y0 + rows_above), std::min(n, h - y0 - bh + rows_below)};
+            rc = run_basic(ctx, m, dm, engine, nullptr, 0, pw, bh + 2 * n, dst + (long)y0 * dst_stride, dst_stride, 1, &fs);
+        } else {
+            rc = run_basic(ctx, m, dm, engine, padp + (long)y0 * pw, pw, pw, bh + 2 * n, dst + (long)y0 * dst_stride, dst_stride);
+        }
         if (rc) return rc;
     }
     return W2X_OK;
@@ -323,14 +333,20 @@ int convert_device(w2x_ctx *ctx, const w2x_model *m, const float *d_in, int w, i
     if (rc) return rc;
     const int n = (int)m->layers.size();
     const int pw = w + 2 * n, ph = h + 2 * n;
+    const long ostride = (long)(out_stride_bytes / 4);
+    const bool split = block_splitting && w2x_requires_splitting(w, h);
+    if (engine == W2X_ENGINE_TC && !(split && ctx->walk == W2X_WALK_BLOCKS)) {
+        // cv::copyMakeBorder (src/convertRoutine.cpp:35, :96) is folded into the first layer's loads: no padded copy of the plane
+        if (split && !ctx->log_muted) emit_reference_progress(ctx, w, h, n, true);
+        LogMute mute(ctx, split);
+        return run_padded_plane(ctx, m, dm, engine, nullptr, w, h, d_out, ostride, d_in, (long)(in_stride_bytes / 4), rows_above, rows_below);
+    }
     rc = ensure(reinterpret_cast<void **>(&ctx->pad_buf), &ctx->pad_bytes, (size_t)pw * ph * sizeof(float));
     if (rc) return rc;
     // cv::copyMakeBorder(in, temp, n, n, n, n, BORDER_REPLICATE)   (src/convertRoutine.cpp:35, :96)
     CU_CHECK(launch_pad_replicate(d_in, w, h, (long)(in_stride_bytes / 4), n, std::min(rows_above, n),
                                   std::min(rows_below, n), ctx->pad_buf, ctx->stream));
     ctx->launches++;
-    const long ostride = (long)(out_stride_bytes / 4);
-    const bool split = block_splitting && w2x_requires_splitting(w, h);
     if (split && ctx->walk == W2X_WALK_BLOCKS) {
         // the literal block walk of convertWithModelsBlockSplit (src/convertRoutine.cpp:114-165)
         const Config &cfg = config();

@@ -186,7 +186,8 @@ int w2x_band_step(w2x_band *band, int step) {
     const int y0 = band->up ? 1 : 0, rows = band->hf - y0 - (band->down ? 1 : 0);
     if (step == 0) {
         LayerTimer t(ctx, 0);
-        CU_CHECK(tc::launch_first(band->pad, band->pw, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8, y0, rows));
+        const tc::FirstSource fsrc{band->pad, band->pw, band->pw, band->hf, 0, 0, 0, 0};       // the session's padded input frame (halo rows come from the neighbours)
+        CU_CHECK(tc::launch_first(fsrc, band->pw, band->hf, L.w.data(), dm->b_host[0].data(), L.n_out, band->act[0], ctx->stream, f8, y0, rows));
         band->cur = 0;
         note_kernel(ctx, 0, "first_1xN");
         ctx->launches++;

@@ -49,11 +49,18 @@ size_t layer_smem_bytes(int cin, int cout);
 // One-time per process: raise the dynamic shared memory limit of every instantiation.
 cudaError_t init_kernels();
 
-// First layer (Cin = 1): fp32 plane (ROI with stride) -> NHWC hi/lo frame of the same size (pw x ph),
-// same-size 3x3 correlation with the ROI border replicated (src/modelHandler.cpp:141-142).
+// First layer (Cin = 1): same-size 3x3 correlation with BORDER_REPLICATE (src/modelHandler.cpp:141-142) on the frame of pw x ph
+// whose pixel (fy, fx) is the source plane's pixel (clamp(fy - pad_top), clamp(fx - pad_x)) -- i.e. cv::copyMakeBorder
+// (src/convertRoutine.cpp:35,96) is folded into the loads; pad_x = pad_top = 0 with w x h = pw x ph reads an already padded ROI.
+// rows_above / rows_below: real rows readable beyond the plane (row bands).  -> RECORD frame.
 // `wgt` ([C][9]) and `bias` ((float)bias) are HOST pointers: they travel as kernel parameters.
-cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt /*[C][9]*/,
-                         const float *bias, int cout, __half *out, cudaStream_t s, int f8 = 0, int out_y0 = 0, int out_rows = -1);
+struct FirstSource {
+    const float *in;
+    long stride_floats;
+    int w, h, pad_x, pad_top, rows_above, rows_below;
+};
+cudaError_t launch_first(const FirstSource &src, int pw, int ph, const float *wgt /*[C][9]*/, const float *bias, int cout, __half *out,
+                         cudaStream_t s, int f8 = 0, int out_y0 = 0, int out_rows = -1);
 // tcgen05 layer: in/out NHWC frames (pw x ph); the tensor maps are built inside.
 // `bias` is a HOST pointer to the layer's (float)bias values (they travel as kernel parameters).
 // f8 = 0: "f16x3" frames [hi][lo], wpack = TcPack::bytes, wstrip = TcPack::strip;

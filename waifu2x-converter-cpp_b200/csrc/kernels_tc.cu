@@ -254,36 +254,31 @@ cudaError_t launch_tc_layer(const __half *in, const void *wpack, const void *wst
 }
 
 template <int COUT>
-static cudaError_t launch_first_c(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias, __half *out,
-                                  cudaStream_t s, int f8, int out_y0, int out_rows) {
+static cudaError_t launch_first_c(const FirstSource &src, int pw, int ph, const float *wgt, const float *bias, __half *out, cudaStream_t s, int f8,
+                                  int out_y0, int out_rows) {
     static_assert(FIRST_TILE_BYTES + 1024 <= 48 * 1024, "the first layer's staging tile stays under the default dynamic shared memory limit");
-    // (under 48 KB no opt-in is required; the attribute is set anyway, once per process, as every other kernel of the engine does)
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(first_layer_kernel<COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(first_layer_kernel<COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_TILE_BYTES + 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
+    FirstParams<COUT> prm;                                    // HOST pointers -> kernel parameters; ACT_SCALE folded in (exact: a power of two)
+    for (int p = 0; p < COUT / 2; p++) {
+        for (int k = 0; k < 9; k++) prm.w[p * 9 + k] = make_float2(wgt[(2 * p) * 9 + k] * ACT_SCALE, wgt[(2 * p + 1) * 9 + k] * ACT_SCALE);
+        prm.b[p] = make_float2(bias[2 * p] * ACT_SCALE, bias[2 * p + 1] * ACT_SCALE);
     }
-    FirstParams<COUT> prm;
-    for (int i = 0; i < COUT * 9; i++) prm.w[i] = wgt[i];     // HOST pointers
-    for (int i = 0; i < COUT; i++) prm.b[i] = bias[i];
+    FirstSrc fs{src.in, src.stride_floats, src.w, src.h, src.pad_x, src.pad_top, src.rows_above, src.rows_below};
     CUtensorMap omap;
     dim3 grid((pw + 31) / 32, (out_rows + 7) / 8);   // blocks tile the store window
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
     if (make_rec_map(&omap, out, COUT, pw, ph, 32, 8, out_y0, out_rows)) return cudaErrorInvalidValue;
-    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omap, prm);
-    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(in, in_stride_floats, pw, ph, out_y0, omap, prm);
+    if (f8) first_layer_kernel<COUT, true><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(fs, pw, ph, out_y0, omap, prm);
+    else first_layer_kernel<COUT, false><<<grid, 256, FIRST_TILE_BYTES + 1024, s>>>(fs, pw, ph, out_y0, omap, prm);
     return cudaGetLastError();
 }
 
-cudaError_t launch_first(const float *in, long in_stride_floats, int pw, int ph, const float *wgt, const float *bias,
-                         int cout, __half *out, cudaStream_t s, int f8, int out_y0, int out_rows) {
+cudaError_t launch_first(const FirstSource &src, int pw, int ph, const float *wgt, const float *bias, int cout, __half *out, cudaStream_t s, int f8,
+                         int out_y0, int out_rows) {
     if (out_rows < 0) { out_y0 = 0; out_rows = ph; }
     switch (cout) {
-        case 32: return launch_first_c<32>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
-        case 64: return launch_first_c<64>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
-        case 128: return launch_first_c<128>(in, in_stride_floats, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 32: return launch_first_c<32>(src, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 64: return launch_first_c<64>(src, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
+        case 128: return launch_first_c<128>(src, pw, ph, wgt, bias, out, s, f8, out_y0, out_rows);
         default: return cudaErrorInvalidValue;
     }
 }

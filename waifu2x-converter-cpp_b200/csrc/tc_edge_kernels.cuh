@@ -6,24 +6,51 @@
 // ================================================================================================
 // First layer (Cin = 1), last layer (Cout = 1), layout converters -- CUDA-core, HBM-bound
 // ================================================================================================
-// First layer: Model::filterWorker with nInputPlanes = 1 on the (already replicate-padded) plane;
-// writes the NHWC frame the tcgen05 layers consume.  One thread per pixel, 32 x 8 pixels per block.
-//   * weights and biases travel as kernel parameters: the 9*COUT FFMAs per pixel take them straight from the constant
-//     bank (as shared-memory broadcasts they were one LDS per FFMA -- the LSU, not the FP32 pipe, bounded the kernel);
-//   * 32 channels at a time are converted into a swizzled shared-memory image of the block's 8 x 32 pixels and leave
-//     through TMA stores (the same path as the tcgen05 epilogue): a thread's own 16-byte stores sat at a 64-byte stride.
+// First layer: Model::filterWorker with nInputPlanes = 1 on the replicate-padded plane; writes the RECORD frame the tcgen05
+// layers consume.  One thread per pixel, 32 x 8 pixels per block.
+//   * the plane is NOT padded beforehand: `in` is the caller's plane (w x h, possibly a row band with real rows above / below)
+//     and frame pixel (fy, fx) reads in[clamp(fy - pad_y), clamp(fx - pad_x)] -- cv::copyMakeBorder(BORDER_REPLICATE)
+//     (src/convertRoutine.cpp:35,96) folded into the loads;
+//   * two output channels per instruction: packed fp32 (FFMA2, sm_100) with the weight PAIRS straight from the constant bank
+//     (kernel parameters -> uniform registers) and the pixel broadcast to both halves; every lane's arithmetic is the
+//     reference's: per tap an fma chain, + (float)bias, leaky = max(v, 0.1f v) (= min(v,0)*0.1f + max(v,0) bit for bit).
+//     ACT_SCALE (16, a power of two) is folded into the weights and biases on the host: exact;
+//   * 32 channels at a time are converted into a swizzled shared-memory image of the block's 8 x 32 records
+//     ([256 px][128 B], SWIZZLE_128B) and leave as ONE TMA box {128 B, 1, 32 px, 8 rows}.
 template <int COUT>
 struct FirstParams {
-    float w[COUT * 9];    // [COUT][3][3]
-    float b[COUT];        // (float)bias
+    float2 w[(COUT / 2) * 9];    // [channel pair][tap] = (w[2p][tap], w[2p+1][tap]) * ACT_SCALE
+    float2 b[COUT / 2];          // ((float)bias[2p], (float)bias[2p+1]) * ACT_SCALE
 };
-constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [fp16 plane 16 KB | lo plane 16 KB]  or  [xh 16 KB | xh8 8 KB | xl8 8 KB]
+constexpr int FIRST_TILE_BYTES = 32 * 1024;   // [256 px][128 B]
 
-// The output is a RECORD frame (tc_epilogue.cuh): the staged image is [256 px][128 B] per 32 channels, SWIZZLE_128B, one box
-// {128 B, 1, 32 px, 8 rows} per 32 channels.
+__device__ __forceinline__ float2 f32x2_fma(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 f32x2_mul(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 f32x2_add(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&r);
+}
+
+// in: plane of w x h (row stride in_stride), readable at rows [-rows_above, h + rows_below); frame = (w + 2 pad_x) x (h + pad_top + pad_bottom)
+struct FirstSrc {
+    const float *in;
+    long in_stride;
+    int w, h, pad_x, pad_top, rows_above, rows_below;
+};
+
 template <int COUT, bool F8>
 __global__ void __launch_bounds__(256, 4)
-first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph, int out_y0, const __grid_constant__ CUtensorMap tmap_out,
+first_layer_kernel(const FirstSrc src, int pw, int ph, int out_y0, const __grid_constant__ CUtensorMap tmap_out,
                    const __grid_constant__ FirstParams<COUT> prm) {
     extern __shared__ uint8_t first_smem[];
     const uint32_t tile = (smem_u32(first_smem) + 1023u) & ~1023u;
@@ -34,8 +61,11 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
-            int gy = min(max(y + ky - 1, 0), ph - 1), gx = min(max(x + kx - 1, 0), pw - 1);
-            v[ky * 3 + kx] = __ldg(in + (long)gy * in_stride + gx);
+            // same-size correlation on the padded plane with BORDER_REPLICATE (src/modelHandler.cpp:141-142), the padded plane itself
+            // being the replicate-padded input: clamp to the frame, then to the rows / columns that really exist
+            const int fy = min(max(y + ky - 1, 0), ph - 1), fx = min(max(x + kx - 1, 0), pw - 1);
+            const int sy = min(max(fy - src.pad_top, -src.rows_above), src.h - 1 + src.rows_below), sx = min(max(fx - src.pad_x, 0), src.w - 1);
+            v[ky * 3 + kx] = __ldg(src.in + (long)sy * src.in_stride + sx);
         }
     const uint32_t r = (uint32_t)threadIdx.x;                            // pixel index inside the block = row of the staged image
     const uint32_t sw128 = r & 7u;
@@ -50,27 +80,27 @@ first_layer_kernel(const float *__restrict__ in, long in_stride, int pw, int ph,
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                float a[2];
+                const int pr = cb * 16 + c8 * 4 + i;                     // channel pair
+                const float2 *w = prm.w + pr * 9;
+                float2 t = f32x2_mul(w[0], make_float2(v[0], v[0]));
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const float *w = prm.w + (cb * 32 + c8 * 8 + 2 * i + e) * 9;
-                    float t = w[0] * v[0];
-#pragma unroll
-                    for (int k = 1; k < 9; k++) t = fmaf(w[k], v[k], t);
-                    float rr = (0.f + t) + prm.b[cb * 32 + c8 * 8 + 2 * i + e];
-                    a[e] = (fminf(rr, 0.f) * 0.1f + fmaxf(rr, 0.f)) * ACT_SCALE;
-                }
-                __half2 h = __floats2half2_rn(a[0], a[1]);
+                for (int k = 1; k < 9; k++) t = f32x2_fma(w[k], make_float2(v[k], v[k]), t);
+                const float2 rr = f32x2_add(t, prm.b[pr]);               // (0 + t) + (float)bias
+                const float2 sc = f32x2_mul(rr, make_float2(0.1f, 0.1f));
+                const float a0 = fmaxf(rr.x, sc.x), a1 = fmaxf(rr.y, sc.y);     // leaky-ReLU 0.1, already x ACT_SCALE
+                __half2 h = __floats2half2_rn(a0, a1);
                 float2 hf = __half22float2(h);
                 hi[i] = *reinterpret_cast<uint32_t *>(&h);
                 if constexpr (F8) {
                     constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
-                    const uint32_t h8 = __nv_cvt_float2_to_fp8x2(make_float2(hf.x * kDown, hf.y * kDown), __NV_SATFINITE, __NV_E4M3);
-                    const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((a[0] - hf.x) * kUp, (a[1] - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+                    const __half2 hd = __hmul2(h, __float2half2_rn(kDown));        // exact (power of two)
+                    const uint32_t h8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hd), __NV_SATFINITE, __NV_E4M3);
+                    const float2 d = f32x2_mul(f32x2_add(make_float2(a0, a1), make_float2(-hf.x, -hf.y)), make_float2(kUp, kUp));
+                    const uint32_t l8 = __nv_cvt_float2_to_fp8x2(d, __NV_SATFINITE, __NV_E4M3);
                     if (i & 1) { lo[i >> 1] |= h8 << 16; lo[2 + (i >> 1)] |= l8 << 16; }     // lo[0..1] = xh8 (8 bytes), lo[2..3] = xl8
                     else { lo[i >> 1] = h8; lo[2 + (i >> 1)] = l8; }
                 } else {
-                    __half2 l = __floats2half2_rn(a[0] - hf.x, a[1] - hf.y);
+                    __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
                     lo[i] = *reinterpret_cast<uint32_t *>(&l);
                 }
             }

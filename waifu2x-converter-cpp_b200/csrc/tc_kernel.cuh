@@ -214,71 +214,8 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
             const long long t_work = prof_on ? clock64() : 0;
             tc_fence_after();
             const uint32_t tcol = tmem_base + ((q * 32u) << 16) + (set * 2u + (uint32_t)j) * C::TILE_COLS;
-            const int fy = p.out_y0 + ty * REGION + oy, fx = tx * REGION + 8 * j + ox;
-            const bool inside = fy < p.Hp && fx < p.Wp && fy >= p.out_y0 && fy < p.out_y0 + p.out_rows;
-            float pt[9];                                   // FUSE: nine per-tap dot products of this pixel
-#pragma unroll
-            for (int t = 0; t < 9; t++) pt[t] = 0.f;
-            uint32_t r[32];
-            if constexpr (!C::STACK) tmem_ld32(tcol, r);
-#pragma unroll
-            for (int cb = 0; cb < COUT / 32; cb++) {
-                // ---- 32 output channels of this pixel: accumulator -> scale, bias, leaky-ReLU ----
-                float act[32];
-                if constexpr (C::STACK) {
-                    uint32_t r2[32];
-                    tmem_ld32(tcol + (uint32_t)cb * 32u, r);
-                    tmem_ld32(tcol + (uint32_t)(COUT + cb * 32), r2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-                } else {
-                    tmem_ld_wait_dep(r);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) act[i] = __uint_as_float(r[i]);
-                    // the next 32 columns travel from TMEM while this block is converted and stored
-                    if (cb + 1 < COUT / 32) tmem_ld32(tcol + (uint32_t)(cb + 1) * 32u, r);
-                    else {   // the accumulators are in registers: hand the TMEM columns back before the last block's conversion
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty(set));
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float v = fmaf(act[i], p.out_scale, p.bias[cb * 32 + i]);     // = ACT_SCALE * (conv + bias)
-                    act[i] = fmaxf(v, 0.1f * v);                                         // leaky 0.1: min(v,0)*0.1 + max(v,0)
-                }
-                if constexpr (!FUSE) {
-                    epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q, cb);   // (row coordinates of the store map are window-relative, never negative)
-                } else {
-                    // last layer folded in: accumulate the nine tap dot products over these 32 channels
-#pragma unroll
-                    for (int g = 0; g < 8; g++) {
-#pragma unroll
-                        for (int t = 0; t < 9; t++) {
-                            const float *w = p.last_w + t * COUT + cb * 32 + 4 * g;   // compile-time offsets into the parameter bank
-                            pt[t] = fmaf(act[4 * g + 0], w[0], pt[t]);
-                            pt[t] = fmaf(act[4 * g + 1], w[1], pt[t]);
-                            pt[t] = fmaf(act[4 * g + 2], w[2], pt[t]);
-                            pt[t] = fmaf(act[4 * g + 3], w[3], pt[t]);
-                        }
-                    }
-                }
-            }
-            if constexpr (FUSE) {
-                if (inside) {
-                    float4 *dst = reinterpret_cast<float4 *>(p.partial + ((size_t)fy * p.Wp + fx) * 12);
-                    dst[0] = make_float4(pt[0], pt[1], pt[2], pt[3]);
-                    dst[1] = make_float4(pt[4], pt[5], pt[6], pt[7]);
-                    dst[2] = make_float4(pt[8], 0.f, 0.f, 0.f);
-                }
-            }
-            if constexpr (C::STACK) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty(set));
-            }
+            tile_epilogue<COUT, FUSE, F8, C::STACK>(p, &tmap_out, tcol, stg, lane, tx * REGION + 8 * j, ty * REGION + 4 * (int)q,
+                                                    tx * REGION + 8 * j + ox, p.out_y0 + ty * REGION + oy, [&] { mbar_arrive(acc_empty(set)); });
             if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
         }
         if constexpr (!FUSE) bulk_wait_all();    // this warp's TMA stores are complete before the CTA may exit
