@@ -117,7 +117,7 @@ def reference_jobs():
 _CPU_REF = {}
 
 
-def cpu_reference_block(n_job, repeats=1):
+def cpu_reference_block(n_job, repeats=1, want=None):
     """One 512x512 block (498x498 output pixels) of the workload plane through the reference's CPU path.
     Returns (seconds per block, kind, description).  Preference order:
       1. oracle/_ref/libw2x_reference.so -- the reference's OWN src/modelHandler.cpp + src/convertRoutine.cpp compiled against
@@ -127,7 +127,8 @@ def cpu_reference_block(n_job, repeats=1):
     W2X_BENCH_CPU=cv2|oracle forces one of the fallbacks."""
     from oracle import oracle
     x = oracle.seeded_plane(4096, 4096, 1, "uniform")[:498, :498]
-    want = os.environ.get("W2X_BENCH_CPU", "")
+    if want is None:
+        want = os.environ.get("W2X_BENCH_CPU", "")
     om = oracle.OracleModel.golden(MODEL)
     fn = kind = desc = None
     if want in ("", "reference"):
@@ -543,6 +544,12 @@ def run_ours(args):
                 desc += f" (preferred baseline failed: {type(e).__name__}: {e})"
             cpu = {"value": 498 * 498 / s / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind,
                    "sample": f"one 512x512 block (498x498 output px) of the same plane, {s:.2f} s; {desc}; -j {nj} of {os.cpu_count()} host threads (the reference's plane partition cannot use more; default -j 4)"}
+            try:      # the same block through OpenCV's own kernels (cv2), driven call for call like Model::filterWorker: "the reference's OpenCV CPU path"
+                s2, kind2, desc2 = cpu_reference_block(nj, want="cv2")
+                if "cv2" in desc2:
+                    cpu["opencv_variant"] = {"value": 498 * 498 / s2 / 1e6, "unit": "Mpix/s", "cores": nj, "kind": kind2, "sample": f"same block, {s2:.2f} s; {desc2}"}
+            except Exception:
+                pass
         host_api = host_api_legs(w2x, max(3, min(args.steps, 10)), args.size) if (world == 1 and not args.no_configs) else {}
         line = {"metric": "Mpix/s full scale2.0x model pass", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,

@@ -42,6 +42,7 @@ inline bool read_png(const std::vector<uint8_t> &f, Image8 &out, std::string &er
         const uint8_t *type = &f[pos + 4], *data = &f[pos + 8];
         if (pos + 12 + len > f.size()) { err = "truncated PNG chunk"; return false; }
         if (!std::memcmp(type, "IHDR", 4)) {
+            if (len != 13) { err = "bad PNG IHDR length"; return false; }
             w = be32(data); h = be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
         } else if (!std::memcmp(type, "PLTE", 4)) plte.assign(data, data + len);
         else if (!std::memcmp(type, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
@@ -49,6 +50,7 @@ inline bool read_png(const std::vector<uint8_t> &f, Image8 &out, std::string &er
         pos += 12 + len;
     }
     if (!w || !h) { err = "PNG without IHDR"; return false; }
+    if (w > 65535u || h > 65535u || (uint64_t)w * h > ((uint64_t)1 << 28)) { err = "PNG dimensions out of range"; return false; }   // (a crafted header must not drive the allocations below)
     if (interlace) { err = "interlaced PNG is not supported"; return false; }
     if (depth != 8 && depth != 16) { err = "only 8/16-bit PNG is supported"; return false; }
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
@@ -143,6 +145,7 @@ inline Image8 imread(const std::string &path, std::string *err_out = nullptr) {
 inline bool imwrite(const std::string &path, const uint8_t *bgr, int w, int h) {
     std::string ext = path.size() >= 4 ? path.substr(path.size() - 4) : "";
     for (auto &c : ext) c = (char)std::tolower(c);
+    if (ext != ".ppm" && ext != ".png") return false;          // cv::imwrite picks the encoder by extension; PNG and binary PPM are what this front end has
     std::ofstream out(path, std::ios::binary);
     if (!out) return false;
     if (ext == ".ppm") {
