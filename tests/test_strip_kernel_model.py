@@ -19,9 +19,10 @@ def blk_of(n, NB):
     return NB - 1 - (n % NB)
 
 
-def replay(Hp, seg_rows, NB, n_ctas, ncols=1, epi_sets=2):
+def replay(Hp, seg_rows, NB, n_ctas, ncols=1, epi_sets=2, strips=None):
     """Replays the kernel's issuer loop for every CTA; returns {(col, y): [(r, ky), ...]} in accumulation order.
-    Asserts the block protocol on the way (a block is never written before it was handed back, never drained twice)."""
+    Asserts the block protocol on the way (a block is never written before it was handed back, never drained twice).
+    `strips`, if a list, receives one tuple per strip: (cta, u, col, y0, j, ky_lo, b0, cnt0, cnt1, acq_n, acq_cnt, com_n, com_cnt)."""
     n_units = ncols * ((Hp + seg_rows - 1) // seg_rows)
     got = {}
     for cta in range(n_ctas):
@@ -38,6 +39,7 @@ def replay(Hp, seg_rows, NB, n_ctas, ncols=1, epi_sets=2):
                 ky_lo, ky_hi = max(0, r + 2 - y1), min(2, r + 1 - y0)
                 assert ky_lo <= ky_hi
                 i_top = r + 1 - ky_lo - y0
+                acq = (nrow + next_new, i_top + 1 - next_new)
                 while next_new <= i_top:
                     n = nrow + next_new
                     b = blk_of(n, NB)
@@ -58,6 +60,9 @@ def replay(Hp, seg_rows, NB, n_ctas, ncols=1, epi_sets=2):
                         assert owner[b] == (u, i), (owner[b], u, i)
                         got[(col, y0 + i)].append((r, ky))
                 i_done = rows - 1 if r == r_last else r - 1 - y0
+                if strips is not None:
+                    strips.append((cta, u, col, y0, r - (y0 - 1), ky_lo, b0, cnt0, cnt1, acq[0], acq[1],
+                                   nrow + next_done, max(0, i_done + 1 - next_done)))
                 while next_done <= i_done:
                     b = blk_of(nrow + next_done, NB)
                     assert owner[b] == (u, next_done)
@@ -77,6 +82,26 @@ def test_schedule_gives_every_row_its_three_taps_in_order(Hp, seg_rows, NB):
         for (col, y), contrib in got.items():
             want = [(r, ky) for ky, r in ((0, y - 1), (1, y), (2, y + 1)) if 0 <= r < Hp]
             assert contrib == want, (y, contrib, want)     # same taps, same order, whatever the unit geometry
+
+
+def test_kernel_plan_arithmetic_is_the_replayed_schedule(tmp_path):
+    """csrc/tc_strip_plan.h -- the closed-form per-strip plan the kernel's software-pipelined issuer computes one strip ahead --
+    compiled with g++ and compared, strip by strip, with the literal replay above (taps, blocks, wrap split, the rows whose
+    blocks are acquired before and handed to the epilogue after the strip)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "strip_plan_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(root, "waifu2x-converter-cpp_b200", "csrc"),
+                           os.path.join(root, "tests", "cpp", "strip_plan_dump.cpp"), "-o", exe])
+    for (Hp, seg_rows, NB) in [(15, 32, 8), (15, 32, 16), (3, 32, 8), (1, 32, 8), (2, 1, 8), (33, 32, 8), (64, 32, 16), (100, 7, 8),
+                               (100, 2, 8), (41, 1, 8), (530, 32, 16), (17, 16, 8), (4110, 32, 8)]:
+        for n_ctas in (1, 3, 7):
+            want = []
+            replay(Hp, seg_rows, NB, n_ctas, ncols=2, strips=want)
+            out = subprocess.check_output([exe, str(Hp), str(seg_rows), str(NB), str(n_ctas), "2"], text=True)
+            got = [tuple(int(v) for v in line.split()) for line in out.splitlines()]
+            assert got == want, (Hp, seg_rows, NB, n_ctas)
 
 
 def swz(a, rowb):

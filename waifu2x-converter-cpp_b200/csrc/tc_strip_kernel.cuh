@@ -26,6 +26,8 @@
 //   for ky (= strips r-1, r, r+1): for 32-channel chunk c: for kx: [xh*wh k0, xh*wh k1, corrections]
 // so block-split, whole-plane, banded and multi-GPU runs stay bit-identical to each other.
 
+#include "tc_strip_plan.h"              // the per-strip schedule (plain integer arithmetic, also compiled by a CPU test)
+
 constexpr int STRIP_W = 128;            // pixels per strip = GEMM M
 constexpr int STRIP_BOXW = STRIP_W + 2;  // staged pixels per row
 
@@ -161,88 +163,136 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
             bulk_load(w_base + (uint32_t)s * C::W_STAGE, p.wpack + (size_t)s * C::W_STAGE, C::W_STAGE, w_full);
     } else if (warp == 1) {
         // ===================== MMA issuer (one converged warp, an elected lane issues) =====================================
+        // The tensor queue hides only about one MMA of issuer time (profiles/r02_strip_issuer.txt: the old loop's ~600 cycles of
+        // index arithmetic between two strips were ~500 idle tensor cycles per strip), so the loop is software-pipelined: the
+        // NEXT strip's plan (tc_strip_plan.h) and its barrier probes are computed in two slices BETWEEN the tap-column groups
+        // of the current strip's last chunk; between the last MMA of a strip and the first of the next there are only the
+        // commits and the (normally already satisfied) waits.
         constexpr uint32_t LO_FIXED = 1u << 16;
         constexpr uint32_t A_HI32 = (uint32_t)(make_desc_const(8 * C::ROWB, 2u) >> 32);     // SWIZZLE_128B, 8-pixel groups are contiguous: SBO = 1024 B
         constexpr uint32_t B_HI32 = (uint32_t)(make_desc_const(8 * 64, 4u) >> 32);
         constexpr uint32_t B8_HI32 = (uint32_t)(make_desc_const(8 * 32, 6u) >> 32);
+        constexpr uint32_t A_STEP = (uint32_t)C::A_SLOT >> 4, W_STEP = (uint32_t)C::W_STAGE >> 4, KX_STEP = (uint32_t)C::ROWB >> 4;
+        constexpr uint32_t B8H_OFF = (uint32_t)C::NROWS * 4u, B8L_OFF = (uint32_t)C::NROWS * 6u;   // e4m3 / lo rows behind the fp16 rows [16-byte units]
+        constexpr uint32_t IDESC_0 = make_idesc(128, 0), IDESC_BLK = (uint32_t)(COUT >> 3) << 17;   // + one N-block
+        constexpr uint32_t LOG_NB = NB == 16 ? 4u : 3u;
+        static_assert(NB == 8 || NB == 16, "ring size");
         auto desc = [](uint32_t hi32, uint32_t lo32) { return ((uint64_t)hi32 << 32) | (uint64_t)lo32; };
-        auto lo14 = [&](uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | LO_FIXED; };
-        uint32_t a_it = 0, nrow = 0, n_strips = 0;
-        // The barriers of the NEXT strip are probed (mbarrier.test_wait, non-blocking) before the current strip's last MMAs
-        // are issued, so the ~90-cycle round trip of a completed-barrier wait does not drain the tensor queue between strips.
-        uint32_t a_ready = 0, new_ready = 0;
+        // shared-memory addresses are below 256 KB: descriptor start fields (addr >> 4, 14 bits) add without carries
+        const uint32_t aa0 = ((a_base >> 4) & 0x3FFFu) | LO_FIXED, bb0 = ((w_base >> 4) & 0x3FFFu) | LO_FIXED;
+        auto blk_bar_empty = [&](uint32_t n) { return blk_empty(NB - 1u - (n & (NB - 1u))); };
+        auto blk_par = [&](uint32_t n) { return (n >> LOG_NB) & 1u; };
+        const bool waits = !(p.dbg & 16), mmas = !(p.dbg & 8);
+
+        uint32_t n_strips = 0;
         unsigned long long w_acc = 0, w_af = 0, w_bf = 0;
         const long long t_begin = clock64();
         mbar_wait_prof(w_full, 0u, prof_on, w_bf);
         tc_fence_after();
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+
+        int u = blockIdx.x;
+        if (u < p.n_units) {
+            // ---- walk state: unit (rows, nbase), strip j; activation slot ring ----
             int col, y0, y1;
             unit_of(u, col, y0, y1);
-            const int rows = y1 - y0;
-            const int r_first = max(y0 - 1, 0), r_last = min(y1, p.Hp - 1);
-            int next_new = 0, next_done = 0;                 // output rows (unit-relative) not yet acquired / not yet committed
-            for (int r = r_first; r <= r_last; r++, n_strips++) {
-                // input row r feeds output row r + 1 - ky with W(ky): the rows of this unit it reaches
-                const int ky_lo = max(0, r + 2 - y1), ky_hi = min(2, r + 1 - y0);
-                const int i_top = r + 1 - ky_lo - y0;         // unit-relative output row of ky_lo (the highest row index)
-                for (; next_new <= i_top; next_new++) {      // first contribution to these rows: their blocks must be drained + zeroed
-                    const uint32_t n = nrow + (uint32_t)next_new;
-                    if (!new_ready && !(p.dbg & 16)) mbar_wait_prof(blk_empty(blk_of(n)), (n / NB) & 1u, prof_on, w_acc);
-                    new_ready = 0;
+            int rows = y1 - y0, j = strip_j_first(y0), j_last = strip_j_last(y1, rows, p.Hp);
+            uint32_t nbase = 0;
+            uint32_t slot = 0, apar = 0;                      // a_full parity of the slot ring's current round
+            StripPlan P = strip_plan(j, true, j == j_last, rows, nbase, NB);
+            uint32_t a_ready = 0, new_ready = 0;
+            // one strip's operands: D blocks, instruction descriptors, B row offsets of the two runs [16-byte units], rows to hand over
+            struct Ops { uint32_t d0, id0, id1, bq0, bq1, run1, acq_n, acq_cnt, com_n, com_cnt; };
+            auto ops_of = [&](const StripPlan &Q) {
+                Ops o;
+                o.d0 = tmem_base + Q.b0 * COUT;
+                o.id0 = IDESC_0 + Q.cnt0 * IDESC_BLK;
+                o.id1 = IDESC_0 + Q.cnt1 * IDESC_BLK;
+                o.bq0 = Q.ky_lo * (uint32_t)(COUT * 4);
+                o.bq1 = o.bq0 + Q.cnt0 * (uint32_t)(COUT * 4);
+                o.run1 = Q.cnt1;
+                o.acq_n = Q.acq_n, o.acq_cnt = Q.acq_cnt, o.com_n = Q.com_n, o.com_cnt = Q.com_cnt;
+                return o;
+            };
+            Ops cur = ops_of(P), nxt = cur;
+            uint32_t aa = aa0;                                // descriptor start field of the current activation slot
+            for (;;) {
+                // ---- blocks that receive their first tap (at most two): drained + zeroed?  (probed during the previous strip) ----
+                if (waits) {
+                    if (cur.acq_cnt > 0 && !new_ready) mbar_wait_prof(blk_bar_empty(cur.acq_n), blk_par(cur.acq_n), prof_on, w_acc);
+                    if (cur.acq_cnt > 1) mbar_wait_prof(blk_bar_empty(cur.acq_n + 1u), blk_par(cur.acq_n + 1u), prof_on, w_acc);
                 }
-                tc_fence_after();
-                // ky ascending = output row descending = block ascending (mod NB): at most two runs of adjacent blocks
-                const uint32_t b0 = blk_of(nrow + (uint32_t)i_top), nky = (uint32_t)(ky_hi - ky_lo + 1);
-                const uint32_t cnt0 = min(nky, NB - b0), cnt1 = nky - cnt0;
-                const uint32_t d0 = tmem_base + b0 * COUT, d1 = tmem_base;
-                const uint32_t row0 = (uint32_t)ky_lo * COUT, row1 = row0 + cnt0 * COUT;      // first B row of each run
-                const uint32_t id0 = make_idesc(128, (int)(cnt0 * COUT)), id1 = make_idesc(128, (int)(cnt1 * COUT));
-                for (int c = 0; c < C::NCH; c++, a_it++) {
-                    const uint32_t slot = a_it % (uint32_t)C::A_SLOTS;
-                    if (!a_ready && !(p.dbg & 16)) mbar_wait_prof(a_full(slot), (a_it / (uint32_t)C::A_SLOTS) & 1u, prof_on, w_af);
+                bool more = true;
+                n_strips++;
+#pragma unroll
+                for (int c = 0; c < C::NCH; c++) {
+                    if (waits && !a_ready) mbar_wait_prof(a_full(slot), apar, prof_on, w_af);
                     tc_fence_after();
-                    if (!(p.dbg & 16)) {   // probe what the next chunk / strip will wait for
-                        const uint32_t nx = a_it + 1u;
-                        a_ready = mbar_test(a_full(nx % (uint32_t)C::A_SLOTS), (nx / (uint32_t)C::A_SLOTS) & 1u);
-                        if (c + 1 == C::NCH) {
-                            const uint32_t n = nrow + (uint32_t)next_new;      // the next output row to acquire (numbering runs on across units)
-                            new_ready = mbar_test(blk_empty(blk_of(n)), (n / NB) & 1u);
-                        }
-                    }
-                    const uint32_t ab = a_base + slot * C::A_SLOT;
+                    uint32_t slot_n = 0, apar_n = 0;
 #pragma unroll
                     for (int kx = 0; kx < 3; kx++) {
-                        const uint32_t sb = w_base + (uint32_t)(c * 3 + kx) * C::W_STAGE;
-                        const uint32_t ah = lo14(ab + kx * C::ROWB);
+                        if (mmas) {
+                            const uint32_t ah = aa + (uint32_t)kx * KX_STEP, sb = bb0 + (uint32_t)(c * 3 + kx) * W_STEP;
 #pragma unroll
-                        for (int s = 0; s < 2; s++) {
-                            const uint32_t cnt = s ? cnt1 : cnt0;
-                            if (cnt == 0 || (p.dbg & 8)) continue;
-                            const uint32_t d = s ? d1 : d0, idesc = s ? id1 : id0, brow = s ? row1 : row0;
-                            const uint32_t bh = lo14(sb + brow * 64u);
-                            umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bh), idesc, 1u);
-                            umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
-                            // the record's quarters: +0 / +2 the fp16 K steps, +4 xh8 (or lo step 0), +6 xl8 (or lo step 1)   [16-byte units]
-                            if constexpr (F8) {
-                                const uint32_t b8h = lo14(sb + C::NROWS * 64u + brow * 32u), b8l = lo14(sb + C::NROWS * 96u + brow * 32u);
-                                umma_f8(d, desc(A_HI32, ah + 6u), desc(B8_HI32, b8h), idesc, 1u);    // xl8 * wh8
-                                umma_f8(d, desc(A_HI32, ah + 4u), desc(B8_HI32, b8l), idesc, 1u);    // xh8 * wl8
-                            } else {
-                                const uint32_t bl = lo14(sb + C::NROWS * 64u + brow * 64u);
-                                umma_f16(d, desc(A_HI32, ah + 4u), desc(B_HI32, bh), idesc, 1u);     // xl * wh
-                                umma_f16(d, desc(A_HI32, ah + 6u), desc(B_HI32, bh + 2u), idesc, 1u);
-                                umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bl), idesc, 1u);          // xh * wl
-                                umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bl + 2u), idesc, 1u);
+                            for (int s = 0; s < 2; s++) {
+                                if (s == 1 && !cur.run1) continue;
+                                const uint32_t d = s ? tmem_base : cur.d0, idesc = s ? cur.id1 : cur.id0, bq = s ? cur.bq1 : cur.bq0;
+                                const uint32_t bh = sb + bq;
+                                umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bh), idesc, 1u);
+                                umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bh + 2u), idesc, 1u);
+                                // the record's quarters: +0 / +2 the fp16 K steps, +4 xh8 (or lo step 0), +6 xl8 (or lo step 1)   [16-byte units]
+                                if constexpr (F8) {
+                                    const uint32_t b8h = sb + B8H_OFF + (bq >> 1), b8l = sb + B8L_OFF + (bq >> 1);
+                                    umma_f8(d, desc(A_HI32, ah + 6u), desc(B8_HI32, b8h), idesc, 1u);    // xl8 * wh8
+                                    umma_f8(d, desc(A_HI32, ah + 4u), desc(B8_HI32, b8l), idesc, 1u);    // xh8 * wl8
+                                } else {
+                                    const uint32_t bl = sb + B8H_OFF + bq;
+                                    umma_f16(d, desc(A_HI32, ah + 4u), desc(B_HI32, bh), idesc, 1u);     // xl * wh
+                                    umma_f16(d, desc(A_HI32, ah + 6u), desc(B_HI32, bh + 2u), idesc, 1u);
+                                    umma_f16(d, desc(A_HI32, ah), desc(B_HI32, bl), idesc, 1u);          // xh * wl
+                                    umma_f16(d, desc(A_HI32, ah + 2u), desc(B_HI32, bl + 2u), idesc, 1u);
+                                }
                             }
+                        }
+                        // ---- slices of the NEXT strip's bookkeeping, placed behind tap columns 0 and 1 ----
+                        if (kx == 0) {
+                            slot_n = slot + 1u == (uint32_t)C::A_SLOTS ? 0u : slot + 1u;
+                            apar_n = slot_n == 0u ? apar ^ 1u : apar;
+                            if (waits) a_ready = mbar_test(a_full(slot_n), apar_n);        // the next chunk's (or strip's) activations
+                            if (c == C::NCH - 1) {
+                                if (j < j_last) {
+                                    j++;
+                                    P = strip_plan(j, false, j == j_last, rows, nbase, NB);
+                                } else {
+                                    u += gridDim.x;
+                                    more = u < p.n_units;
+                                    if (more) {
+                                        nbase += (uint32_t)rows;
+                                        unit_of(u, col, y0, y1);
+                                        rows = y1 - y0;
+                                        j = strip_j_first(y0);
+                                        j_last = strip_j_last(y1, rows, p.Hp);
+                                        P = strip_plan(j, true, j == j_last, rows, nbase, NB);
+                                    }
+                                }
+                                asm volatile("" : "+r"(P.b0), "+r"(P.cnt0), "+r"(P.cnt1), "+r"(P.ky_lo), "+r"(P.acq_n), "+r"(P.acq_cnt));   // keep the slice here
+                            }
+                        } else if (kx == 1 && c == C::NCH - 1) {
+                            nxt = ops_of(P);
+                            new_ready = 0;
+                            if (waits && more && nxt.acq_cnt) new_ready = mbar_test(blk_bar_empty(nxt.acq_n), blk_par(nxt.acq_n));
+                            asm volatile("" : "+r"(nxt.d0), "+r"(nxt.id0), "+r"(nxt.id1), "+r"(nxt.bq0), "+r"(nxt.bq1), "+r"(nxt.run1));
                         }
                     }
                     umma_commit_one(a_empty(slot));
+                    slot = slot_n;
+                    apar = apar_n;
+                    aa = aa0 + slot * A_STEP;
                 }
-                // complete after this strip: output rows <= r - 1 (their ky = 2 tap), or every row after the unit's last strip
-                const int i_done = r == r_last ? rows - 1 : r - 1 - y0;
-                for (; next_done <= i_done; next_done++) umma_commit_one(blk_full(blk_of(nrow + (uint32_t)next_done)));
+                if (cur.com_cnt > 0) umma_commit_one(blk_full(NB - 1u - (cur.com_n & (NB - 1u))));
+                if (cur.com_cnt > 1) umma_commit_one(blk_full(NB - 1u - ((cur.com_n + 1u) & (NB - 1u))));
+                if (!more) break;
+                cur = nxt;
             }
-            nrow += (uint32_t)rows;
         }
         if (prof_on && lane == 0) {
             prof[PROF_TOTAL] += (unsigned long long)(clock64() - t_begin);
