@@ -163,7 +163,7 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
             bulk_load(w_base + (uint32_t)s * C::W_STAGE, p.wpack + (size_t)s * C::W_STAGE, C::W_STAGE, w_full);
     } else if (warp == 1) {
         // ===================== MMA issuer (one converged warp, an elected lane issues) =====================================
-        // The tensor queue hides only about one MMA of issuer time (profiles/r02_strip_issuer.txt: the old loop's ~600 cycles of
+        // The tensor queue hides only about one MMA of issuer time (profiles/r02_strip_issuer_experiment.txt: the old loop's ~600 cycles of
         // index arithmetic between two strips were ~500 idle tensor cycles per strip), so the loop is software-pipelined: the
         // NEXT strip's plan (tc_strip_plan.h) and its barrier probes are computed in two slices BETWEEN the tap-column groups
         // of the current strip's last chunk; between the last MMA of a strip and the first of the next there are only the
