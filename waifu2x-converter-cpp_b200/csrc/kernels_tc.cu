@@ -186,6 +186,7 @@ static cudaError_t launch_strip(const __half *in, const void *wstrip, const floa
     p.n_units = p.ncols * ((ph + p.seg_rows - 1) / p.seg_rows);
     p.out_scale = out_scale * ACT_SCALE;
     p.prof = prof;
+    p.out_win = reinterpret_cast<uint8_t *>(out) + (size_t)out_y0 * pw * cout * 4;
 #ifdef W2X_EPI_EXPERIMENTS
     static const int dbg_strip = std::getenv("W2X_DEBUG_STRIP") ? std::atoi(std::getenv("W2X_DEBUG_STRIP")) : 0;
     p.dbg = dbg_strip;

@@ -58,6 +58,43 @@ __device__ __forceinline__ void epilogue_store32_rec(const float (&act)[32], con
     }
 }
 
+// The same record straight from registers: 4 x 32-byte (STG.256) or 8 x 16-byte global stores per lane, no staging tile and no
+// TMA store -- nothing of the epilogue crosses the shared-memory pipe (which bounds the 64 -> 64 strip layer), but a
+// warp-wide store touches 32 different 128-byte lines: 16-byte stores are LSU-bound everywhere, 32-byte stores pay off where
+// the shared-memory pipe is the bound and lose where it is not (profiles/r02_strip_direct_store_experiment.txt).
+template <bool F8>
+__device__ __forceinline__ void epilogue_store32_direct(const float (&act)[32], uint8_t *rec, bool wide) {
+    uint32_t g[32];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float v0 = act[2 * i], v1 = act[2 * i + 1];
+        __half2 h = __floats2half2_rn(v0, v1);
+        float2 hf = __half22float2(h);
+        g[i] = *reinterpret_cast<uint32_t *>(&h);
+        if constexpr (F8) {
+            constexpr float kDown = 1.0f / (float)(1 << F8_C), kUp = (float)(1 << F8_A);
+            const __half2 hd = __hmul2(h, __float2half2_rn(kDown));
+            const uint32_t h8 = __nv_cvt_halfraw2_to_fp8x2(static_cast<__half2_raw>(hd), __NV_SATFINITE, __NV_E4M3);
+            const uint32_t l8 = __nv_cvt_float2_to_fp8x2(make_float2((v0 - hf.x) * kUp, (v1 - hf.y) * kUp), __NV_SATFINITE, __NV_E4M3);
+            if (i & 1) { g[16 + (i >> 1)] |= h8 << 16; g[24 + (i >> 1)] |= l8 << 16; }
+            else { g[16 + (i >> 1)] = h8; g[24 + (i >> 1)] = l8; }
+        } else {
+            __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+            g[16 + i] = *reinterpret_cast<uint32_t *>(&l);
+        }
+    }
+    if (wide) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rec + 32 * u), "r"(g[8 * u]), "r"(g[8 * u + 1]), "r"(g[8 * u + 2]),
+                         "r"(g[8 * u + 3]), "r"(g[8 * u + 4]), "r"(g[8 * u + 5]), "r"(g[8 * u + 6]), "r"(g[8 * u + 7])
+                         : "memory");
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) *reinterpret_cast<uint4 *>(rec + 16 * u) = make_uint4(g[4 * u], g[4 * u + 1], g[4 * u + 2], g[4 * u + 3]);
+    }
+}
+
 // One M-tile's share of a tile-set in the 16x16-tile kernels (single-CTA and CTA-pair): this warp's 32 pixels x COUT
 // accumulator columns -> scale, bias, leaky-ReLU -> either records (TMA store) or, with the last layer folded in (FUSE),
 // the nine per-tap dot products of the pixel.  `release()` hands the accumulator columns back to the MMA issuer (a local

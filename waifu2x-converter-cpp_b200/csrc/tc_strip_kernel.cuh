@@ -48,9 +48,12 @@ struct StripCfg {
     static constexpr int SMEM_MAX = 227 * 1024;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int STG_WARP = 4096;
+    // 64 -> 64 (144 KB of weights, bound by the shared-memory pipe): the epilogue stores its records straight from registers
+    // (32-byte global stores) -- no staging tiles, so two epilogue sets and a fourth activation slot fit
+    static constexpr bool DIRECT = CIN == 64 && COUT == 64;
     // two epilogue warp sets (alternate output rows) when the resident weights leave room for their staging tiles
-    static constexpr int EPI_SETS = (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - 8 * STG_WARP) / A_SLOT >= 3 ? 2 : 1;
-    static constexpr int STG_BYTES = EPI_SETS * 4 * STG_WARP;
+    static constexpr int EPI_SETS = DIRECT ? 2 : (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - 8 * STG_WARP) / A_SLOT >= 3 ? 2 : 1;
+    static constexpr int STG_BYTES = DIRECT ? 0 : EPI_SETS * 4 * STG_WARP;
     static constexpr int A_FIT = (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - STG_BYTES) / A_SLOT;
     static constexpr int A_SLOTS = A_FIT > 6 ? 6 : A_FIT;
     static constexpr int SMEM_BYTES = 1024 + W_BYTES + A_SLOTS * A_SLOT + STG_BYTES + BAR_BYTES;
@@ -69,6 +72,7 @@ struct StripParams {
     int ncols, n_units, seg_rows;   // units = 128-pixel columns x segments of seg_rows rows, unit u = seg * ncols + col
     float out_scale;
     unsigned long long *prof;
+    uint8_t *out_win;           // first stored row of the output frame (direct stores: StripCfg::DIRECT, or experiments 128 / 256 = 16- / 32-byte stores, results correct)
     int dbg;                    // always 0 in product builds; -DW2X_EPI_EXPERIMENTS + W2X_DEBUG_STRIP (timing only, results WRONG):
                                 // 1 = no TMA stores, 2 = no staging either, 4 = no activation loads, 8 = no MMAs,
                                 // 16 = the issuer neither waits for nor probes a barrier, 32 = the epilogue does not touch TMEM,
@@ -361,6 +365,11 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
                     const int gy = y0 + i - p.out_y0;
+                    if (C::DIRECT || (p.dbg & (128 | 256))) {
+                        if (gx0 + lane < p.Wp && gy >= 0 && gy < p.out_rows)
+                            epilogue_store32_direct<F8>(act, p.out_win + (((size_t)gy * p.Wp + gx0 + lane) * (COUT / 32) + cb) * 128u, !(p.dbg & 128));
+                        continue;
+                    }
                     if (gx0 < p.Wp && gy >= 0 && gy < p.out_rows) epilogue_store32_rec<F8>(act, &tmap_out, p.dbg, stg, lane, gx0, gy, cb);
                 }
                 if (prof_on) work_e += (unsigned long long)(clock64() - t_work);
