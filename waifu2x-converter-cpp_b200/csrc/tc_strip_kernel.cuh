@@ -50,7 +50,10 @@ struct StripCfg {
     static constexpr int STG_WARP = 4096;
     // 64 -> 64 (144 KB of weights, bound by the shared-memory pipe): the epilogue stores its records straight from registers
     // (32-byte global stores) -- no staging tiles, so two epilogue sets and a fourth activation slot fit
-    static constexpr bool DIRECT = CIN == 64 && COUT == 64;
+#ifndef W2X_STRIP_DIRECT
+#define W2X_STRIP_DIRECT 1              // -DW2X_STRIP_DIRECT=0: staging tile + TMA store for every shape (A/B timing builds)
+#endif
+    static constexpr bool DIRECT = W2X_STRIP_DIRECT && CIN == 64 && COUT == 64;
     // two epilogue warp sets (alternate output rows) when the resident weights leave room for their staging tiles
     static constexpr int EPI_SETS = DIRECT ? 2 : (SMEM_MAX - 1024 - BAR_BYTES - W_BYTES - 8 * STG_WARP) / A_SLOT >= 3 ? 2 : 1;
     static constexpr int STG_BYTES = DIRECT ? 0 : EPI_SETS * 4 * STG_WARP;
@@ -365,7 +368,12 @@ tc_conv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmap_in, const __gri
                         act[k] = fmaxf(v, 0.1f * v);                                         // leaky 0.1
                     }
                     const int gy = y0 + i - p.out_y0;
-                    if (C::DIRECT || (p.dbg & (128 | 256))) {
+#ifdef W2X_EPI_EXPERIMENTS
+                    const bool direct = C::DIRECT || (p.dbg & (128 | 256)) != 0;
+#else
+                    constexpr bool direct = C::DIRECT;
+#endif
+                    if (direct) {
                         if (gx0 + lane < p.Wp && gy >= 0 && gy < p.out_rows)
                             epilogue_store32_direct<F8>(act, p.out_win + (((size_t)gy * p.Wp + gx0 + lane) * (COUT / 32) + cb) * 128u, !(p.dbg & 128));
                         continue;
