@@ -66,14 +66,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     main_cpp = os.path.join(HERE, "host", "main.cpp")
     if os.path.exists(main_cpp) and (force or _newer(CLI, [main_cpp, LIB] + _headers())):
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
+        cmd = ["g++", "-O3", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
                main_cpp, "-o", CLI, "-L", HERE, "-lw2x_b200", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"CLI build failed:\n{r.stdout}\n{r.stderr}")
     bench_cpp = os.path.join(HERE, "host", "bench_host.cpp")
     if os.path.exists(bench_cpp) and (force or _newer(BENCH_HOST, [bench_cpp, LIB] + _headers())):
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
+        cmd = ["g++", "-O3", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "host"),
                bench_cpp, "-o", BENCH_HOST, "-L", HERE, "-lw2x_b200", "-pthread", "-Wl,-rpath,$ORIGIN"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

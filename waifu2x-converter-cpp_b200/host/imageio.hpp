@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace w2xio {
@@ -157,34 +159,82 @@ inline bool imwrite(const std::string &path, const uint8_t *bgr, int w, int h) {
         }
         return (bool)out;
     }
-    // PNG, 8-bit RGB, filter type 0
-    std::vector<uint8_t> raw((size_t)(w * 3 + 1) * h);
-    for (int y = 0; y < h; y++) {
-        uint8_t *r = &raw[(size_t)(w * 3 + 1) * y];
-        r[0] = 0;
-        for (int x = 0; x < w; x++) { const uint8_t *p = bgr + ((size_t)y * w + x) * 3; r[1 + x * 3] = p[2]; r[2 + x * 3] = p[1]; r[3 + x * 3] = p[0]; }
+    // PNG, 8-bit RGB.  Encoder settings are cv::imwrite's defaults (filter SUB, Z_BEST_SPEED, Z_RLE: grfmt_png.cpp); the rows are
+    // deflated in independent bands on several threads -- every band but the last ends on a full flush (byte-aligned, no final
+    // block), so the concatenation is one valid deflate stream; the zlib trailer is the combined Adler-32 of the bands.
+    const size_t stride = (size_t)w * 3 + 1;
+    int nband = (int)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    nband = std::max(1, std::min(nband, h / 16));
+    if ((size_t)w * h < (1u << 16)) nband = 1;
+    std::vector<std::vector<uint8_t>> parts((size_t)nband);
+    std::vector<uLong> adler((size_t)nband), lens((size_t)nband);
+    std::vector<int> ok((size_t)nband, 0);
+    auto work = [&](int bi) {
+        const int y0 = (int)((long)h * bi / nband), y1 = (int)((long)h * (bi + 1) / nband);
+        std::vector<uint8_t> raw(stride * (size_t)(y1 - y0));
+        for (int y = y0; y < y1; y++) {
+            uint8_t *r = &raw[stride * (size_t)(y - y0)];
+            const uint8_t *p = bgr + (size_t)y * w * 3;
+            r[0] = 1;                                                            // filter type 1 (SUB): byte - byte of the pixel to the left
+            uint8_t pr = 0, pg = 0, pb = 0;
+            for (int x = 0; x < w; x++, p += 3) {
+                r[1 + x * 3] = (uint8_t)(p[2] - pr); r[2 + x * 3] = (uint8_t)(p[1] - pg); r[3 + x * 3] = (uint8_t)(p[0] - pb);
+                pr = p[2]; pg = p[1]; pb = p[0];
+            }
+        }
+        adler[(size_t)bi] = adler32(adler32(0L, Z_NULL, 0), raw.data(), (uInt)raw.size());
+        lens[(size_t)bi] = (uLong)raw.size();
+        z_stream zs;
+        std::memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, Z_BEST_SPEED, Z_DEFLATED, -15, 8, Z_RLE) != Z_OK) return;
+        std::vector<uint8_t> &o = parts[(size_t)bi];
+        o.resize(deflateBound(&zs, (uLong)raw.size()) + 16);
+        zs.next_in = raw.data(); zs.avail_in = (uInt)raw.size();
+        zs.next_out = o.data(); zs.avail_out = (uInt)o.size();
+        const int rc = deflate(&zs, bi == nband - 1 ? Z_FINISH : Z_FULL_FLUSH);
+        if ((bi == nband - 1 && rc == Z_STREAM_END) || (bi != nband - 1 && rc == Z_OK && zs.avail_in == 0)) ok[(size_t)bi] = 1;
+        o.resize(o.size() - zs.avail_out);
+        deflateEnd(&zs);
+    };
+    if (nband == 1) work(0);
+    else {
+        std::vector<std::thread> ts;
+        for (int bi = 0; bi < nband; bi++) ts.emplace_back(work, bi);
+        for (auto &t : ts) t.join();
     }
-    uLongf clen = compressBound((uLong)raw.size());
-    std::vector<uint8_t> comp(clen);
-    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 3) != Z_OK) return false;
-    comp.resize(clen);
-    auto chunk = [&](const char *type, const std::vector<uint8_t> &data) {
-        std::vector<uint8_t> c;
-        detail::put32(c, (uint32_t)data.size());
-        c.insert(c.end(), type, type + 4);
-        c.insert(c.end(), data.begin(), data.end());
-        uint32_t crc = (uint32_t)crc32(0L, c.data() + 4, (uInt)(c.size() - 4));
-        detail::put32(c, crc);
-        out.write(reinterpret_cast<const char *>(c.data()), (std::streamsize)c.size());
+    // one IDAT chunk per band (their concatenation is the zlib stream): header in front of the first, Adler-32 behind the last
+    uLong ad = adler[0];
+    for (int bi = 0; bi < nband; bi++) {
+        if (!ok[(size_t)bi]) return false;
+        if (bi > 0) ad = adler32_combine(ad, adler[(size_t)bi], (z_off_t)lens[(size_t)bi]);
+    }
+    auto chunk = [&](const char *type, const uint8_t *head, size_t nhead, const std::vector<uint8_t> &data, const uint8_t *tail, size_t ntail) {
+        uint8_t len[4], crcb[4];
+        const uint32_t n = (uint32_t)(nhead + data.size() + ntail);
+        len[0] = n >> 24; len[1] = n >> 16; len[2] = n >> 8; len[3] = n;
+        uLong crc = crc32(0L, reinterpret_cast<const Bytef *>(type), 4);
+        if (nhead) crc = crc32(crc, head, (uInt)nhead);
+        if (!data.empty()) crc = crc32(crc, data.data(), (uInt)data.size());
+        if (ntail) crc = crc32(crc, tail, (uInt)ntail);
+        crcb[0] = crc >> 24; crcb[1] = crc >> 16; crcb[2] = crc >> 8; crcb[3] = crc;
+        out.write(reinterpret_cast<const char *>(len), 4);
+        out.write(type, 4);
+        if (nhead) out.write(reinterpret_cast<const char *>(head), (std::streamsize)nhead);
+        if (!data.empty()) out.write(reinterpret_cast<const char *>(data.data()), (std::streamsize)data.size());
+        if (ntail) out.write(reinterpret_cast<const char *>(tail), (std::streamsize)ntail);
+        out.write(reinterpret_cast<const char *>(crcb), 4);
     };
     static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
     out.write(reinterpret_cast<const char *>(sig), 8);
     std::vector<uint8_t> ihdr;
     detail::put32(ihdr, (uint32_t)w); detail::put32(ihdr, (uint32_t)h);
     ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
-    chunk("IHDR", ihdr);
-    chunk("IDAT", comp);
-    chunk("IEND", {});
+    chunk("IHDR", nullptr, 0, ihdr, nullptr, 0);
+    static const uint8_t zhdr[2] = {0x78, 0x01};                                 // zlib header: deflate, 32 KB window, fastest
+    const uint8_t ztail[4] = {(uint8_t)(ad >> 24), (uint8_t)(ad >> 16), (uint8_t)(ad >> 8), (uint8_t)ad};
+    for (int bi = 0; bi < nband; bi++)
+        chunk("IDAT", bi == 0 ? zhdr : nullptr, bi == 0 ? 2 : 0, parts[(size_t)bi], bi == nband - 1 ? ztail : nullptr, bi == nband - 1 ? 4 : 0);
+    chunk("IEND", nullptr, 0, {}, nullptr, 0);
     return (bool)out;
 }
 

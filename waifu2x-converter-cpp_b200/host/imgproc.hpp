@@ -10,7 +10,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <memory>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace w2ximg {
@@ -37,12 +40,28 @@ inline void parallel_rows(int rows, long work_per_row, F &&fn) {   // fn(row_beg
     for (auto &th : ts) th.join();
 }
 
+// std::vector without the zero fill of resize()/the sizing constructor: the images here are 100 MB and every element is
+// written by the (row-parallel) routine that creates them, so the fill would be a serial extra pass over fresh pages
+template <typename T>
+struct no_init_alloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = no_init_alloc<U>; };
+    template <typename U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+    template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+using FloatBuf = std::vector<float, no_init_alloc<float>>;
+
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(W2X_NO_TARGET_CLONES)
+#define W2X_SIMD_CLONES __attribute__((target_clones("avx2", "default")))   // runtime dispatch; no FMA: the arithmetic stays the scalar code's
+#else
+#define W2X_SIMD_CLONES
+#endif
+
 // interleaved 3-channel float image (what cv::Mat CV_32FC3 holds), channel order as loaded (B,G,R for imread)
 struct Image3f {
     int width = 0, height = 0;
-    std::vector<float> data;   // [h][w][3]
+    FloatBuf data;   // [h][w][3]
     Image3f() {}
-    Image3f(int w, int h) : width(w), height(h), data((size_t)w * h * 3, 0.f) {}
+    Image3f(int w, int h) : width(w), height(h), data((size_t)w * h * 3) {}
     float *px(int y, int x) { return &data[((size_t)y * width + x) * 3]; }
     const float *px(int y, int x) const { return &data[((size_t)y * width + x) * 3]; }
 };
@@ -59,16 +78,22 @@ inline Image3f from_u8(const uint8_t *bgr, int w, int h) {
 }
 
 // image.convertTo(image, CV_8U, 255.0)   (src/main.cpp:172): saturate_cast<uchar>(cvRound(v * 255)) , round half to even
+W2X_SIMD_CLONES inline void to_u8_span(const float *src, uint8_t *dst, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        float v = src[i] * 255.0f;
+        v = v > 0.f ? v : 0.f;                 // saturate first (NaN -> 0, as saturate_cast<uchar>(cvRound(NaN)) gives) ...
+        v = v < 255.f ? v : 255.f;
+        const float t = v + 8388608.0f;        // ... then round to nearest, ties to even (cvRound): at 2^23 the float grid is the integers
+        uint32_t bits;
+        std::memcpy(&bits, &t, 4);
+        dst[i] = (uint8_t)(bits & 0xFFu);
+    }
+}
 inline std::vector<uint8_t> to_u8(const Image3f &im) {
-    std::vector<uint8_t> out(im.data.size());
+    std::vector<uint8_t> out;
+    out.resize(im.data.size());
     const size_t row = (size_t)im.width * 3;
-    parallel_rows(im.height, (long)row, [&](int y0, int y1) {
-        for (size_t i = (size_t)y0 * row; i < (size_t)y1 * row; i++) {
-            float v = im.data[i] * 255.0f;
-            long r = std::lrintf(v);   // FE_TONEAREST: ties to even, as cvRound
-            out[i] = (uint8_t)std::min(255L, std::max(0L, r));
-        }
-    });
+    parallel_rows(im.height, (long)row, [&](int y0, int y1) { to_u8_span(im.data.data() + (size_t)y0 * row, out.data() + (size_t)y0 * row, (size_t)(y1 - y0) * row); });
     return out;
 }
 
@@ -103,17 +128,76 @@ inline void yuv2rgb(Image3f &im) {
 }
 
 // cv::split / cv::merge of one channel
+inline void get_channel(const Image3f &im, int c, float *plane, size_t stride_floats) {
+    parallel_rows(im.height, (long)im.width * 2, [&](int y0, int y1) {
+        for (int y = y0; y < y1; y++) {
+            const float *s = im.px(y, 0) + c;
+            float *d = plane + (size_t)y * stride_floats;
+            for (int x = 0; x < im.width; x++) d[x] = s[(size_t)x * 3];
+        }
+    });
+}
 inline std::vector<float> channel(const Image3f &im, int c) {
     std::vector<float> out((size_t)im.width * im.height);
-    for (size_t i = 0; i < out.size(); i++) out[i] = im.data[i * 3 + c];
+    get_channel(im, c, out.data(), (size_t)im.width);
     return out;
 }
 inline void set_channel(Image3f &im, int c, const float *plane, size_t stride_floats) {
-    for (int y = 0; y < im.height; y++)
-        for (int x = 0; x < im.width; x++) im.px(y, x)[c] = plane[(size_t)y * stride_floats + x];
+    parallel_rows(im.height, (long)im.width * 2, [&](int y0, int y1) {
+        for (int y = y0; y < y1; y++) {
+            float *d = im.px(y, 0) + c;
+            const float *s = plane + (size_t)y * stride_floats;
+            for (int x = 0; x < im.width; x++) d[(size_t)x * 3] = s[x];
+        }
+    });
 }
 
 enum Interp { NEAREST, LINEAR, CUBIC };
+
+namespace detail {
+// vertical pass of one output row: dst[i] = ((0 + r0[i] w0) + r1[i] w1) + ... in this order (the order the tests pin against cv2)
+template <int NTAP>
+W2X_SIMD_CLONES inline void vpass_row(float *dst, const float *const *rows, const float *w, size_t n) {
+    if (NTAP == 4) {
+        const float *r0 = rows[0], *r1 = rows[1], *r2 = rows[2], *r3 = rows[3];
+        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        for (size_t i = 0; i < n; i++) dst[i] = ((r0[i] * w0 + r1[i] * w1) + r2[i] * w2) + r3[i] * w3;
+    } else {
+        const float *r0 = rows[0], *r1 = rows[1];
+        const float w0 = w[0], w1 = w[1];
+        for (size_t i = 0; i < n; i++) dst[i] = r0[i] * w0 + r1[i] * w1;
+    }
+}
+// horizontal pass of one source row: dw output pixels x 3 channels, taps gathered through xi (element offsets, already x3)
+template <int NTAP>
+inline void hpass_row(float *dst, const float *src, const int *xi, const float *xw, int dw) {
+    for (int x = 0; x < dw; x++, xi += NTAP, xw += NTAP, dst += 3) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int k = 0; k < NTAP; k++) {
+            const float *s = src + xi[k];
+            const float wk = xw[k];
+            a0 += s[0] * wk; a1 += s[1] * wk; a2 += s[2] * wk;
+        }
+        dst[0] = a0; dst[1] = a1; dst[2] = a2;
+    }
+}
+}  // namespace detail
+
+
+// Channel c of cv::resize(src, Size(dw, dh), 0, 0, INTER_NEAREST) written straight into a plane (what src/main.cpp:135-139 obtains
+// with resize + split): sx = min(floor(dx * scale), w - 1), scale = src/dst in double.
+inline void resize_nearest_channel(const Image3f &src, int c, int dw, int dh, float *plane, size_t stride_floats) {
+    const double sx = (double)src.width / dw, sy = (double)src.height / dh;
+    std::vector<int> xo((size_t)dw);
+    for (int x = 0; x < dw; x++) xo[(size_t)x] = 3 * std::min((int)std::floor(x * sx), src.width - 1) + c;
+    parallel_rows(dh, (long)dw, [&](int y0, int y1) {
+        for (int y = y0; y < y1; y++) {
+            const float *s = src.px(std::min((int)std::floor(y * sy), src.height - 1), 0);
+            float *d = plane + (size_t)y * stride_floats;
+            for (int x = 0; x < dw; x++) d[x] = s[xo[(size_t)x]];
+        }
+    });
+}
 
 // cv::resize(src, dst, Size(dw, dh), 0, 0, interp) for CV_32FC3 (src/main.cpp:135,144,166).
 // OpenCV conventions: scale = src/dst (double); nearest: sx = floor(dx*scale); linear/cubic: fx = (dx+0.5)*scale-0.5,
@@ -122,13 +206,14 @@ inline Image3f resize(const Image3f &src, int dw, int dh, Interp interp) {
     Image3f dst(dw, dh);
     const double sx = (double)src.width / dw, sy = (double)src.height / dh;
     if (interp == NEAREST) {
+        std::vector<int> xo((size_t)dw);
+        for (int x = 0; x < dw; x++) xo[(size_t)x] = 3 * std::min((int)std::floor(x * sx), src.width - 1);
         parallel_rows(dh, (long)dw * 3, [&](int y0, int y1) {
             for (int y = y0; y < y1; y++) {
-                int yy = std::min((int)std::floor(y * sy), src.height - 1);
-                for (int x = 0; x < dw; x++) {
-                    int xx = std::min((int)std::floor(x * sx), src.width - 1);
-                    const float *s = src.px(yy, xx);
-                    float *d = dst.px(y, x);
+                const float *srow = src.px(std::min((int)std::floor(y * sy), src.height - 1), 0);
+                float *d = dst.px(y, 0);
+                for (int x = 0; x < dw; x++, d += 3) {
+                    const float *s = srow + xo[(size_t)x];
                     d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
                 }
             }
@@ -160,15 +245,14 @@ inline Image3f resize(const Image3f &src, int dw, int dh, Interp interp) {
     std::vector<int> xi((size_t)dw * ntap);
     std::vector<float> xw((size_t)dw * ntap);
     for (int x = 0; x < dw; x++) coeffs(sx, x, src.width, &xi[(size_t)x * ntap], &xw[(size_t)x * ntap]);
-    std::vector<float> tmp((size_t)src.height * dw * 3);
+    for (auto &v : xi) v *= 3;                                                    // element offsets into an interleaved row
+    FloatBuf tmp((size_t)src.height * dw * 3);
     parallel_rows(src.height, (long)dw * 3 * ntap, [&](int y0, int y1) {
-        for (int y = y0; y < y1; y++)
-            for (int x = 0; x < dw; x++)
-                for (int c = 0; c < 3; c++) {
-                    float acc = 0.f;
-                    for (int k = 0; k < ntap; k++) acc += src.px(y, xi[(size_t)x * ntap + k])[c] * xw[(size_t)x * ntap + k];
-                    tmp[((size_t)y * dw + x) * 3 + c] = acc;
-                }
+        for (int y = y0; y < y1; y++) {
+            float *t = &tmp[(size_t)y * dw * 3];
+            if (ntap == 4) detail::hpass_row<4>(t, src.px(y, 0), xi.data(), xw.data(), dw);
+            else detail::hpass_row<2>(t, src.px(y, 0), xi.data(), xw.data(), dw);
+        }
     });
     // vertical pass
     parallel_rows(dh, (long)dw * 3 * ntap, [&](int y0, int y1) {
@@ -176,12 +260,10 @@ inline Image3f resize(const Image3f &src, int dw, int dh, Interp interp) {
             int yi[4];
             float yw[4];
             coeffs(sy, y, src.height, yi, yw);
-            for (int x = 0; x < dw; x++)
-                for (int c = 0; c < 3; c++) {
-                    float acc = 0.f;
-                    for (int k = 0; k < ntap; k++) acc += tmp[((size_t)yi[k] * dw + x) * 3 + c] * yw[k];
-                    dst.px(y, x)[c] = acc;
-                }
+            const float *rows[4];
+            for (int k = 0; k < ntap; k++) rows[k] = &tmp[(size_t)yi[k] * dw * 3];
+            if (ntap == 4) detail::vpass_row<4>(dst.px(y, 0), rows, yw, (size_t)dw * 3);
+            else detail::vpass_row<2>(dst.px(y, 0), rows, yw, (size_t)dw * 3);
         }
     });
     return dst;

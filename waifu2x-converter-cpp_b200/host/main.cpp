@@ -10,6 +10,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "imageio.hpp"
@@ -115,10 +116,15 @@ struct CmdLine {
     }
 };
 
-w2xc::Plane plane_of(const w2ximg::Image3f &im, int c) {
+w2xc::Plane plane_of(const w2ximg::Image3f &im, int c) {              // cv::split, one channel
     w2xc::Plane p(im.width, im.height);
-    for (int y = 0; y < im.height; y++)
-        for (int x = 0; x < im.width; x++) p.at(y, x) = im.px(y, x)[c];
+    w2ximg::get_channel(im, c, p.data, p.stride_bytes / 4);
+    return p;
+}
+// channel c of cv::resize(im, Size(dw, dh), 0, 0, INTER_NEAREST) (src/main.cpp:135-139: resize, then split, then only [0] is used)
+w2xc::Plane plane_of_nearest(const w2ximg::Image3f &im, int c, int dw, int dh) {
+    w2xc::Plane p(dw, dh);
+    w2ximg::resize_nearest_channel(im, c, dw, dh, p.data, p.stride_bytes / 4);
     return p;
 }
 
@@ -138,6 +144,13 @@ int main(int argc, char **argv) {
     cmd.add("", "gpus", "number of GPUs the conversion is spread over", false, "1", "integer").hidden = true;
     cmd.parse(argc, argv);
     if (std::atoi(cmd.get("gpus").c_str()) > 1) w2xc::gpuRuntime::setNumberOfGpus(std::atoi(cmd.get("gpus").c_str()));
+    // CUDA context creation (~0.2 s) overlaps image decoding, colour conversion and model parsing; joined before the first conversion
+    std::thread gpu_warmup([] { w2xc::gpuRuntime::warmup(); });
+    // every way out of main below joins it first: std::exit runs the static destructors, and the runtime must not still be under construction
+    auto leave = [&](int code) {
+        if (gpu_warmup.joinable()) gpu_warmup.join();
+        std::exit(code);
+    };
     const bool timing = std::getenv("W2X_CLI_TIMING") != nullptr;   // stage times (ms) as one JSON line on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
@@ -152,7 +165,7 @@ int main(int argc, char **argv) {
     w2xio::Image8 in8 = w2xio::imread(inputFile, &ioerr);
     if (in8.empty()) {
         std::cerr << "Error : couldn't read image " << inputFile << " (" << ioerr << ")" << std::endl;
-        std::exit(-1);
+        leave(-1);
     }
     const double t_read = now();
     w2ximg::Image3f image = w2ximg::from_u8(in8.bgr.data(), in8.width, in8.height);
@@ -165,13 +178,14 @@ int main(int argc, char **argv) {
     if (mode == "noise" || mode == "noise_scale") {
         std::string modelFileName = modelDir + "/noise" + std::to_string(nrLevel) + "_model.json";
         std::vector<std::unique_ptr<w2xc::Model>> models;
-        if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) std::exit(-1);
+        if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) leave(-1);
         w2xc::Plane imageY = plane_of(image, 0), out;
+        if (gpu_warmup.joinable()) gpu_warmup.join();
         const double t0 = now();
         // The reference ignores the return value here (:96) because a failing layer has already ended the process inside
         // convertWithModelsBasic (src/convertRoutine.cpp:69: std::exit(-1)).  The library never exits, so the same outcome
         // is produced here: no device, out of memory or a CUDA error must not write the un-denoised image with exit code 0.
-        if (!w2xc::convertWithModels(imageY, out, models) || out.empty()) std::exit(-1);
+        if (!w2xc::convertWithModels(imageY, out, models) || out.empty()) leave(-1);
         t_conv += now() - t0;
         w2ximg::set_channel(image, 0, out.data, out.stride_bytes / 4);
     }
@@ -184,18 +198,18 @@ int main(int argc, char **argv) {
             shrinkRatio = scaleRatio / std::pow(2.0, static_cast<double>(iterTimesTwiceScaling));
         std::string modelFileName = modelDir + "/scale2.0x_model.json";
         std::vector<std::unique_ptr<w2xc::Model>> models;
-        if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) std::exit(-1);
+        if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) leave(-1);
         std::cout << "start scaling" << std::endl;
         for (int nIteration = 0; nIteration < iterTimesTwiceScaling; nIteration++) {
             std::cout << "#" << std::to_string(nIteration + 1) << " 2x scaling..." << std::endl;
             const int w2 = image.width * 2, h2 = image.height * 2;
-            w2ximg::Image3f nearest = w2ximg::resize(image, w2, h2, w2ximg::NEAREST);    // :135
-            w2xc::Plane imageY = plane_of(nearest, 0), out;
+            w2xc::Plane imageY = plane_of_nearest(image, 0, w2, h2), out;                 // :135-139 (only the Y plane of the nearest image is used)
             w2ximg::Image3f bicubic = w2ximg::resize(image, w2, h2, w2ximg::CUBIC);      // :144
+            if (gpu_warmup.joinable()) gpu_warmup.join();
             const double t0 = now();
             if (!w2xc::convertWithModels(imageY, out, models)) {
                 std::cerr << "w2xc::convertWithModels : something error has occured.\nstop." << std::endl;
-                std::exit(1);
+                leave(1);
             }
             t_conv += now() - t0;
             w2ximg::set_channel(bicubic, 0, out.data, out.stride_bytes / 4);              // merge, :154
@@ -223,12 +237,18 @@ int main(int argc, char **argv) {
     const double t_write0 = now();
     if (!w2xio::imwrite(outputFileName, out8.data(), image.width, image.height)) {
         std::cerr << "Error : couldn't write " << outputFileName << std::endl;
-        std::exit(-1);
+        leave(-1);
     }
     if (timing)
         std::cerr << "{\"w2x_cli_timing_ms\": {\"imread\": " << t_read - t_start << ", \"convertWithModels\": " << t_conv
                   << ", \"colour_resize_plumbing\": " << (t_write0 - t_read) - t_conv << ", \"imwrite\": " << now() - t_write0
                   << ", \"total\": " << now() - t_start << "}}" << std::endl;
     std::cout << "process successfully done!" << std::endl;
+    if (gpu_warmup.joinable()) gpu_warmup.join();
+    if (!std::getenv("W2X_CLI_FULL_TEARDOWN")) {   // the file is written and closed: skip the CUDA context / page-locked memory teardown (~0.1 s)
+        std::cout.flush();
+        std::cerr.flush();
+        std::_Exit(0);
+    }
     return 0;
 }

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -76,7 +77,17 @@ public:
         requested() = n;
         return true;
     }
-    static w2x_ctx *context() { return instance().ctx_; }
+    // nullptr if the runtime could not be created; the reason is printed ONCE, by the first caller that needs the context (not by
+    // whichever thread happened to construct the runtime: a front end may create it in the background, see host/main.cpp)
+    static w2x_ctx *context() {
+        gpuRuntime &rt = instance();
+        if (!rt.ctx_ && !rt.error_.empty()) {
+            static std::once_flag once;
+            std::call_once(once, [&] { std::cerr << ("Error : " + rt.error_ + "\n") << std::flush; });
+        }
+        return rt.ctx_;
+    }
+    static void warmup() { (void)instance(); }                // create the runtime (CUDA context) now, silently
     static w2x_multi *multi() { return instance().multi_; }   // nullptr with one GPU
 private:
     static int &requested() { static int n = 0; return n; }
@@ -84,6 +95,7 @@ private:
     static gpuRuntime &instance() { static gpuRuntime rt; return rt; }
     w2x_ctx *ctx_ = nullptr;
     w2x_multi *multi_ = nullptr;
+    std::string error_;
     gpuRuntime() {
         created() = true;
         const char *dev = std::getenv("W2X_DEVICE"), *ng = std::getenv("W2X_GPUS");
@@ -93,13 +105,13 @@ private:
             std::vector<int> ids;
             for (int i = 0; i < n; i++) ids.push_back(first + i);
             if (w2x_multi_create(ids.data(), n, &multi_) != W2X_OK) {
-                std::cerr << "Error : " << w2x_last_error() << std::endl;
+                error_ = w2x_last_error();
                 multi_ = nullptr;
                 return;
             }
             ctx_ = w2x_multi_ctx(multi_, 0);
         } else if (w2x_ctx_create(first, &ctx_) != W2X_OK) {
-            std::cerr << "Error : " << w2x_last_error() << std::endl;
+            error_ = w2x_last_error();
             ctx_ = nullptr;
         }
     }
