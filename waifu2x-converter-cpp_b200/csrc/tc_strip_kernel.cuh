@@ -22,6 +22,10 @@
 // 128-pixel column (130/128 L2->SMEM amplification instead of 1.27x), all weights stay resident in shared memory
 // (36..144 KB), the frame is walked in units of `seg_rows` rows x 128 columns, static round-robin over the CTAs.
 //
+// Warps: 0 = activation producer (TMA), 1 = MMA issuer (software-pipelined: the next strip's plan, tc_strip_plan.h, is computed
+// between the current strip's tap groups), 2 = weights + TMEM owner, 4.. = one or two epilogue sets (alternate output rows).
+// The 64 -> 64 shape, whose bound was the shared-memory pipe, stores its records straight from registers (StripCfg::DIRECT).
+//
 // Every output element still sees the same operations in the same order whatever the unit/strip geometry:
 //   for ky (= strips r-1, r, r+1): for 32-channel chunk c: for kx: [xh*wh k0, xh*wh k1, corrections]
 // so block-split, whole-plane, banded and multi-GPU runs stay bit-identical to each other.
