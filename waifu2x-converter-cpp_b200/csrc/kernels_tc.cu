@@ -47,6 +47,7 @@ namespace tc {
 
 #include "tc_ptx.cuh"
 #include "tc_config.cuh"
+#include "tc_issue.cuh"
 #include "tc_epilogue.cuh"
 #include "tc_kernel.cuh"
 #include "tc_pair_kernel.cuh"

@@ -1,6 +1,6 @@
 // tc_epilogue.cuh -- the epilogue store: accumulator block -> frame planes -> swizzled staging tile -> TMA store
 // Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
-//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_edge_kernels.cuh
+//   tc_ptx.cuh, tc_config.cuh, tc_issue.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
 // (pure code organisation: the generated SASS is the same as with one file).
 
 // Epilogue store of 32 activated output channels of ONE pixel per thread (lane = pixel inside this warp's 32-pixel block:

@@ -1,6 +1,6 @@
 // tc_kernel.cuh -- tc_conv3x3_kernel: the single-CTA layer kernel (warp roles, pipelines)
 // Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
-//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_edge_kernels.cuh
+//   tc_ptx.cuh, tc_config.cuh, tc_issue.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
 // (pure code organisation: the generated SASS is the same as with one file).
 
 // ================================================================================================
@@ -156,10 +156,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                         if constexpr (C::MERGE) {
                             // one stage = [wh fp16 | wh8 | wl8]: main product (two K=16 steps) + both e4m3 corrections (K=32 each)
                             acquire_b(b0);
-                            umma_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
-                            umma_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
-                            umma_f8(dj, desc(A_HI32, ah + 6u), desc(B8_HI32, b0 + (COUT * 64u >> 4)), idesc_c, 1u);    // xl8 * wh8
-                            umma_f8(dj, desc(A_HI32, ah + 4u), desc(B8_HI32, b0 + (COUT * 96u >> 4)), idesc_c, 1u);    // xh8 * wl8
+                            issue_tap_f8<false>(dj, ah, b0, COUT, A_HI32, B_HI32, B8_HI32, idesc_c, acc0);
                             release_b();
                         } else if constexpr (C::STACK) {
                             // one stage = [wh ; wl]: xh*[wh;wl] (N = 2*Cout, D1|D2) then xl*wh (N = Cout, D1)
@@ -185,7 +182,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
                         }
                     }
                     // next tap: kx+1, or the next halo row
-                    tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
+                    tap_off += tap_step<C::ROWB>(t);
                 }
                 umma_commit_one(a_empty(slot));   // the staged boxes may be overwritten once these MMAs retire
             }

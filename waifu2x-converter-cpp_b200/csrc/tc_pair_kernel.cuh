@@ -1,6 +1,6 @@
 // tc_pair_kernel.cuh -- tc_conv3x3_pair_kernel: the cta_group::2 variant for the 128-wide layers
 // Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
-//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_edge_kernels.cuh
+//   tc_ptx.cuh, tc_config.cuh, tc_issue.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
 // (pure code organisation: the generated SASS is the same as with one file).
 
 // ================================================================================================
@@ -179,10 +179,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                             uint32_t b0;
                             acquire_b(b0);                  // one stage per 32-channel step: this CTA's rows of both blocks
                             if constexpr (F8) {
-                                umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
-                                umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
-                                umma2_f8(dj, desc(A_HI32, ah + 6u), desc(B8_HI32, b0 + (4096u >> 4)), idesc_c, 1u);    // xl8 * wh8
-                                umma2_f8(dj, desc(A_HI32, ah + 4u), desc(B8_HI32, b0 + (6144u >> 4)), idesc_c, 1u);    // xh8 * wl8
+                                issue_tap_f8<true>(dj, ah, b0, COUT / 2, A_HI32, B_HI32, B8_HI32, idesc_c, acc0);   // this CTA holds half of the B rows
                             } else {
                                 umma2_f16(dj, desc(A_HI32, ah), desc(B_HI32, b0), idesc_c, acc0);
                                 umma2_f16(dj, desc(A_HI32, ah + 2u), desc(B_HI32, b0 + 2u), idesc_c, 1u);
@@ -193,7 +190,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid
                             }
                             release_b();
                         }
-                        tap_off += (t % 3 == 2) ? ((HALO - 2) * C::ROWB >> 4) : (C::ROWB >> 4);
+                        tap_off += tap_step<C::ROWB>(t);
                     }
                     umma2_commit_one(a_empty(slot));
                 }

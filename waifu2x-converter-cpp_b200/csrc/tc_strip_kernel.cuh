@@ -1,7 +1,7 @@
 // tc_strip_kernel.cuh -- tc_conv3x3_strip_kernel: the narrow layers (Cin, Cout <= 64) as row strips with the three ky taps
 // stacked along N
 // Part of the tcgen05 engine's single translation unit: included by kernels_tc.cu inside namespace w2x::tc, in this order:
-//   tc_ptx.cuh, tc_config.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
+//   tc_ptx.cuh, tc_config.cuh, tc_issue.cuh, tc_epilogue.cuh, tc_kernel.cuh, tc_pair_kernel.cuh, tc_strip_kernel.cuh, tc_edge_kernels.cuh
 //
 // Why: an M128 x N x K16 tcgen05.mma fetches (128 + N) operand rows of 32 B from shared memory at 128 B/clk whatever N is
 // (profiles/r01_umma_microbench.txt), while its math takes N/2 clocks.  With N = Cout = 32 / 64 the fetch (40 / 48 clk)
