@@ -37,6 +37,13 @@ def test_batched_tiles_equal_plane_by_plane(w2x, models, oracle_mod, engine, pre
         # a scratch limit smaller than the batch: processed in groups, same bits
         ctx.set_scratch_limit(128 * (96 + 14) * (80 + 14) * 4 * 2)
         assert np.array_equal(ctx.convert_tiles(models["noise2"], tiles), batch)
+        # eight tiles and more run as copy-pipelined groups (uploads / layers / downloads overlap): same bits per tile, twice in a row
+        many = np.stack([oracle_mod.seeded_plane(64, 48, 300 + t, "uniform") for t in range(11)])
+        ctx.set_scratch_limit(1 << 34)
+        piped = ctx.convert_tiles(models["noise2"], many)
+        for t in range(11):
+            assert np.array_equal(piped[t], ctx.convert_plane(models["noise2"], many[t], block_splitting=False)), t
+        assert np.array_equal(ctx.convert_tiles(models["noise2"], many), piped)
     finally:
         ctx.close()
 

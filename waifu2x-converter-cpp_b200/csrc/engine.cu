@@ -875,9 +875,53 @@ int w2x_convert_tiles_async(w2x_ctx *ctx, const w2x_model *model, const float *c
 
 int w2x_convert_tiles(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles, float *const *out_tiles, int n_tiles,
                       int width, int height, size_t in_stride_bytes, size_t out_stride_bytes) {
-    int rc = w2x_convert_tiles_async(ctx, model, in_tiles, out_tiles, n_tiles, width, height, in_stride_bytes, out_stride_bytes);
-    int rc2 = ctx ? w2x_ctx_synchronize(ctx) : W2X_OK;
-    return rc ? rc : rc2;
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    // Larger batches run as up to four groups: the uploads of group g+1 and the downloads of group g-1 overlap the layers of
+    // group g (copy engines + compute), as the row bands of w2x_convert_plane do.  Tiles are independent, so the grouping
+    // does not change a bit of any of them.
+    const int groups = n_tiles >= 8 ? std::min(4, n_tiles / 4) : 1;
+    if (groups < 2) {
+        int rc = w2x_convert_tiles_async(ctx, model, in_tiles, out_tiles, n_tiles, width, height, in_stride_bytes, out_stride_bytes);
+        int rc2 = w2x_ctx_synchronize(ctx);
+        return rc ? rc : rc2;
+    }
+    if (!in_tiles || !out_tiles || width < 1 || height < 1) return fail(W2X_ERR_ARG, "w2x_convert_tiles: bad argument");
+    if (in_stride_bytes < (size_t)width * 4 || out_stride_bytes < (size_t)width * 4)
+        return fail(W2X_ERR_ARG, "w2x_convert_tiles: row stride smaller than a row");
+    for (int t = 0; t < n_tiles; t++)
+        if (!in_tiles[t] || !out_tiles[t]) return fail(W2X_ERR_ARG, "w2x_convert_tiles: NULL tile %d", t);
+    DeviceGuard g(ctx->device);
+    const size_t tile_px = (size_t)width * height, tile_bytes = tile_px * sizeof(float);
+    for (int i = 0; i < 2; i++) {
+        int rc = ensure(reinterpret_cast<void **>(&ctx->io_buf[i]), &ctx->io_bytes[i], tile_bytes * (size_t)n_tiles);
+        if (rc) return rc;
+    }
+    auto first = [&](int gi) { return (int)((long)n_tiles * gi / groups); };
+    for (int gi = 0; gi < groups; gi++) {
+        for (int t = first(gi); t < first(gi + 1); t++)
+            CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0] + tile_px * (size_t)t, (size_t)width * 4, in_tiles[t], in_stride_bytes, (size_t)width * 4,
+                                       (size_t)height, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU_CHECK(cudaEventRecord(ctx->ev_in[gi], ctx->copy_in));
+    }
+    for (int gi = 0; gi < groups; gi++) {
+        const int t0 = first(gi), nt = first(gi + 1) - t0;
+        CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[gi], 0));
+        int rc = convert_tiles_dev(ctx, model, ctx->io_buf[0] + tile_px * (size_t)t0, ctx->io_buf[1] + tile_px * (size_t)t0, nt, width, height);
+        if (rc) {   // copies already queued still touch the caller's buffers and the staging: drain them first
+            cudaStreamSynchronize(ctx->copy_in);
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->copy_out);
+            return rc;
+        }
+        CU_CHECK(cudaEventRecord(ctx->ev_done[gi], ctx->stream));
+        CU_CHECK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[gi], 0));
+        for (int t = t0; t < t0 + nt; t++)
+            CU_CHECK(cudaMemcpy2DAsync(out_tiles[t], out_stride_bytes, ctx->io_buf[1] + tile_px * (size_t)t, (size_t)width * 4, (size_t)width * 4,
+                                       (size_t)height, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CU_CHECK(cudaStreamSynchronize(ctx->copy_out));
+    CU_CHECK(cudaStreamSynchronize(ctx->stream));
+    return W2X_OK;
 }
 
 }  // extern "C"
