@@ -246,7 +246,8 @@ W2X_API int w2x_slab_synchronize(w2x_slab *slab);
 /* ---- independent planes of one shape in one pass ---------------------------------------------- */
 /* The reference's block loop (src/convertRoutine.cpp:114-165) and BASELINE config 5 (64 x 512x512 tiles):
  * n_tiles planes, each converted exactly like w2x_convert_plane(block_splitting = 0) would -- bit-identical --
- * but stacked into ONE frame so that every layer is one launch for the whole batch.  HOST pointers. */
+ * but stacked into ONE frame so that every layer is one launch for the whole batch.  HOST pointers; batches of
+ * eight tiles and more are cut into up to four such frames so that uploads, layers and downloads overlap. */
 W2X_API int w2x_convert_tiles(w2x_ctx *ctx, const w2x_model *model, const float *const *in_tiles,
                               float *const *out_tiles, int n_tiles, int width, int height,
                               size_t in_stride_bytes, size_t out_stride_bytes);
