@@ -631,14 +631,15 @@ int w2x_convert_plane(w2x_ctx *ctx, const w2x_model *model, const float *in, int
     std::vector<int> r0((size_t)nb + 1);
     for (int i = 0; i <= nb; i++) r0[(size_t)i] = (int)((long)height * i / nb);
     for (int i = 0; i < nb; i++) {
-        const int y = r0[(size_t)i], rows = r0[(size_t)i + 1] - y;
+        // upload i carries band i plus the n rows of context band i needs from band i+1, so that band i waits for ITS upload only
+        const int y = i == 0 ? 0 : r0[(size_t)i] + n_model, y_end = i + 1 < nb ? r0[(size_t)i + 1] + n_model : height;
         CU_CHECK(cudaMemcpy2DAsync(ctx->io_buf[0] + (size_t)y * width, (size_t)width * 4, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes,
-                                   in_stride_bytes, (size_t)width * 4, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_in));
+                                   in_stride_bytes, (size_t)width * 4, (size_t)(y_end - y), cudaMemcpyHostToDevice, ctx->copy_in));
         CU_CHECK(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
     }
     for (int i = 0; i < nb; i++) {
         const int y = r0[(size_t)i], rows = r0[(size_t)i + 1] - y;
-        CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[std::min(i + 1, nb - 1)], 0));   // needs the first rows of the next band
+        CU_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[i], 0));
         const int above = i > 0 ? n_model : 0, below = i + 1 < nb ? n_model : 0;
         int rc = convert_device(ctx, model, ctx->io_buf[0] + (size_t)y * width, width, rows, (size_t)width * 4, above, below,
                                 ctx->io_buf[1] + (size_t)y * width, (size_t)width * 4, 0);

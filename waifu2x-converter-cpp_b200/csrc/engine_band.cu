@@ -492,15 +492,21 @@ int slab_enqueue_compute(w2x_slab *s, const float *in, size_t in_stride_bytes) {
     auto at = [&](int t) { return s->order ? K - 1 - t : t; };      // t-th sub-band in processing order
     CU_CHECK(cudaStreamWaitEvent(ctx->copy_in, s->ev_done[(size_t)at(K - 1)], 0));   // the previous pass has finished reading d_in
     CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_drained, 0));                    // ... and its downloads have left d_out
+    // Upload t carries the t-th sub-band's rows shifted by n towards the sub-band processed next: its own rows minus the n the previous
+    // upload already brought, plus the n rows of overlap context it reads from the next one -- so a sub-band waits for ITS upload only.
+    const int n = (int)s->model->layers.size();
     for (int t = 0; t < K; t++) {
-        const int i = at(t), y = s->r0[(size_t)i], rows = s->r0[(size_t)i + 1] - y;
-        CU_CHECK(cudaMemcpy2DAsync(s->d_in + (size_t)y * s->width, rowb, reinterpret_cast<const char *>(in) + (size_t)y * in_stride_bytes, in_stride_bytes, rowb,
-                                   (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_in));
+        const int i = at(t);
+        int ya, yb;
+        if (!s->order) { ya = s->r0[(size_t)i] + (t == 0 ? 0 : n); yb = s->r0[(size_t)i + 1] + (t == K - 1 ? 0 : n); }
+        else { ya = s->r0[(size_t)i] - (t == K - 1 ? 0 : n); yb = s->r0[(size_t)i + 1] - (t == 0 ? 0 : n); }
+        CU_CHECK(cudaMemcpy2DAsync(s->d_in + (size_t)ya * s->width, rowb, reinterpret_cast<const char *>(in) + (size_t)ya * in_stride_bytes, in_stride_bytes, rowb,
+                                   (size_t)(yb - ya), cudaMemcpyHostToDevice, ctx->copy_in));
         CU_CHECK(cudaEventRecord(s->ev_in[(size_t)i], ctx->copy_in));
     }
     for (int t = 0; t < K; t++) {
         const int i = at(t), y = s->r0[(size_t)i];
-        for (int j = std::max(0, i - 1); j <= std::min(K - 1, i + 1); j++) CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_in[(size_t)j], 0));   // own rows + the overlap rows
+        CU_CHECK(cudaStreamWaitEvent(ctx->stream, s->ev_in[(size_t)i], 0));   // own rows + the overlap rows (earlier uploads are ordered before it)
         int rc = w2x_band_run(s->sub[(size_t)i], s->d_in + (size_t)y * s->width, rowb, s->d_out + (size_t)y * s->width, rowb);
         if (rc) {
             cudaStreamSynchronize(ctx->copy_in);
