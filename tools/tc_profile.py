@@ -33,7 +33,7 @@ ctx.debug_tc_profile_enable(True)
 ctx.convert_plane(m, x)
 times = ctx.layer_times()
 print(f"per-layer ms with counters:", [round(t[0], 3) for t in times])
-print("layer  ms     cyc/tileset  mma_wait_acc  mma_wait_a  mma_wait_b  issue+other | aprod_wait bprod_wait | epi_wait epi_work  (cycles per tile-set, per-CTA average)")
+print("layer  ms     cyc/unit     mma_wait_acc  mma_wait_a  mma_wait_b  issue+other | aprod_wait bprod_wait | epi_wait epi_work  (cycles per unit = 128-pixel strip on L1-L3, pair of 16x16 tile-sets on L4-L5; per-CTA average)")
 for li in range(1, 6):
     d = ctx.debug_tc_profile_read(li)
     n = max(d["tilesets"], 1)
