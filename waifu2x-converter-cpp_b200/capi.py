@@ -150,6 +150,7 @@ def lib():
     L.w2x_debug_set_host_bands.argtypes = [vp, ci]
     L.w2x_debug_set_pair.argtypes = [vp, ci]
     L.w2x_debug_set_fuse_last.argtypes = [vp, ci]
+    L.w2x_debug_set_num_sms.argtypes = [vp, ci]
     L.w2x_debug_tc_pack8.argtypes = [vp, ci, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(cs)]
     L.w2x_debug_tc_strip.argtypes = [vp, ci, ci, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(cs)]
     L.w2x_debug_set_strip.argtypes = [vp, ci]
@@ -301,6 +302,7 @@ class Context:
     def debug_set_strip(self, on): _check(lib().w2x_debug_set_strip(self._h, int(on)))
     def debug_set_host_bands(self, n): _check(lib().w2x_debug_set_host_bands(self._h, n))
     def debug_set_fuse_last(self, on): _check(lib().w2x_debug_set_fuse_last(self._h, int(on)))
+    def debug_set_num_sms(self, n): _check(lib().w2x_debug_set_num_sms(self._h, int(n)))
     def debug_tc_profile_enable(self, on=True): _check(lib().w2x_debug_tc_profile_enable(self._h, int(on)))
 
     def debug_tc_profile_read(self, layer):

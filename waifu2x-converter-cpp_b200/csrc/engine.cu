@@ -562,6 +562,15 @@ W2X_API int w2x_debug_set_strip(w2x_ctx *ctx, int on) {
     return W2X_OK;
 }
 
+// Probe switch (not part of the stable ABI): number of SMs the persistent tcgen05 kernels of this context occupy (0 = all).
+W2X_API int w2x_debug_set_num_sms(w2x_ctx *ctx, int n) {
+    if (check_ctx(ctx)) return W2X_ERR_ARG;
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->num_sms = n > 0 && n < prop.multiProcessorCount ? n : prop.multiProcessorCount;
+    return W2X_OK;
+}
+
 // Probe switch (not part of the stable ABI): number of host-copy pipeline bands of w2x_convert_plane (0 auto, 1 off).
 W2X_API int w2x_debug_set_host_bands(w2x_ctx *ctx, int bands) {
     if (check_ctx(ctx)) return W2X_ERR_ARG;
