@@ -137,3 +137,57 @@ def test_default_precision_on_adversarial_planes_stays_inside_the_gate(oracle_mo
         worst[label] = err / scale
         assert err <= 6e-5 * scale, (name, label, err)
     print(name, {k: f"{v:.1e}" for k, v in worst.items()})
+
+
+def test_winograd_f2x2_3x3_in_the_split_arithmetic_would_stay_inside_the_gate(oracle_mod, oracle_models, ncpu):
+    """What comes next: the tensor-bound layers are bound by energy, and Winograd F(2x2,3x3) needs
+    16/36 of the direct convolution's multiply-adds.  Emulated here with the SAME operand split (fp16 main product + two e4m3
+    correction products, fp32 accumulation) applied to the transformed operands V = B^T d B (fp32 transform of the x16
+    activations) and U = G g G^T, on the three widest layers: the error against the reference stays where the direct form's
+    is (2e-5 on white noise), far inside the 1e-4 gate -- the obstacle is TMEM capacity (16 live accumulators per output
+    tile), not numerics."""
+    import torch
+    import torch.nn.functional as F
+    A, Cc = 10, 1
+    e4m3 = lambda t: t.to(torch.float8_e4m3fn).to(torch.float64)
+    Bt = torch.tensor([[1, 0, -1, 0], [0, 1, 1, 0], [0, -1, 1, 0], [0, 1, 0, -1]], dtype=torch.float64)
+    G = torch.tensor([[1, 0, 0], [.5, .5, .5], [.5, -.5, .5], [0, 0, 1]], dtype=torch.float64)
+    At = torch.tensor([[1, 1, 1, 0], [0, 1, -1, -1]], dtype=torch.float64)
+
+    def split_mm(V, U):     # [P, Cin] x [Cout, Cin]^T in the GPU's arithmetic
+        Vh, Uh = V.float().half().double(), U.float().half().double()
+        return Vh @ Uh.T + e4m3((V - Vh) * 2.0 ** A) @ e4m3(Uh * 2.0 ** -A).T + e4m3(Vh * 2.0 ** -Cc) @ e4m3((U - Uh) * 2.0 ** Cc).T
+
+    def conv_direct(xs, w):
+        wh, xh = w.float().half().double(), xs.float().half().double()
+        return (F.conv2d(xh, wh, padding=1) + F.conv2d(e4m3((xs - xh) * 2.0 ** A), e4m3(wh * 2.0 ** -A), padding=1) +
+                F.conv2d(e4m3(xh * 2.0 ** -Cc), e4m3((w - wh) * 2.0 ** Cc), padding=1))
+
+    def conv_winograd(xs, w):
+        _, C, H, W = xs.shape
+        Co, th, tw = w.shape[0], (H + 1) // 2, (W + 1) // 2
+        tiles = F.pad(xs, (1, 1 + (W % 2), 1, 1 + (H % 2))).unfold(2, 4, 2).unfold(3, 4, 2)          # [1, C, th, tw, 4, 4]
+        V = torch.einsum('ij,bcthjk,lk->bcthil', Bt, tiles, Bt).float().double()[0].permute(1, 2, 0, 3, 4).reshape(th * tw, C, 4, 4)
+        U = torch.einsum('ij,ocjk,lk->ocil', G, w.double(), G).float().double()
+        M = torch.stack([torch.stack([split_mm(V[:, :, i, j], U[:, :, i, j]).float().double() for j in range(4)], -1) for i in range(4)], -2)
+        Y = torch.einsum('ij,pojk,lk->poil', At, M, At).float().double()
+        return Y.reshape(th, tw, Co, 2, 2).permute(2, 0, 3, 1, 4).reshape(Co, th * 2, tw * 2)[None, :, :H, :W]
+
+    om = oracle_models["scale2.0x"]
+    x = oracle_mod.seeded_plane(48, 40, 4, "uniform")
+    ref = om.convert(x, n_job=ncpu)
+    n = len(om)
+    errs = {}
+    for label, wino in (("direct", ()), ("winograd on L3-L5", (3, 4, 5))):
+        act = torch.from_numpy(np.pad(x, n, mode="edge"))[None, None]
+        act = T.leaky(F.conv2d(F.pad(act, (1, 1, 1, 1), mode="replicate"), torch.from_numpy(om.weights[0])) +
+                      torch.from_numpy(om.biases[0].astype(np.float32))[None, :, None, None])
+        for li in range(1, n - 1):
+            ws = T.wscale_of(om.weights[li])
+            w, xs = (torch.from_numpy(om.weights[li]) * ws).double(), (act * 16.0).double()
+            acc = conv_winograd(xs, w) if li in wino else conv_direct(xs, w)
+            act = T.leaky(acc.float() * np.float32(1 / (ws * 16.0)) + torch.from_numpy(om.biases[li].astype(np.float32))[None, :, None, None])
+        out = T.leaky(F.conv2d(act, torch.from_numpy(om.weights[-1]), padding=1) + np.float32(om.biases[-1][0]))[0, 0, n:-n, n:-n].numpy()
+        errs[label] = float(np.abs(out - ref).max())
+    print(errs)
+    assert errs["direct"] <= 4e-5 and errs["winograd on L3-L5"] <= 4e-5, errs
