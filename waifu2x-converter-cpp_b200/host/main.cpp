@@ -154,7 +154,12 @@ int main(int argc, char **argv) {
     const bool timing = std::getenv("W2X_CLI_TIMING") != nullptr;   // stage times (ms) as one JSON line on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
-    double t_conv = 0.0;
+    double t_conv = 0.0, t_ctx_wait = 0.0;
+    auto wait_for_gpu = [&] {                      // the part of the CUDA context creation the host work before it did not hide
+        const double t0 = now();
+        if (gpu_warmup.joinable()) gpu_warmup.join();
+        t_ctx_wait += now() - t0;
+    };
 
     const std::string mode = cmd.get("mode"), inputFile = cmd.get("input_file"), modelDir = cmd.get("model_dir");
     const int nrLevel = std::atoi(cmd.get("noise_level").c_str());
@@ -180,7 +185,7 @@ int main(int argc, char **argv) {
         std::vector<std::unique_ptr<w2xc::Model>> models;
         if (!w2xc::modelUtility::generateModelFromJSON(modelFileName, models)) leave(-1);
         w2xc::Plane imageY = plane_of(image, 0), out;
-        if (gpu_warmup.joinable()) gpu_warmup.join();
+        wait_for_gpu();
         const double t0 = now();
         // The reference ignores the return value here (:96) because a failing layer has already ended the process inside
         // convertWithModelsBasic (src/convertRoutine.cpp:69: std::exit(-1)).  The library never exits, so the same outcome
@@ -205,7 +210,7 @@ int main(int argc, char **argv) {
             const int w2 = image.width * 2, h2 = image.height * 2;
             w2xc::Plane imageY = plane_of_nearest(image, 0, w2, h2), out;                 // :135-139 (only the Y plane of the nearest image is used)
             w2ximg::Image3f bicubic = w2ximg::resize(image, w2, h2, w2ximg::CUBIC);      // :144
-            if (gpu_warmup.joinable()) gpu_warmup.join();
+            wait_for_gpu();
             const double t0 = now();
             if (!w2xc::convertWithModels(imageY, out, models)) {
                 std::cerr << "w2xc::convertWithModels : something error has occured.\nstop." << std::endl;
@@ -241,7 +246,8 @@ int main(int argc, char **argv) {
     }
     if (timing)
         std::cerr << "{\"w2x_cli_timing_ms\": {\"imread\": " << t_read - t_start << ", \"convertWithModels\": " << t_conv
-                  << ", \"colour_resize_plumbing\": " << (t_write0 - t_read) - t_conv << ", \"imwrite\": " << now() - t_write0
+                  << ", \"cuda_context_wait\": " << t_ctx_wait << ", \"colour_resize_plumbing\": " << (t_write0 - t_read) - t_conv - t_ctx_wait
+                  << ", \"imwrite\": " << now() - t_write0
                   << ", \"total\": " << now() - t_start << "}}" << std::endl;
     std::cout << "process successfully done!" << std::endl;
     if (gpu_warmup.joinable()) gpu_warmup.join();
