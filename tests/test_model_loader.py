@@ -76,6 +76,20 @@ def test_loader_error_paths(w2x, tmp_path):
     short = dict(ok, bias=[0])
     expect(4, json.dumps([short]))
     expect(4, json.dumps([dict(ok, weight="x")]))
+    # arrays of bare numbers take the reader's flat fast path: where arrays were expected the diagnostics are still the
+    # element-by-element ones, and a mixed array falls back to the generic path
+    assert "is not an object" in expect(4, "[1, 2, 3]")
+    assert "weight has 3 output planes" in expect(4, json.dumps([dict(ok, weight=[1, 2, 3])]))
+    assert "weight[o] is not an array" in expect(4, json.dumps([dict(ok, weight=[1, 2])]))
+    assert "kernel matrix has too few rows" in expect(4, json.dumps([dict(ok, weight=[[7], [7]])]))
+    assert "kernel row has too few columns" in expect(4, json.dumps([dict(ok, weight=[[[1, 2, 3]], [[1, 2, 3]]])]))
+    assert "kernel row has too few columns" in expect(4, json.dumps([dict(ok, weight=[[[[0, 0], [0, 0, 0], [0, 0, 0]]]] * 2)]))
+    assert "non-numeric weight" in expect(4, json.dumps([dict(ok, weight=[[[[0, "a", 0], [0, 0, 0], [0, 0, 0]]]] * 2)]))
+    assert "non-numeric bias" in expect(4, json.dumps([dict(ok, bias=[0, None])]))
+    assert "PicoJSON Error" in expect(3, "[{\"nInputPlane\": 1, \"bias\": [1, 2e+, 3]}]")          # malformed number inside a numeric array
+    mixed = dict(ok, weight=[[[[0, 1.5e-3, -2], [0, 0, 0], [0, 0, 0, "extra columns are ignored"]]]] * 2)
+    m = w2x.Model.load_json(str((tmp_path / "mixed.json").write_text(json.dumps([mixed])) and tmp_path / "mixed.json"))
+    assert m.params(0)[0][0, 0, 0].tolist() == [0.0, float(np.float32(1.5e-3)), -2.0]
 
 
 def test_model_create_from_arrays(w2x, oracle_models):

@@ -108,9 +108,14 @@ struct JVal {
     enum T { Null, Bool, Num, Str, Arr, Obj } t = Null;
     double num = 0;
     bool b = false;
+    bool flat = false;            // Arr whose elements are all numbers: kept in `nums` (a model file is 99.9 % such arrays: kernel rows, biases)
     std::string str;
     std::vector<JVal> arr;
+    std::vector<double> nums;
     std::vector<std::pair<std::string, JVal>> obj;
+    size_t size() const { return flat ? nums.size() : arr.size(); }
+    bool is_num(size_t i) const { return flat || arr[i].t == Num; }
+    double num_at(size_t i) const { return flat ? nums[i] : arr[i].num; }
     const JVal *get(const char *key) const {
         for (auto &kv : obj)
             if (kv.first == key) return &kv.second;
@@ -174,6 +179,16 @@ struct Parser {
         p++;
         return true;
     }
+    // number token at p: the same scan + std::from_chars for every number of the file
+    bool parse_number(double &d) {
+        const char *q = p;
+        if (*q == '-') q++;
+        while (q < end && ((*q >= '0' && *q <= '9') || *q == '.' || *q == 'e' || *q == 'E' || *q == '+' || *q == '-')) q++;
+        auto r = std::from_chars(p, q, d);
+        if (r.ec != std::errc() || r.ptr != q) return false;
+        p = q;
+        return true;
+    }
     bool parse_value(JVal &v, int depth) {
         if (depth > 64) return error("nesting too deep");
         ws();
@@ -184,6 +199,22 @@ struct Parser {
             p++;
             ws();
             if (p < end && *p == ']') { p++; return true; }
+            if (p < end && (*p == '-' || (*p >= '0' && *p <= '9'))) {
+                // fast path: an array of numbers only.  Anything else in it (or a malformed number) rewinds to the generic path
+                // below, which then produces exactly the diagnostics it always did.
+                const char *rewind = p;
+                for (;;) {
+                    double d = 0;
+                    if (p >= end || !(*p == '-' || (*p >= '0' && *p <= '9')) || !parse_number(d)) break;
+                    v.nums.push_back(d);
+                    ws();
+                    if (p < end && *p == ',') { p++; ws(); continue; }
+                    if (p < end && *p == ']') { p++; v.flat = true; return true; }
+                    break;
+                }
+                v.nums.clear();
+                p = rewind;
+            }
             for (;;) {
                 v.arr.emplace_back();
                 if (!parse_value(v.arr.back(), depth + 1)) return false;
@@ -221,15 +252,10 @@ struct Parser {
         if (c == 'f' && end - p >= 5 && !std::strncmp(p, "false", 5)) { v.t = JVal::Bool; v.b = false; p += 5; return true; }
         if (c == 'n' && end - p >= 4 && !std::strncmp(p, "null", 4)) { v.t = JVal::Null; p += 4; return true; }
         if (c == '-' || (c >= '0' && c <= '9')) {
-            const char *q = p;
-            if (*q == '-') q++;
-            while (q < end && ((*q >= '0' && *q <= '9') || *q == '.' || *q == 'e' || *q == 'E' || *q == '+' || *q == '-')) q++;
             double d = 0;
-            auto r = std::from_chars(p, q, d);
-            if (r.ec != std::errc() || r.ptr != q) return error("bad number");
+            if (!parse_number(d)) return error("bad number");
             v.t = JVal::Num;
             v.num = d;
-            p = q;
             return true;
         }
         return error("unexpected character");
@@ -258,6 +284,7 @@ int parse_model_json(const char *path, w2x_model **out) {
     if (root.t != JVal::Arr)
         return fail(W2X_ERR_MODEL, "Error : model file %s : root is not an array of layer objects", path);
     auto m = std::make_unique<w2x_model>();
+    if (root.flat) return fail(W2X_ERR_MODEL, "Error : model layer %zu is not an object", (size_t)0);
     for (size_t li = 0; li < root.arr.size(); li++) {
         const JVal &o = root.arr[li];
         if (o.t != JVal::Obj) return fail(W2X_ERR_MODEL, "Error : model layer %zu is not an object", li);
@@ -275,34 +302,37 @@ int parse_model_json(const char *path, w2x_model **out) {
         if (!w || w->t != JVal::Arr || !b || b->t != JVal::Arr)
             return fail(W2X_ERR_MODEL, "Error : model layer %zu : weight/bias missing or not arrays", li);
         // src/modelHandler.cpp:81-107: iterate weight[o][i], read kernelSize rows x kernelSize cols
-        if ((int)w->arr.size() != L.n_out)
-            return fail(W2X_ERR_MODEL, "Error : model layer %zu : weight has %zu output planes, expected %d", li, w->arr.size(), L.n_out);
+        // (a `flat` array holds numbers where arrays are expected: the diagnostics are the ones the element-by-element walk gives)
+        if ((int)w->size() != L.n_out)
+            return fail(W2X_ERR_MODEL, "Error : model layer %zu : weight has %zu output planes, expected %d", li, w->size(), L.n_out);
+        if (w->flat) return fail(W2X_ERR_MODEL, "Error : model layer %zu : weight[o] is not an array of %d input planes", li, L.n_in);
         L.w.resize((size_t)L.n_out * L.n_in * L.k * L.k);
         size_t idx = 0;
         for (const JVal &wo : w->arr) {
-            if (wo.t != JVal::Arr || (int)wo.arr.size() != L.n_in)
+            if (wo.t != JVal::Arr || (int)wo.size() != L.n_in)
                 return fail(W2X_ERR_MODEL, "Error : model layer %zu : weight[o] is not an array of %d input planes", li, L.n_in);
+            if (wo.flat) return fail(W2X_ERR_MODEL, "Error : model layer %zu : kernel matrix has too few rows", li);
             for (const JVal &wi : wo.arr) {
-                if (wi.t != JVal::Arr || (int)wi.arr.size() < L.k)
+                if (wi.t != JVal::Arr || (int)wi.size() < L.k)
                     return fail(W2X_ERR_MODEL, "Error : model layer %zu : kernel matrix has too few rows", li);
+                if (wi.flat) return fail(W2X_ERR_MODEL, "Error : model layer %zu : kernel row has too few columns", li);
                 for (int r = 0; r < L.k; r++) {
                     const JVal &row = wi.arr[(size_t)r];
-                    if (row.t != JVal::Arr || (int)row.arr.size() < L.k)
+                    if (row.t != JVal::Arr || (int)row.size() < L.k)
                         return fail(W2X_ERR_MODEL, "Error : model layer %zu : kernel row has too few columns", li);
                     for (int c = 0; c < L.k; c++) {
-                        const JVal &e = row.arr[(size_t)c];
-                        if (e.t != JVal::Num) return fail(W2X_ERR_MODEL, "Error : model layer %zu : non-numeric weight", li);
-                        L.w[idx++] = static_cast<float>(e.num);   // double -> float, cpp:96-97
+                        if (!row.is_num((size_t)c)) return fail(W2X_ERR_MODEL, "Error : model layer %zu : non-numeric weight", li);
+                        L.w[idx++] = static_cast<float>(row.num_at((size_t)c));   // double -> float, cpp:96-97
                     }
                 }
             }
         }
-        if ((int)b->arr.size() < L.n_out)
-            return fail(W2X_ERR_MODEL, "Error : model layer %zu : bias has %zu entries, expected %d", li, b->arr.size(), L.n_out);
+        if ((int)b->size() < L.n_out)
+            return fail(W2X_ERR_MODEL, "Error : model layer %zu : bias has %zu entries, expected %d", li, b->size(), L.n_out);
         L.b.resize((size_t)L.n_out);
         for (int i = 0; i < L.n_out; i++) {
-            if (b->arr[(size_t)i].t != JVal::Num) return fail(W2X_ERR_MODEL, "Error : model layer %zu : non-numeric bias", li);
-            L.b[(size_t)i] = b->arr[(size_t)i].num;                // kept double, cpp:109-112
+            if (!b->is_num((size_t)i)) return fail(W2X_ERR_MODEL, "Error : model layer %zu : non-numeric bias", li);
+            L.b[(size_t)i] = b->num_at((size_t)i);                 // kept double, cpp:109-112
         }
         m->layers.push_back(std::move(L));
     }

@@ -163,6 +163,10 @@ int main(int argc, char **argv) {
 
     const std::string mode = cmd.get("mode"), inputFile = cmd.get("input_file"), modelDir = cmd.get("model_dir");
     const int nrLevel = std::atoi(cmd.get("noise_level").c_str());
+    // the model files this run will ask for are read and parsed in the background while the image is decoded (silently: failures are
+    // reported where the reference reports them, by the generateModelFromJSON calls below)
+    if (mode == "noise" || mode == "noise_scale") w2xc::modelUtility::prefetchModelFromJSON(modelDir + "/noise" + std::to_string(nrLevel) + "_model.json");
+    if (mode == "scale" || mode == "noise_scale") w2xc::modelUtility::prefetchModelFromJSON(modelDir + "/scale2.0x_model.json");
     const double scaleRatio = std::strtod(cmd.get("scale_ratio").c_str(), nullptr);
 
     // load image file (src/main.cpp:74-76)

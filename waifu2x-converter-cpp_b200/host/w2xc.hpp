@@ -16,6 +16,8 @@
 #include <cstring>
 #include <iostream>
 #include <memory>
+#include <future>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -197,8 +199,8 @@ public:
     // static bool generateModelFromJSON(const std::string& fileName, std::vector<std::unique_ptr<Model>>& models)
     // (src/modelHandler.cpp:170-197): appends one Model per layer; false + message on failure.
     static bool generateModelFromJSON(const std::string &fileName, std::vector<std::unique_ptr<Model>> &models) {
-        w2x_model *m = nullptr;
-        if (w2x_model_load_json(fileName.c_str(), &m) != W2X_OK) {
+        w2x_model *m = take_prefetched(fileName);
+        if (!m && w2x_model_load_json(fileName.c_str(), &m) != W2X_OK) {
             std::cerr << w2x_last_error() << std::endl;
             return false;
         }
@@ -206,10 +208,45 @@ public:
         for (int i = 0; i < w2x_model_layer_count(m); i++) models.push_back(std::unique_ptr<Model>(new Model(sp, i)));
         return true;
     }
+    // Not in the reference: start reading + parsing a model file on a background thread (a 5.5 MB JSON file costs ~60 ms); a later
+    // generateModelFromJSON(fileName, ...) of the same name takes the result.  Silent: if the background load failed, the
+    // foreground call loads again and reports the failure exactly as it always did.
+    static void prefetchModelFromJSON(const std::string &fileName) {
+        std::lock_guard<std::mutex> lock(prefetch_mutex());
+        if (prefetched().count(fileName)) return;
+        prefetched()[fileName] = std::async(std::launch::async, [fileName]() -> w2x_model * {
+            w2x_model *m = nullptr;
+            return w2x_model_load_json(fileName.c_str(), &m) == W2X_OK ? m : nullptr;
+        });
+    }
     static modelUtility &getInstance() {
         static modelUtility inst;
         return inst;
     }
+
+private:
+    static std::mutex &prefetch_mutex() { static std::mutex mu; return mu; }
+    static std::map<std::string, std::future<w2x_model *>> &prefetched() {
+        struct Holder {
+            std::map<std::string, std::future<w2x_model *>> map;
+            ~Holder() { for (auto &kv : map) if (kv.second.valid()) if (w2x_model *m = kv.second.get()) w2x_model_free(m); }   // never collected
+        };
+        static Holder h;
+        return h.map;
+    }
+    static w2x_model *take_prefetched(const std::string &fileName) {
+        std::future<w2x_model *> f;
+        {
+            std::lock_guard<std::mutex> lock(prefetch_mutex());
+            auto it = prefetched().find(fileName);
+            if (it == prefetched().end()) return nullptr;
+            f = std::move(it->second);
+            prefetched().erase(it);
+        }
+        return f.valid() ? f.get() : nullptr;
+    }
+
+public:
     bool setNumberOfJobs(int setNJob) { return w2x_set_jobs(setNJob) == W2X_OK; }
     int getNumberOfJobs() { return w2x_get_jobs(); }
     bool setBlockSize(int width, int height) { return w2x_set_block_size(width, height) == W2X_OK; }
